@@ -85,6 +85,105 @@ int sprl_env_rollout(int device, int game, uint64_t seed, uint64_t first_game, i
  * on the device (a pass is a ply; a terminal node above the horizon counts 1). */
 int sprl_env_perft(int device, int game, int depth, uint64_t* count, float* elapsed_ms);
 
+/* ------------------------------------------------------------------ self-play engine
+ * Replaces UCTTree (uct/UCTTree.hpp:38-210), selfPlay / runIteration
+ * (selfplay/SelfPlay.hpp:50-248) and the sample embedding + .npy dump of runWorker
+ * (selfplay/GridWorker.hpp:143-196) for `num_slots` concurrent games on one GPU. */
+typedef struct sprl_engine sprl_engine;
+
+typedef struct {
+    int device;             /* CUDA device ordinal */
+    int game;               /* SPRL_GAME_* */
+    int evaluator;          /* SPRL_EVAL_* */
+    uint64_t seed;          /* run seed of the counter-based streams (constants.hpp:4 SEED) */
+    int num_slots;          /* concurrent games (trees) on the device */
+    int sims;               /* numTraversals per move (OTHWorker.cpp:23 UCT_TRAVERSALS) */
+    int max_batch;          /* maxBatchSize (OTHWorker.cpp:24) */
+    int max_queue;          /* maxQueueSize (OTHWorker.cpp:25) */
+    float dir_eps;          /* OTHWorker.cpp:27 */
+    float dir_alpha;        /* OTHWorker.cpp:28 */
+    float u_weight;         /* constants.hpp:6 U_WEIGHT */
+    int add_noise;          /* Dirichlet noise at the decision node */
+    int use_sym;            /* symmetrizer present: random symmetry per leaf, S-fold samples */
+    int init_q;             /* SPRL_INITQ_* (GridWorker.hpp:141 uses PARENT) */
+    int64_t units_per_tree; /* 16-byte units per tree slab; 0 = derive from sims */
+    int64_t max_games;      /* capacity of the per-game records (games per iteration) */
+    int record_stats;       /* keep per-move root N/W/P for sprl_move_stats (parity tests) */
+    int rounds_per_launch;  /* device evaluators: search rounds per kernel launch; 0 = default */
+} sprl_config;
+
+/* Fills a config with the reference's Othello worker constants (OTHWorker.cpp:12-28,
+ * constants.hpp) for `game`; the caller then overrides what it needs. */
+int sprl_default_config(int game, sprl_config* cfg);
+
+int sprl_create(const sprl_config* cfg, sprl_engine** out);
+void sprl_destroy(sprl_engine* e);
+
+/* All engine work is enqueued on this CUDA stream (a cudaStream_t; NULL = default). */
+int sprl_set_stream(sprl_engine* e, void* cuda_stream);
+
+/* SPRL_EVAL_EXTERNAL: device buffers of the traced network's input and outputs
+ * (networks/GridNetwork.hpp:70,99-102), batch = num_slots * max_queue rows, row
+ * tree*max_queue + q:  d_in [batch, 2H+1, R, C] is WRITTEN by sprl_round;
+ * d_logits [batch, A] and d_value [batch] are READ by the next sprl_round. */
+int sprl_bind_eval_buffers(sprl_engine* e, float* d_in, const float* d_logits, const float* d_value);
+int64_t sprl_eval_batch(const sprl_engine* e);
+
+/* Starts runIteration(num_games): games first_game .. first_game+num_games-1, game g on
+ * stream (seed, g), slot s plays games s, s+num_slots, ... one after the other. */
+int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games);
+
+/* Enqueues one search launch: apply the evaluations of the previous launch, finish
+ * moves whose traversal budget is spent (sample, re-root, compact), then run the next
+ * searchAndGetLeaves batch of every live tree.  Asynchronous, capturable in a CUDA graph. */
+int sprl_round(sprl_engine* e);
+
+/* Synchronises the stream; reports slots still playing and slots stopped by an error. */
+int sprl_poll(sprl_engine* e, int64_t* slots_playing, int64_t* slots_failed);
+
+/* Evaluator callback for sprl_run_iteration with SPRL_EVAL_EXTERNAL: run the network
+ * on d_in (batch rows) and leave its outputs in d_logits / d_value, on `cuda_stream`. */
+typedef int (*sprl_forward_fn)(void* user, const float* d_in, int64_t batch, float* d_logits, float* d_value,
+                               void* cuda_stream);
+
+/* begin + rounds until every game is finished.  forward may be NULL for device evaluators. */
+int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, sprl_forward_fn forward, void* user);
+
+/* Totals of the finished iteration. */
+int sprl_iteration_counts(sprl_engine* e, int64_t* n_moves, int64_t* n_samples);
+
+/* Writes the iteration's samples, in the reference's order (games, moves, symmetries),
+ * to HOST arrays: states [n, 2H+1, R, C], distributions [n, A], outcomes [n]. */
+int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions,
+                         float* h_outcomes, int64_t* n_samples);
+/* Same, left on the device (engine-owned, valid until the next begin/collect). */
+int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_distributions, float** d_outcomes,
+                                int64_t* n_samples);
+
+/* Per-move search record of the iteration (needs record_stats), move-major in game order:
+ * N, W, P [n_moves, A]; root_N, root_W [n_moves]; action, traversals [n_moves];
+ * player [n_moves]; game_moves [num_games]; game_draws [num_games] (RNG draws used). */
+int sprl_move_stats(sprl_engine* e, int64_t cap_moves, float* h_N, float* h_W, float* h_P, float* h_root_N,
+                    float* h_root_W, int32_t* h_action, int32_t* h_traversals, int8_t* h_player,
+                    int32_t* h_game_moves, uint64_t* h_game_draws, int64_t* n_moves);
+
+typedef struct {
+    uint64_t sims, evals, moves, games;
+    uint64_t depth_sum, legal_sum, nodes_visited;
+    uint64_t leaves_terminal, leaves_gray, leaves_empty;
+    uint64_t units_high_water;      /* largest slab fill seen by any tree */
+    uint64_t units_per_tree;
+    uint64_t launches;              /* kernels this engine launched since creation */
+    uint64_t device_bytes;          /* HBM held by the engine */
+} sprl_stats;
+
+/* Counters accumulated since sprl_create (or the last sprl_reset_stats). */
+int sprl_get_stats(sprl_engine* e, sprl_stats* out);
+int sprl_reset_stats(sprl_engine* e);
+
+/* npy::write_npy (utils/npy.hpp:616-639) for float32 C-order data: byte-identical header. */
+int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* shape, int ndim);
+
 #ifdef __cplusplus
 }
 #endif

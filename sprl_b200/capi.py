@@ -1,0 +1,118 @@
+"""ctypes binding of libsprl_b200.so (include/sprl_b200.h).
+
+The library is the product: CUDA kernels + a C ABI.  This module only declares
+the prototypes and converts errors to exceptions; there is no Python or CPU
+implementation behind it.  Importing works without a GPU (symbols resolve);
+any compute call without a device raises SprlError(SPRL_E_NOGPU).
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+SPRL_OK = 0
+SPRL_E_INVALID, SPRL_E_CUDA, SPRL_E_CAPACITY, SPRL_E_STATE, SPRL_E_IO, SPRL_E_NOGPU = -1, -2, -3, -4, -5, -6
+GAME_OTHELLO, GAME_C4, GAME_GO7, GAME_GO9 = 0, 1, 2, 3
+EVAL_UNIFORM, EVAL_HASHNET, EVAL_EXTERNAL = 0, 1, 2
+INITQ_ZERO, INITQ_PARENT = 0, 1
+
+EXPORTS = [
+    "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
+    "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
+    "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_begin_iteration", "sprl_round", "sprl_poll",
+    "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
+    "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
+]
+
+
+class SprlError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libsprl_b200 error {code}: {message}")
+        self.code = code
+
+
+class GameInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("rows", "cols", "cells", "actions", "history", "nsym", "max_plies")]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("game", C.c_int), ("evaluator", C.c_int), ("seed", C.c_uint64),
+                ("num_slots", C.c_int), ("sims", C.c_int), ("max_batch", C.c_int), ("max_queue", C.c_int),
+                ("dir_eps", C.c_float), ("dir_alpha", C.c_float), ("u_weight", C.c_float),
+                ("add_noise", C.c_int), ("use_sym", C.c_int), ("init_q", C.c_int),
+                ("units_per_tree", C.c_int64), ("max_games", C.c_int64), ("record_stats", C.c_int),
+                ("rounds_per_launch", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("sims", "evals", "moves", "games", "depth_sum", "legal_sum", "nodes_visited",
+                                          "leaves_terminal", "leaves_gray", "leaves_empty", "units_high_water",
+                                          "units_per_tree", "launches", "device_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+FORWARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Loads the shared library (building it in-tree first when it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("SPRL_B200_REBUILD"):
+        _build.build_library()
+    lib = C.CDLL(path)
+    lib.sprl_last_error.restype = C.c_char_p
+    lib.sprl_eval_batch.restype = C.c_int64
+    lib.sprl_eval_batch.argtypes = [C.c_void_p]
+    lib.sprl_destroy.restype = None
+    lib.sprl_destroy.argtypes = [C.c_void_p]
+    lib.sprl_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.sprl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sprl_bind_eval_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sprl_begin_iteration.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+    lib.sprl_round.argtypes = [C.c_void_p]
+    lib.sprl_poll.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sprl_run_iteration.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.sprl_iteration_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sprl_collect_samples.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.sprl_collect_samples_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.sprl_move_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.POINTER(C.c_int64)]
+    lib.sprl_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.sprl_reset_stats.argtypes = [C.c_void_p]
+    lib.sprl_env_step.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 8
+    lib.sprl_env_rollout.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+    lib.sprl_env_perft.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    lib.sprl_write_npy_f32.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    lib.sprl_default_config.argtypes = [C.c_int, C.POINTER(Config)]
+    lib.sprl_game_info_get.argtypes = [C.c_int, C.POINTER(GameInfo)]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != SPRL_OK:
+        raise SprlError(rc, load().sprl_last_error().decode(errors="replace"))
+
+
+def game_info(game):
+    gi = GameInfo()
+    check(load().sprl_game_info_get(game, C.byref(gi)))
+    return gi
+
+
+def default_config(game):
+    cfg = Config()
+    check(load().sprl_default_config(game, C.byref(cfg)))
+    return cfg

@@ -1,0 +1,452 @@
+// engine.cu -- host side of the self-play engine behind the C ABI of
+// include/sprl_b200.h: owns the device pools, enqueues the search kernels of
+// search.cu on one CUDA stream, turns the per-game records into the reference's
+// sample arrays and writes them as .npy.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "search.cuh"
+
+namespace sprl {
+void search_launch_begin(int game, const EngineParams& p, cudaStream_t s);
+void search_launch_round(int game, const EngineParams& p, cudaStream_t s);
+void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
+                        cudaStream_t s);
+int search_header_units(int game);
+}  // namespace sprl
+
+using namespace sprl;
+
+struct sprl_engine {
+    sprl_config cfg;
+    sprl_game_info gi;
+    EngineParams p;
+    cudaStream_t stream = nullptr;
+    int words = 1;                  // 64-bit words per colour
+    int64_t num_games = 0;          // of the running / last iteration
+    int64_t active_slots = 0;
+    bool iteration_open = false;
+    bool failed = false;            // sticky CUDA error
+    uint64_t launches = 0;
+    uint64_t device_bytes = 0;
+    std::vector<void*> allocations;
+    // sample output (device), sized on demand
+    float* d_states = nullptr; float* d_dists = nullptr; float* d_outcomes = nullptr;
+    long long* d_row0 = nullptr;
+    int64_t sample_cap = 0;
+    // counters snapshot at reset
+    sprl_stats base;
+    std::vector<int> h_moves;
+
+    template <typename T> int alloc(T** out, size_t count, bool zero) {
+        void* ptr = nullptr;
+        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        cudaError_t err = cudaMalloc(&ptr, bytes);
+        if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
+        if (zero) {
+            err = cudaMemset(ptr, 0, bytes);
+            if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaMemset: %s", cudaGetErrorString(err));
+        }
+        allocations.push_back(ptr);
+        device_bytes += bytes;
+        *out = (T*)ptr;
+        return SPRL_OK;
+    }
+    void free_all() {
+        for (void* q : allocations) cudaFree(q);
+        allocations.clear();
+        if (d_states) cudaFree(d_states);
+        if (d_dists) cudaFree(d_dists);
+        if (d_outcomes) cudaFree(d_outcomes);
+        if (d_row0) cudaFree(d_row0);
+        d_states = d_dists = d_outcomes = nullptr; d_row0 = nullptr;
+    }
+};
+
+#define ENGINE_CHECK(e)                                                                   \
+    do {                                                                                  \
+        if (!(e)) return fail(SPRL_E_INVALID, "null engine");                             \
+        if ((e)->failed) return fail(SPRL_E_CUDA, "engine is in a failed state: %s", last_error_ref().c_str()); \
+        cudaError_t se__ = cudaSetDevice((e)->cfg.device);                                \
+        if (se__ != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(se__)); \
+    } while (0)
+
+#define ENGINE_CUDA(e, expr)                                                              \
+    do {                                                                                  \
+        cudaError_t err__ = (expr);                                                       \
+        if (err__ != cudaSuccess) {                                                       \
+            (e)->failed = true;                                                           \
+            return fail(SPRL_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(err__)); \
+        }                                                                                 \
+    } while (0)
+
+static int sum_tree_stats(sprl_engine* e, sprl_stats* out) {
+    std::vector<TreeState> ts(e->cfg.num_slots);
+    ENGINE_CUDA(e, cudaMemcpyAsync(ts.data(), e->p.trees, ts.size() * sizeof(TreeState), cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    memset(out, 0, sizeof(*out));
+    for (const TreeState& t : ts) {
+        out->sims += t.sims; out->evals += t.evals; out->moves += t.moves; out->games += t.games;
+        out->depth_sum += t.depth_sum; out->legal_sum += t.legal_sum; out->nodes_visited += t.nodes_visited;
+        out->leaves_terminal += t.leaves_terminal; out->leaves_gray += t.leaves_gray; out->leaves_empty += t.leaves_empty;
+        out->units_high_water = std::max<uint64_t>(out->units_high_water, t.high_water);
+    }
+    out->units_per_tree = e->p.cap_units;
+    out->launches = e->launches;
+    out->device_bytes = e->device_bytes;
+    return SPRL_OK;
+}
+
+extern "C" {
+
+int sprl_default_config(int game, sprl_config* cfg) {
+    if (!cfg) return fail(SPRL_E_INVALID, "null config");
+    sprl_game_info gi;
+    int rc = sprl_game_info_get(game, &gi);
+    if (rc) return rc;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0; cfg->game = game; cfg->evaluator = SPRL_EVAL_UNIFORM; cfg->seed = 0;
+    cfg->num_slots = 1024;
+    cfg->dir_eps = 0.25f; cfg->u_weight = 1.1f;           // constants.hpp:6
+    cfg->add_noise = 1; cfg->use_sym = 1; cfg->init_q = SPRL_INITQ_PARENT;
+    switch (game) {
+    case SPRL_GAME_OTHELLO: cfg->sims = 8192; cfg->max_batch = 8; cfg->max_queue = 4; cfg->dir_alpha = 0.3f; break;   // OTHWorker.cpp:23-28
+    case SPRL_GAME_C4: cfg->sims = 512; cfg->max_batch = 8; cfg->max_queue = 4; cfg->dir_alpha = 0.5f; break;        // C4Worker.cpp:22-27
+    default: cfg->sims = 32768; cfg->max_batch = 16; cfg->max_queue = 8; cfg->dir_alpha = 0.2f; break;               // GoWorker.cpp:22-27
+    }
+    cfg->units_per_tree = 0; cfg->max_games = 0; cfg->record_stats = 0; cfg->rounds_per_launch = 0;
+    return SPRL_OK;
+}
+
+int sprl_create(const sprl_config* cfg, sprl_engine** out) {
+    if (!cfg || !out) return fail(SPRL_E_INVALID, "null argument");
+    *out = nullptr;
+    sprl_game_info gi;
+    int rc = sprl_game_info_get(cfg->game, &gi);
+    if (rc) return rc;
+    if (cfg->num_slots <= 0 || cfg->sims <= 0 || cfg->max_batch <= 0 || cfg->max_queue <= 0)
+        return fail(SPRL_E_INVALID, "num_slots, sims, max_batch and max_queue must be positive");
+    if (cfg->evaluator < SPRL_EVAL_UNIFORM || cfg->evaluator > SPRL_EVAL_EXTERNAL) return fail(SPRL_E_INVALID, "unknown evaluator %d", cfg->evaluator);
+    if (cfg->init_q != SPRL_INITQ_ZERO && cfg->init_q != SPRL_INITQ_PARENT) return fail(SPRL_E_INVALID, "unknown init_q %d", cfg->init_q);
+    if (!(cfg->dir_alpha > 0.0f) && cfg->add_noise) return fail(SPRL_E_INVALID, "dir_alpha must be positive");
+    rc = use_device(cfg->device);
+    if (rc) return rc;
+
+    sprl_engine* e = new sprl_engine();
+    e->cfg = *cfg;
+    e->gi = gi;
+    e->words = gi.cells <= 64 ? 1 : 2;
+    memset(&e->base, 0, sizeof(e->base));
+    if (e->cfg.max_games <= 0) e->cfg.max_games = e->cfg.num_slots;
+    if (e->cfg.rounds_per_launch <= 0) e->cfg.rounds_per_launch = 8;
+    const int hdr = search_header_units(cfg->game);
+    if (e->cfg.units_per_tree <= 0) {
+        // a search adds at most one node per descent; the kept subtree is bounded in practice by a few
+        // searches' worth of nodes.  Average record = header + ~legal/2 edges.
+        int64_t avg = hdr + std::max(4, gi.actions / 3);
+        e->cfg.units_per_tree = std::max<int64_t>(4096, (int64_t)(cfg->sims + cfg->max_batch) * 4 * avg / 2);
+    }
+    if (e->cfg.units_per_tree > (1 << 24) - 1) e->cfg.units_per_tree = (1 << 24) - 1;       // child index is 24 bits
+    if (e->cfg.units_per_tree < 2 * (hdr + gi.actions) + SLAB_SLACK + 2) { delete e; return fail(SPRL_E_INVALID, "units_per_tree too small"); }
+
+    EngineParams& p = e->p;
+    memset(&p, 0, sizeof(p));
+    p.cap_units = (unsigned long long)e->cfg.units_per_tree;
+    p.n_slots = cfg->num_slots;
+    p.max_moves = gi.max_plies;
+    p.evaluator = cfg->evaluator; p.seed = cfg->seed;
+    p.sims = cfg->sims; p.max_batch = cfg->max_batch; p.max_queue = cfg->max_queue;
+    p.dir_eps = cfg->dir_eps; p.dir_alpha = cfg->dir_alpha; p.u_weight = cfg->u_weight;
+    p.add_noise = cfg->add_noise; p.use_sym = cfg->use_sym; p.init_q = cfg->init_q;
+    p.rounds_per_launch = (cfg->evaluator == SPRL_EVAL_EXTERNAL) ? 1 : e->cfg.rounds_per_launch;
+    p.record_stats = cfg->record_stats;
+
+    const size_t S = (size_t)cfg->num_slots, MG = (size_t)e->cfg.max_games, MM = (size_t)gi.max_plies, A = (size_t)gi.actions;
+    rc = e->alloc(&p.pool, S * 2 * p.cap_units, false);
+    if (!rc) rc = e->alloc(&p.trees, S, true);
+    if (!rc) rc = e->alloc(&p.q_leaf, S * cfg->max_queue, true);
+    if (!rc) rc = e->alloc(&p.q_sym, S * cfg->max_queue, true);
+    if (!rc) rc = e->alloc(&p.root_p, S * A, true);
+    if (!rc) rc = e->alloc(&p.rec_board, MG * MM * 2 * e->words, true);
+    if (!rc) rc = e->alloc(&p.rec_player, MG * MM, true);
+    if (!rc) rc = e->alloc(&p.rec_pdf, MG * MM * A, false);
+    if (!rc) rc = e->alloc(&p.rec_moves, MG, true);
+    if (!rc) rc = e->alloc(&p.rec_winner, MG, true);
+    if (!rc) rc = e->alloc(&p.rec_draws, MG, true);
+    if (!rc) rc = e->alloc(&p.counters, 4, true);
+    if (!rc && cfg->record_stats) {
+        rc = e->alloc(&p.rec_N, MG * MM * A, false);
+        if (!rc) rc = e->alloc(&p.rec_W, MG * MM * A, false);
+        if (!rc) rc = e->alloc(&p.rec_P, MG * MM * A, false);
+        if (!rc) rc = e->alloc(&p.rec_root_N, MG * MM, false);
+        if (!rc) rc = e->alloc(&p.rec_root_W, MG * MM, false);
+        if (!rc) rc = e->alloc(&p.rec_action, MG * MM, false);
+        if (!rc) rc = e->alloc(&p.rec_trav, MG * MM, false);
+    }
+    if (rc) { e->free_all(); delete e; return rc; }
+    *out = e;
+    return SPRL_OK;
+}
+
+void sprl_destroy(sprl_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    e->free_all();
+    delete e;
+}
+
+int sprl_set_stream(sprl_engine* e, void* cuda_stream) {
+    ENGINE_CHECK(e);
+    e->stream = (cudaStream_t)cuda_stream;
+    return SPRL_OK;
+}
+
+int sprl_bind_eval_buffers(sprl_engine* e, float* d_in, const float* d_logits, const float* d_value) {
+    ENGINE_CHECK(e);
+    if (e->cfg.evaluator != SPRL_EVAL_EXTERNAL) return fail(SPRL_E_STATE, "engine was not created with SPRL_EVAL_EXTERNAL");
+    if (!d_in || !d_logits || !d_value) return fail(SPRL_E_INVALID, "null evaluator buffer");
+    e->p.nn_in = d_in; e->p.nn_logits = d_logits; e->p.nn_value = d_value;
+    return SPRL_OK;
+}
+
+int64_t sprl_eval_batch(const sprl_engine* e) { return e ? (int64_t)e->cfg.num_slots * e->cfg.max_queue : 0; }
+
+int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games) {
+    ENGINE_CHECK(e);
+    if (num_games <= 0) return fail(SPRL_E_INVALID, "num_games must be positive");
+    if (num_games > e->cfg.max_games) return fail(SPRL_E_CAPACITY, "num_games %lld exceeds max_games %lld", (long long)num_games, (long long)e->cfg.max_games);
+    e->p.first_game = first_game;
+    e->p.num_games = num_games;
+    e->num_games = num_games;
+    e->active_slots = std::min<int64_t>(num_games, e->cfg.num_slots);
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_moves, 0, (size_t)e->cfg.max_games * sizeof(int), e->stream));
+    search_launch_begin(e->cfg.game, e->p, e->stream);
+    e->launches += 1;
+    ENGINE_CUDA(e, cudaGetLastError());
+    e->iteration_open = true;
+    return SPRL_OK;
+}
+
+int sprl_round(sprl_engine* e) {
+    ENGINE_CHECK(e);
+    if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration in progress");
+    if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
+    search_launch_round(e->cfg.game, e->p, e->stream);
+    e->launches += 1;
+    ENGINE_CUDA(e, cudaGetLastError());
+    return SPRL_OK;
+}
+
+int sprl_poll(sprl_engine* e, int64_t* slots_playing, int64_t* slots_failed) {
+    ENGINE_CHECK(e);
+    unsigned long long c[4] = { 0, 0, 0, 0 };
+    ENGINE_CUDA(e, cudaMemcpyAsync(c, e->p.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (slots_playing) *slots_playing = e->active_slots - (int64_t)c[0] - (int64_t)c[1];
+    if (slots_failed) *slots_failed = (int64_t)c[1];
+    return SPRL_OK;
+}
+
+static int report_slot_failure(sprl_engine* e) {
+    std::vector<TreeState> ts(e->cfg.num_slots);
+    cudaMemcpy(ts.data(), e->p.trees, ts.size() * sizeof(TreeState), cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < ts.size(); ++i) {
+        if (ts[i].status == ST_ERR_CAPACITY)
+            return fail(SPRL_E_CAPACITY, "tree slot %zu ran out of node units (units_per_tree=%llu, game %llu move %d); raise units_per_tree",
+                        i, (unsigned long long)e->p.cap_units, (unsigned long long)ts[i].game_id, ts[i].move_count);
+        if (ts[i].status == ST_ERR_MOVES)
+            return fail(SPRL_E_CAPACITY, "tree slot %zu exceeded %d moves in one game", i, e->p.max_moves);
+    }
+    return fail(SPRL_E_STATE, "a slot failed for an unknown reason");
+}
+
+int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, sprl_forward_fn forward, void* user) {
+    ENGINE_CHECK(e);
+    if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
+    int rc = sprl_begin_iteration(e, first_game, num_games);
+    if (rc) return rc;
+    const int check_every = (e->cfg.evaluator == SPRL_EVAL_EXTERNAL) ? 64 : 4;
+    for (;;) {
+        for (int i = 0; i < check_every; ++i) {
+            rc = sprl_round(e);
+            if (rc) return rc;
+            if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL) {
+                rc = forward(user, e->p.nn_in, sprl_eval_batch(e), const_cast<float*>(e->p.nn_logits),
+                             const_cast<float*>(e->p.nn_value), (void*)e->stream);
+                if (rc) return fail(SPRL_E_STATE, "forward callback returned %d", rc);
+            }
+        }
+        int64_t playing = 0, failed = 0;
+        rc = sprl_poll(e, &playing, &failed);
+        if (rc) return rc;
+        if (failed > 0) return report_slot_failure(e);
+        if (playing == 0) break;
+    }
+    return SPRL_OK;
+}
+
+static int load_game_moves(sprl_engine* e, int64_t* n_moves) {
+    e->h_moves.resize((size_t)e->num_games);
+    ENGINE_CUDA(e, cudaMemcpyAsync(e->h_moves.data(), e->p.rec_moves, (size_t)e->num_games * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    int64_t total = 0;
+    for (int m : e->h_moves) total += m;
+    *n_moves = total;
+    return SPRL_OK;
+}
+
+int sprl_iteration_counts(sprl_engine* e, int64_t* n_moves, int64_t* n_samples) {
+    ENGINE_CHECK(e);
+    if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
+    int64_t moves = 0;
+    int rc = load_game_moves(e, &moves);
+    if (rc) return rc;
+    int S = e->cfg.use_sym ? e->gi.nsym : 1;
+    if (n_moves) *n_moves = moves;
+    if (n_samples) *n_samples = moves * S;
+    return SPRL_OK;
+}
+
+int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_distributions, float** d_outcomes, int64_t* n_samples) {
+    ENGINE_CHECK(e);
+    if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
+    int64_t moves = 0;
+    int rc = load_game_moves(e, &moves);
+    if (rc) return rc;
+    const int S = e->cfg.use_sym ? e->gi.nsym : 1;
+    const int64_t n = moves * S;
+    const size_t row = (size_t)(2 * e->gi.history + 1) * e->gi.cells;
+    if (n > e->sample_cap || !e->d_row0) {
+        if (e->d_states) cudaFree(e->d_states);
+        if (e->d_dists) cudaFree(e->d_dists);
+        if (e->d_outcomes) cudaFree(e->d_outcomes);
+        if (e->d_row0) cudaFree(e->d_row0);
+        e->d_states = e->d_dists = e->d_outcomes = nullptr; e->d_row0 = nullptr;
+        int64_t cap = std::max<int64_t>(n, 1);
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_states, (size_t)cap * row * sizeof(float)));
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_dists, (size_t)cap * e->gi.actions * sizeof(float)));
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_outcomes, (size_t)cap * sizeof(float)));
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_row0, (size_t)e->cfg.max_games * sizeof(long long)));
+        e->sample_cap = cap;
+    }
+    std::vector<long long> row0((size_t)e->num_games);
+    long long at = 0;
+    for (int64_t g = 0; g < e->num_games; ++g) { row0[g] = at; at += (long long)e->h_moves[g] * S; }
+    ENGINE_CUDA(e, cudaMemcpyAsync(e->d_row0, row0.data(), row0.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));      // row0 is a stack-lifetime host buffer
+    if (n > 0) {
+        search_launch_emit(e->cfg.game, e->p, e->d_row0, S, e->d_states, e->d_dists, e->d_outcomes, e->stream);
+        e->launches += 1;
+        ENGINE_CUDA(e, cudaGetLastError());
+    }
+    if (d_states) *d_states = e->d_states;
+    if (d_distributions) *d_distributions = e->d_dists;
+    if (d_outcomes) *d_outcomes = e->d_outcomes;
+    if (n_samples) *n_samples = n;
+    return SPRL_OK;
+}
+
+int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions, float* h_outcomes,
+                         int64_t* n_samples) {
+    int64_t n = 0;
+    float *ds, *dd, *dout;
+    int rc = sprl_collect_samples_device(e, &ds, &dd, &dout, &n);
+    if (rc) return rc;
+    if (n_samples) *n_samples = n;
+    if (n > cap_samples) return fail(SPRL_E_CAPACITY, "%lld samples do not fit the caller's capacity %lld", (long long)n, (long long)cap_samples);
+    const size_t row = (size_t)(2 * e->gi.history + 1) * e->gi.cells;
+    if (n > 0) {
+        if (h_states) ENGINE_CUDA(e, cudaMemcpyAsync(h_states, ds, (size_t)n * row * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (h_distributions) ENGINE_CUDA(e, cudaMemcpyAsync(h_distributions, dd, (size_t)n * e->gi.actions * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (h_outcomes) ENGINE_CUDA(e, cudaMemcpyAsync(h_outcomes, dout, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    return SPRL_OK;
+}
+
+int sprl_move_stats(sprl_engine* e, int64_t cap_moves, float* h_N, float* h_W, float* h_P, float* h_root_N,
+                    float* h_root_W, int32_t* h_action, int32_t* h_traversals, int8_t* h_player,
+                    int32_t* h_game_moves, uint64_t* h_game_draws, int64_t* n_moves) {
+    ENGINE_CHECK(e);
+    if (!e->cfg.record_stats) return fail(SPRL_E_STATE, "engine was created without record_stats");
+    if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
+    int64_t moves = 0;
+    int rc = load_game_moves(e, &moves);
+    if (rc) return rc;
+    if (n_moves) *n_moves = moves;
+    if (moves > cap_moves) return fail(SPRL_E_CAPACITY, "%lld moves do not fit the caller's capacity %lld", (long long)moves, (long long)cap_moves);
+    const size_t A = (size_t)e->gi.actions, MM = (size_t)e->p.max_moves;
+    int64_t at = 0;
+    for (int64_t g = 0; g < e->num_games; ++g) {
+        size_t m = (size_t)e->h_moves[g], src = (size_t)g * MM;
+        if (m == 0) continue;
+        if (h_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_N + at * A, e->p.rec_N + src * A, m * A * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_W) ENGINE_CUDA(e, cudaMemcpyAsync(h_W + at * A, e->p.rec_W + src * A, m * A * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_P) ENGINE_CUDA(e, cudaMemcpyAsync(h_P + at * A, e->p.rec_P + src * A, m * A * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_root_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_N + at, e->p.rec_root_N + src, m * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_root_W) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_W + at, e->p.rec_root_W + src, m * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_action) ENGINE_CUDA(e, cudaMemcpyAsync(h_action + at, e->p.rec_action + src, m * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_traversals) ENGINE_CUDA(e, cudaMemcpyAsync(h_traversals + at, e->p.rec_trav + src, m * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (h_player) ENGINE_CUDA(e, cudaMemcpyAsync(h_player + at, e->p.rec_player + src, m, cudaMemcpyDeviceToHost, e->stream));
+        at += (int64_t)m;
+    }
+    if (h_game_moves) memcpy(h_game_moves, e->h_moves.data(), (size_t)e->num_games * sizeof(int));
+    if (h_game_draws) ENGINE_CUDA(e, cudaMemcpyAsync(h_game_draws, e->p.rec_draws, (size_t)e->num_games * 8, cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    return SPRL_OK;
+}
+
+int sprl_get_stats(sprl_engine* e, sprl_stats* out) {
+    ENGINE_CHECK(e);
+    if (!out) return fail(SPRL_E_INVALID, "null output");
+    sprl_stats now;
+    int rc = sum_tree_stats(e, &now);
+    if (rc) return rc;
+    *out = now;
+    out->sims -= e->base.sims; out->evals -= e->base.evals; out->moves -= e->base.moves; out->games -= e->base.games;
+    out->depth_sum -= e->base.depth_sum; out->legal_sum -= e->base.legal_sum; out->nodes_visited -= e->base.nodes_visited;
+    out->leaves_terminal -= e->base.leaves_terminal; out->leaves_gray -= e->base.leaves_gray; out->leaves_empty -= e->base.leaves_empty;
+    out->launches -= e->base.launches;
+    return SPRL_OK;
+}
+
+int sprl_reset_stats(sprl_engine* e) {
+    ENGINE_CHECK(e);
+    return sum_tree_stats(e, &e->base);
+}
+
+int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* shape, int ndim) {
+    if (!path || (!h_data && ndim > 0) || ndim < 0 || ndim > 8) return fail(SPRL_E_INVALID, "bad argument to sprl_write_npy_f32");
+    // utils/npy.hpp:430-476: v1.0 header, dict padded with spaces to a multiple of 16 (a full 16 when already aligned)
+    std::string tuple;
+    uint64_t count = 1;
+    if (ndim == 0) tuple = "()";
+    else if (ndim == 1) tuple = "(" + std::to_string(shape[0]) + ",)";
+    else {
+        tuple = "(";
+        for (int i = 0; i < ndim; ++i) tuple += std::to_string(shape[i]) + (i + 1 < ndim ? ", " : ")");
+    }
+    for (int i = 0; i < ndim; ++i) count *= shape[i];
+    std::string dict = "{'descr': '<f4', 'fortran_order': False, 'shape': " + tuple + ", }";
+    size_t length = 6 + 2 + 2 + dict.size() + 1;
+    size_t pad = 16 - length % 16;
+    size_t hlen = dict.size() + pad + 1;
+    if (hlen > 65535) return fail(SPRL_E_INVALID, "npy header too long");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SPRL_E_IO, "io error: failed to open %s", path);
+    const unsigned char magic[10] = { 0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(hlen & 0xff), (unsigned char)(hlen >> 8) };
+    bool ok = fwrite(magic, 1, 10, f) == 10 && fwrite(dict.data(), 1, dict.size(), f) == dict.size();
+    std::string padding(pad, ' ');
+    padding += '\n';
+    ok = ok && fwrite(padding.data(), 1, padding.size(), f) == padding.size();
+    ok = ok && (count == 0 || fwrite(h_data, sizeof(float), (size_t)count, f) == (size_t)count);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(SPRL_E_IO, "io error: short write to %s", path);
+    return SPRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,849 @@
+// search.cu -- warp-per-tree UCT search, move finalisation, subtree compaction and
+// sample emission.  Restates on the device, with the reference's fp32 operand
+// order, what /root/reference/cpp/src/uct/UCTTree.hpp, uct/UCTNode.hpp and
+// selfplay/SelfPlay.hpp do per game; see search.cuh for the data model.
+//
+// Every branch on tree state below is warp-uniform: all 32 lanes of the owning
+// warp hold identical copies of the tree registers and of the RNG stream, and
+// only the parts marked "lane k" diverge (one lane per edge / cell).
+#include "common.cuh"
+#include "search.cuh"
+
+namespace sprl {
+
+#define FULL 0xffffffffu
+
+// ---- symmetries (symmetry/D4GridSymmetrizer.hpp:106-117, ConnectFourSymmetrizer.cpp) ----
+template <class G>
+__device__ __forceinline__ int sym_cell(int s, int from) {     // to = f_s(from)
+    if (G::KIND == GAME_C4) {
+        int r = from / 7, c = from - r * 7;
+        return s == 1 ? r * 7 + (6 - c) : from;
+    }
+    const int w = G::COLS;
+    int r = from / w, c = from - r * w, tr, tc;
+    switch (s) {
+    case 0: tr = r; tc = c; break;
+    case 1: tr = c; tc = w - 1 - r; break;
+    case 2: tr = w - 1 - r; tc = w - 1 - c; break;
+    case 3: tr = w - 1 - c; tc = r; break;
+    case 4: tr = r; tc = w - 1 - c; break;
+    case 5: tr = w - 1 - c; tc = w - 1 - r; break;
+    case 6: tr = w - 1 - r; tc = c; break;
+    default: tr = c; tc = r; break;
+    }
+    return tr * w + tc;
+}
+template <class G>
+__device__ __forceinline__ int sym_action(int s, int a) {
+    if (G::KIND == GAME_C4) return s == 1 ? 6 - a : a;
+    return a == G::CELLS ? a : sym_cell<G>(s, a);
+}
+template <class G>
+__device__ __forceinline__ int sym_inverse(int s) {             // D4GridSymmetrizer.hpp:47-50
+    if (G::KIND == GAME_C4) return s;
+    return (s == 1) ? 3 : ((s == 3) ? 1 : s);
+}
+
+// ---- node header in registers ---------------------------------------------------------------
+template <int W>
+struct Hdr {
+    Bits<W> b0, b1, legal;
+    u32 parent, own_edge;
+    float net_value;
+    u32 meta, aux;
+};
+
+template <int W> struct HL;
+template <> struct HL<1> {
+    static constexpr int HDR = 3;
+    __device__ static void load(const uint4* p, Hdr<1>& h) {
+        uint4 a = p[0], b = p[1], c = p[2];
+        h.b0 = Bits<1>((u64)a.x | ((u64)a.y << 32));
+        h.b1 = Bits<1>((u64)a.z | ((u64)a.w << 32));
+        h.legal = Bits<1>((u64)b.x | ((u64)b.y << 32));
+        h.parent = b.z; h.own_edge = b.w;
+        h.net_value = __uint_as_float(c.x); h.meta = c.y; h.aux = c.z;
+    }
+    __device__ static void store_unit(uint4* p, int i, const Hdr<1>& h) {
+        if (i == 0) p[0] = make_uint4((u32)h.b0.w0, (u32)(h.b0.w0 >> 32), (u32)h.b1.w0, (u32)(h.b1.w0 >> 32));
+        else if (i == 1) p[1] = make_uint4((u32)h.legal.w0, (u32)(h.legal.w0 >> 32), h.parent, h.own_edge);
+        else p[2] = make_uint4(__float_as_uint(h.net_value), h.meta, h.aux, 0u);
+    }
+    __device__ static u32* meta_ptr(uint4* p) { return reinterpret_cast<u32*>(p + 2) + 1; }
+    __device__ static float* value_ptr(uint4* p) { return reinterpret_cast<float*>(p + 2); }
+    __device__ static void load_links(const uint4* p, u32& parent, u32& own_edge) { uint4 b = p[1]; parent = b.z; own_edge = b.w; }
+    __device__ static void load_boards(const uint4* p, Bits<1>& b0, Bits<1>& b1) {
+        uint4 a = p[0];
+        b0 = Bits<1>((u64)a.x | ((u64)a.y << 32));
+        b1 = Bits<1>((u64)a.z | ((u64)a.w << 32));
+    }
+};
+template <> struct HL<2> {
+    static constexpr int HDR = 5;
+    __device__ static Bits<2> bits(uint4 a) { return Bits<2>((u64)a.x | ((u64)a.y << 32), (u64)a.z | ((u64)a.w << 32)); }
+    __device__ static uint4 unit(const Bits<2>& b) { return make_uint4((u32)b.w0, (u32)(b.w0 >> 32), (u32)b.w1, (u32)(b.w1 >> 32)); }
+    __device__ static void load(const uint4* p, Hdr<2>& h) {
+        h.b0 = bits(p[0]); h.b1 = bits(p[1]); h.legal = bits(p[2]);
+        uint4 d = p[3], e = p[4];
+        h.parent = d.x; h.own_edge = d.y; h.net_value = __uint_as_float(d.z); h.meta = d.w; h.aux = e.x;
+    }
+    __device__ static void store_unit(uint4* p, int i, const Hdr<2>& h) {
+        if (i == 0) p[0] = unit(h.b0);
+        else if (i == 1) p[1] = unit(h.b1);
+        else if (i == 2) p[2] = unit(h.legal);
+        else if (i == 3) p[3] = make_uint4(h.parent, h.own_edge, __float_as_uint(h.net_value), h.meta);
+        else p[4] = make_uint4(h.aux, 0u, 0u, 0u);
+    }
+    __device__ static u32* meta_ptr(uint4* p) { return reinterpret_cast<u32*>(p + 3) + 3; }
+    __device__ static float* value_ptr(uint4* p) { return reinterpret_cast<float*>(p + 3) + 2; }
+    __device__ static void load_links(const uint4* p, u32& parent, u32& own_edge) { uint4 d = p[3]; parent = d.x; own_edge = d.y; }
+    __device__ static void load_boards(const uint4* p, Bits<2>& b0, Bits<2>& b1) { b0 = bits(p[0]); b1 = bits(p[1]); }
+};
+
+template <class G>
+__device__ __forceinline__ void pos_to_hdr(const typename G::P& p, u32 parent, u32 own_edge, Hdr<G::W>& h) {
+    h.b0 = p.b[0]; h.b1 = p.b[1]; h.legal = p.legal;
+    h.parent = parent; h.own_edge = own_edge; h.net_value = 0.0f;
+    u32 n = p.terminal ? 0u : (u32)p.n_legal();          // edges exist only below non-terminal nodes
+    h.meta = n | ((u32)p.player << 8) | ((u32)p.terminal << 9) | ((u32)p.winner << 10) |
+             ((u32)p.pass_legal << 14) | ((u32)p.action << 16);
+    h.aux = p.depth;
+}
+template <class G>
+__device__ __forceinline__ void hdr_to_pos(const Hdr<G::W>& h, typename G::P& p) {
+    p.b[0] = h.b0; p.b[1] = h.b1; p.legal = h.legal;
+    p.player = META_PLAYER(h.meta); p.terminal = META_TERMINAL(h.meta); p.winner = META_WINNER(h.meta);
+    p.pass_legal = META_PASS_LEGAL(h.meta); p.action = META_ACTION(h.meta); p.depth = (unsigned short)h.aux;
+}
+
+// shared-memory scratch of one warp
+struct WarpScratch {
+    float pol[96];      // dense per-action vector (policy / pdf)
+    float aux[96];      // per-slot vector (noise, cdf)
+};
+
+// ---- the warp that owns a tree -----------------------------------------------------------------
+template <class G>
+struct TreeWarp {
+    static constexpr int W = G::W;
+    static constexpr int HDR = HL<W>::HDR;
+    static constexpr int NCH = (G::ACTIONS + 31) / 32;
+    typedef Hdr<W> H;
+    typedef typename G::P P;
+
+    const EngineParams& p;
+    const int tree, lane;
+    TreeState st;
+    Rng rng;
+    uint4* slab;            // current slab
+    WarpScratch& sm;
+
+    __device__ TreeWarp(const EngineParams& p_, int tree_, int lane_, WarpScratch& sm_)
+        : p(p_), tree(tree_), lane(lane_), sm(sm_) {
+        st = p.trees[tree];
+        rng.seed = p.seed; rng.game = st.game_id; rng.ctr = st.rng_ctr;
+        slab = slab_ptr(st.slab);
+    }
+    __device__ uint4* slab_ptr(u32 which) const { return p.pool + ((size_t)tree * 2 + which) * p.cap_units; }
+    __device__ void save() {
+        st.rng_ctr = rng.ctr;
+        if (st.n_units > st.high_water) st.high_water = st.n_units;
+        if (lane == 0) p.trees[tree] = st;
+    }
+    __device__ size_t rec_index() const { return (size_t)st.game_index * p.max_moves + st.move_count; }
+
+    // ---- history of boards above a node: tree ancestors, then the game's earlier moves ----
+    struct TreeHist {
+        const TreeWarp* t;
+        u32 start;          // first unit whose board is compared (walks parent links to the root)
+        __device__ bool seen(const Bits<W>& a0, const Bits<W>& a1) const {
+            u32 cur = start;
+            for (;;) {
+                Bits<W> b0, b1;
+                HL<W>::load_boards(t->slab + cur, b0, b1);
+                if (b0 == a0 && b1 == a1) return true;
+                if (cur == ROOT_UNIT) break;
+                u32 par, own;
+                HL<W>::load_links(t->slab + cur, par, own);
+                cur = par;
+            }
+            const unsigned long long* rb = t->p.rec_board + (size_t)t->st.game_index * t->p.max_moves * 2 * W;
+            for (int m = t->st.move_count - 1; m >= 0; --m) {
+                bool same = true;
+                for (int w = 0; w < W; ++w)
+                    same = same && rb[(size_t)m * 2 * W + w] == a0.word(w) && rb[(size_t)m * 2 * W + W + w] == a1.word(w);
+                if (same) return true;
+            }
+            return false;
+        }
+    };
+
+    // boards of the position `t` plies above `unit` (0 = itself); false when the game is younger
+    __device__ bool history_board(u32 unit, int t, Bits<W>& b0, Bits<W>& b1) const {
+        u32 cur = unit;
+        while (t > 0 && cur != ROOT_UNIT) {
+            u32 par, own;
+            HL<W>::load_links(slab + cur, par, own);
+            cur = par; --t;
+        }
+        if (t == 0) { HL<W>::load_boards(slab + cur, b0, b1); return true; }
+        int m = st.move_count - t;
+        if (m < 0) return false;
+        const unsigned long long* rb = p.rec_board + ((size_t)st.game_index * p.max_moves + m) * 2 * W;
+        for (int w = 0; w < W; ++w) { b0.set_word(w, rb[w]); b1.set_word(w, rb[W + w]); }
+        return true;
+    }
+
+    // ---- GameNode::getNextNodeImpl for the child of `par` (unit par_unit) ----
+    __device__ void make_child_pos(const P& par, u32 par_unit, int action, P& child) {
+        if constexpr (G::KIND == GAME_GO7 || G::KIND == GAME_GO9) {
+            G::template next_board<NoHistory>(par, action, child);
+            if (!child.terminal) {
+                // legality of every empty point for the side to move, one lane per cell;
+                // superko compares against the new board itself, `par` and everything above it
+                const typename G::Masks m = G::masks();
+                struct Hist {
+                    TreeHist th; Bits<W> s0, s1;
+                    __device__ bool seen(const Bits<W>& a, const Bits<W>& b) const { return (a == s0 && b == s1) || th.seen(a, b); }
+                } hist = { { this, par_unit }, child.b[0], child.b[1] };
+                Bits<W> legal;
+                for (int base = 0; base < G::CELLS; base += 32) {
+                    int c = base + lane;
+                    bool ok = c < G::CELLS && G::legal_at(child.b[child.player], child.b[1 - child.player], child.player, c, m, hist);
+                    u32 bal = __ballot_sync(FULL, ok);
+                    legal = legal | from_ballot(bal, base);
+                }
+                child.legal = legal;
+            }
+        } else {
+            G::next(par, action, NoHistory(), child);
+        }
+    }
+    // 32 cells [base, base+32) of a bit set, from a warp ballot
+    __device__ static Bits<W> from_ballot(u32 bal, int base) {
+        Bits<W> r;
+        if (base < 64) r.set_word(0, (u64)bal << base);
+        else if constexpr (W == 2) r.set_word(1, (u64)bal << (base - 64));
+        return r;
+    }
+
+    // ---- writes a node record at `unit`; all lanes hold `child` ----
+    __device__ bool write_node(uint4* dst_slab, u32 unit, const P& child, u32 parent, u32 own_edge, H& h) {
+        pos_to_hdr<G>(child, parent, own_edge, h);
+        int n = META_NLEGAL(h.meta);
+        if (lane < HDR) HL<W>::store_unit(dst_slab + unit, lane, h);
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) {
+                u32 a = (u32)legal_action<G>(child, k);
+                dst_slab[unit + HDR + k] = make_uint4(0u, 0u, 0u, a << 24);
+            }
+        }
+        return true;
+    }
+
+    __device__ void init_game() {
+        st.game_id = p.first_game + (unsigned long long)st.game_index;
+        rng.game = st.game_id; rng.ctr = 0;
+        st.slab = 0; slab = slab_ptr(0);
+        st.traversals = 0; st.move_count = 0; st.n_queued = 0;
+        P start;
+        G::start(start);
+        H h;
+        if (lane == 0) slab[0] = make_uint4(0u, 0u, 0u, 0u);
+        write_node(slab, ROOT_UNIT, start, 0u, 0u, h);
+        st.n_units = ROOT_UNIT + HDR + META_NLEGAL(h.meta);
+        __syncwarp();
+    }
+
+    // ---- UCTTree::backup (uct/UCTTree.hpp:261-273) by walking parent links ----
+    __device__ void backup(u32 leaf, int leaf_player, float value) {
+        float est = -value * (leaf_player == 0 ? 1.0f : -1.0f);
+        u32 cur = leaf;
+        int player = leaf_player;
+        for (;;) {
+            u32 par, own;
+            HL<W>::load_links(slab + cur, par, own);
+            float term = 1.0f + est * (player == 0 ? 1.0f : -1.0f);
+            if (lane == 0) {
+                float* w = reinterpret_cast<float*>(slab + own) + 1;
+                *w = *w + term;
+            }
+            if (cur == ROOT_UNIT) break;
+            cur = par; player ^= 1;
+        }
+        __syncwarp();
+    }
+
+    // ---- Dirichlet mix at the decision node (uct/UCTNode.hpp:330-346) ----
+    __device__ void root_noise(int n) {
+        float sum = 0.0f;
+        for (int k = 0; k < n; ++k) {                    // sequential stream: every lane draws the same values
+            float g = rng_gamma(rng, p.dir_alpha);
+            if (lane == 0) sm.aux[k] = g;
+            sum += g;
+        }
+        float norm = 1.0f / sum;
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) {
+                float noise = sm.aux[k] * norm;
+                float prior = __uint_as_float(slab[ROOT_UNIT + HDR + k].x);
+                float mixed = (float)((1.0 - (double)p.dir_eps) * (double)prior + (double)(p.dir_eps * noise));
+                p.root_p[(size_t)tree * G::ACTIONS + k] = mixed;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- UCTNode::expand (uct/UCTNode.hpp:314-348): gray -> active ----
+    __device__ void expand(u32 unit, u32& meta) {
+        meta |= META_EXPANDED;
+        if (lane == 0) *HL<W>::meta_ptr(slab + unit) = meta;
+        if (unit == ROOT_UNIT && p.add_noise) root_noise(META_NLEGAL(meta));
+        __syncwarp();
+    }
+
+    // ---- one descent: UCTTree::selectLeaf (uct/UCTTree.hpp:225-249) ----
+    // Virtual loss (N += 1, W -= 1) is written on the edge INTO a node at the moment
+    // the edge is chosen; the pre-loss N of that edge is what the child's sqrt(N()) uses.
+    __device__ u32 select_leaf(H& leaf_hdr) {
+        u32 cur = ROOT_UNIT;
+        uint4 d = slab[0];
+        float n_own = __uint_as_float(d.z);
+        if (lane == 0) slab[0] = make_uint4(d.x, __float_as_uint(__uint_as_float(d.y) - 1.0f), __float_as_uint(n_own + 1.0f), d.w);
+        int depth = 0;
+        bool have = false;
+        H h;
+        for (;;) {
+            if (!have) HL<W>::load(slab + cur, h);
+            have = false;
+            if (META_TERMINAL(h.meta) || !(h.meta & META_EXPANDED)) break;
+            const int n = META_NLEGAL(h.meta);
+            st.nodes_visited += 1; st.legal_sum += n;
+            // UCTNode::bestAction (uct/UCTNode.hpp:221-251)
+            const float sq = sqrtf(n_own);
+            uint4 e[NCH];
+            float val[NCH];
+            float best = -__int_as_float(0x7f800000);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                int k = ch * 32 + lane;
+                val[ch] = -__int_as_float(0x7f800000);
+                if (k < n) {
+                    e[ch] = slab[cur + HDR + k];
+                    float prior = (cur == ROOT_UNIT && p.add_noise) ? p.root_p[(size_t)tree * G::ACTIONS + k] : __uint_as_float(e[ch].x);
+                    float w = __uint_as_float(e[ch].y), nv = __uint_as_float(e[ch].z);
+                    float q = w / (1.0f + nv);
+                    float u = prior * sq / (1.0f + nv);
+                    val[ch] = q + p.u_weight * u;
+                }
+                best = fmaxf(best, val[ch]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
+            u32 bal[NCH];
+            int cnt = 0;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                bal[ch] = __ballot_sync(FULL, (ch * 32 + lane < n) && val[ch] == best);
+                cnt += __popc(bal[ch]);
+            }
+            int r = rng_uniform_int(rng, 0, cnt - 1);       // tie-break, uct/UCTNode.hpp:250
+            int ksel = 0;
+            bool found = false;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                int c = __popc(bal[ch]);
+                if (!found && r < c) { ksel = ch * 32 + (int)__fns(bal[ch], 0, r + 1); found = true; }
+                if (!found) r -= c;
+            }
+            uint4 es = e[0];
+#pragma unroll
+            for (int ch = 1; ch < NCH; ++ch) if ((ksel >> 5) == ch) es = e[ch];
+            const int src_lane = ksel & 31;
+            u32 ew = __shfl_sync(FULL, es.w, src_lane);
+            float child_n = __uint_as_float(__shfl_sync(FULL, es.z, src_lane));
+            u32 child = EDGE_CHILD(ew);
+            const u32 edge_unit = cur + HDR + ksel;
+            float w_sel = __uint_as_float(es.y);
+            if (child == 0) {
+                // UCTNode::getAddChild (uct/UCTNode.hpp:258-284) + GameNode::getAddChild
+                P par, cp;
+                hdr_to_pos<G>(h, par);
+                make_child_pos(par, cur, (int)EDGE_ACTION(ew), cp);
+                u32 need = HDR + (cp.terminal ? 0u : (u32)cp.n_legal());
+                if (st.n_units + need + SLAB_SLACK > p.cap_units) { st.status = ST_ERR_CAPACITY; leaf_hdr = h; return cur; }
+                child = st.n_units;
+                st.n_units += need;
+                H ch;
+                write_node(slab, child, cp, cur, edge_unit, ch);
+                ew |= child;
+                w_sel = (p.init_q == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
+                h = ch; have = true;
+            }
+            if (lane == src_lane)
+                slab[edge_unit] = make_uint4(es.x, __float_as_uint(w_sel - 1.0f), __float_as_uint(child_n + 1.0f), ew);
+            n_own = child_n;
+            cur = child;
+            ++depth;
+            __syncwarp();
+        }
+        st.depth_sum += depth;
+        leaf_hdr = h;
+        return cur;
+    }
+
+    // ---- UCTTree::searchAndGetLeaves (uct/UCTTree.hpp:76-114) + the symmetry draws of :141-149 ----
+    __device__ void search_batch() {
+        int trav = 0, nq = 0;
+        while (trav < p.max_batch) {
+            ++trav;
+            H h;
+            u32 leaf = select_leaf(h);
+            if (st.status != ST_PLAYING) return;
+            int player = META_PLAYER(h.meta);
+            if (META_TERMINAL(h.meta)) {
+                u32 wn = META_WINNER(h.meta);
+                float value = (wn == WINNER_NONE) ? 0.0f : ((int)wn - 1 == player ? 1.0f : -1.0f);
+                backup(leaf, player, value);
+                st.leaves_terminal += 1;
+                continue;
+            } else if (h.meta & META_EVALUATED) {
+                expand(leaf, h.meta);
+                backup(leaf, player, h.net_value);
+                st.leaves_gray += 1;
+                continue;
+            } else {
+                if (lane == 0) p.q_leaf[(size_t)tree * p.max_queue + nq] = leaf;
+                ++nq;
+                st.leaves_empty += 1;
+            }
+            if (nq >= p.max_queue) break;
+        }
+        st.traversals += trav;
+        st.sims += trav;
+        st.n_queued = nq;
+        __syncwarp();
+        for (int q = 0; q < nq; ++q) {
+            int s = p.use_sym ? rng_uniform_int(rng, 0, G::NSYM - 1) : 0;
+            if (lane == 0) p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s;
+            if (p.evaluator == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)tree * p.max_queue + q);
+        }
+        st.evals += nq;
+        __syncwarp();
+    }
+
+    // ---- network input planes of a leaf under symmetry s (networks/GridNetwork.hpp:72-97) ----
+    __device__ void encode_leaf(u32 unit, int s, size_t slot) {
+        constexpr int PLANES = 2 * G::HISTORY + 1;
+        float* out = p.nn_in + slot * PLANES * G::CELLS;
+        u32 meta = *HL<W>::meta_ptr(slab + unit);
+        int player = META_PLAYER(meta);
+        int inv = sym_inverse<G>(s);
+        for (int t = 0; t < G::HISTORY; ++t) {
+            Bits<W> b0, b1;
+            bool valid = history_board(unit, t, b0, b1);
+            const Bits<W>& own = player == 0 ? b0 : b1;
+            const Bits<W>& opp = player == 0 ? b1 : b0;
+            for (int to = lane; to < G::CELLS; to += 32) {
+                int from = sym_cell<G>(inv, to);
+                out[(2 * t) * G::CELLS + to] = (valid && own.test(from)) ? 1.0f : 0.0f;
+                out[(2 * t + 1) * G::CELLS + to] = (valid && opp.test(from)) ? 1.0f : 0.0f;
+            }
+        }
+        for (int to = lane; to < G::CELLS; to += 32) out[(PLANES - 1) * G::CELLS + to] = player == 0 ? 1.0f : 0.0f;
+    }
+
+    // symmetrised bitboard: bit f_s(i) of the result = bit i of x
+    __device__ Bits<W> sym_bits(const Bits<W>& x, int s) {
+        int inv = sym_inverse<G>(s);
+        Bits<W> r;
+        for (int base = 0; base < G::CELLS; base += 32) {
+            int to = base + lane;
+            bool bit = to < G::CELLS && x.test(sym_cell<G>(inv, to));
+            u32 bal = __ballot_sync(FULL, bit);
+            r = r | from_ballot(bal, base);
+        }
+        return r;
+    }
+
+    // hash of the symmetrised input state (HashNet, shared definition with the oracle)
+    __device__ unsigned long long state_hash(u32 unit, int player, int s) {
+        unsigned long long h = hashnet_seed(player);
+        for (int t = 0; t < G::HISTORY; ++t) {
+            Bits<W> b0, b1;
+            if (!history_board(unit, t, b0, b1)) break;
+            Bits<W> own = sym_bits(player == 0 ? b0 : b1, s), opp = sym_bits(player == 0 ? b1 : b0, s);
+            h = hash_mix(h ^ own.word(0));
+            h = hash_mix(h ^ (W == 2 ? own.word(W - 1) : 0ULL));
+            h = hash_mix(h ^ opp.word(0));
+            h = hash_mix(h ^ (W == 2 ? opp.word(W - 1) : 0ULL));
+        }
+        return h;
+    }
+
+    // ---- INetwork::evaluate for one leaf + inverse symmetry + UCTNode::addNetworkOutput ----
+    // Policy entries live in the SYMMETRISED frame but are masked with the leaf's
+    // un-symmetrised mask (uct/UCTTree.hpp:136-149, networks/GridNetwork.hpp:117-125:
+    // reference quirk Q3), then mapped back with the inverse symmetry.
+    __device__ void evaluate_leaf(u32 unit, H& h, int s, size_t slot) {
+        const int n = META_NLEGAL(h.meta);
+        const int player = META_PLAYER(h.meta);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        float value = 0.0f;
+        for (int i = lane; i < G::ACTIONS; i += 32) sm.pol[i] = 0.0f;
+        __syncwarp();
+        if (p.evaluator == SPRL_EVAL_UNIFORM) {             // networks/RandomNetwork.hpp:21-49
+            float uniform = 1.0f / (float)n;
+            for (int base = 0; base < n; base += 32) {
+                int k = base + lane;
+                if (k < n) sm.pol[legal_action<G>(pos, k)] = uniform;
+            }
+            __syncwarp();
+        } else {
+            unsigned long long hh = 0;
+            if (p.evaluator == SPRL_EVAL_HASHNET) { hh = state_hash(unit, player, s); value = hashnet_value(hh); }
+            else value = p.nn_value[slot];
+            for (int base = 0; base < n; base += 32) {
+                int k = base + lane;
+                if (k < n) {
+                    int i = legal_action<G>(pos, k);        // mask index == policy index (symmetrised frame)
+                    sm.pol[i] = (p.evaluator == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
+                                                                    : det_expf(p.nn_logits[slot * G::ACTIONS + i]);
+                }
+            }
+            __syncwarp();
+            float sum = 0.0f;                                // GameActionDist::sum, ascending index
+            for (int k = 0; k < n; ++k) sum += sm.pol[legal_action<G>(pos, k)];
+            __syncwarp();
+            if (sum == 0.0f) {
+                float uniform = 1.0f / (float)n;
+                for (int base = 0; base < n; base += 32) { int k = base + lane; if (k < n) sm.pol[legal_action<G>(pos, k)] = uniform; }
+            } else {
+                float inv = 1.0f / sum;                      // operator/(dist, float) = multiply by the reciprocal
+                for (int base = 0; base < n; base += 32) {
+                    int k = base + lane;
+                    if (k < n) { int i = legal_action<G>(pos, k); sm.pol[i] = sm.pol[i] * inv; }
+                }
+            }
+            __syncwarp();
+        }
+        // inverse symmetry: prior of action a = policy[f_s(a)]
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) {
+                int a = legal_action<G>(pos, k);
+                float prior = sm.pol[p.use_sym ? sym_action<G>(s, a) : a];
+                reinterpret_cast<float*>(slab + unit + HDR + k)[0] = prior;
+            }
+        }
+        h.net_value = value;
+        h.meta |= META_EVALUATED;
+        if (lane == 0) { *HL<W>::value_ptr(slab + unit) = value; *HL<W>::meta_ptr(slab + unit) = h.meta; }
+        __syncwarp();
+    }
+
+    // ---- UCTTree::evaluateAndBackpropLeaves (uct/UCTTree.hpp:154-183) ----
+    __device__ void apply_leaves() {
+        for (int q = 0; q < st.n_queued; ++q) {
+            size_t slot = (size_t)tree * p.max_queue + q;
+            u32 leaf = p.q_leaf[slot];
+            int s = p.q_sym[slot];
+            H h;
+            HL<W>::load(slab + leaf, h);
+            if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, slot);
+            if (!(h.meta & META_EXPANDED)) expand(leaf, h.meta);
+            backup(leaf, META_PLAYER(h.meta), h.net_value);
+        }
+        st.n_queued = 0;
+    }
+
+    // ---- copies the subtree below src unit `c` into the other slab (UCTTree::advanceDecision,
+    //      pruneChildrenExcept + clearSubtree, uct/UCTTree.hpp:197-210,283-298) ----
+    // Breadth-first, so parents precede children and siblings end up adjacent.  Every
+    // copied edge restarts with W = N = 0 and every node un-expanded; cached evaluations
+    // (netP, net_value, evaluated bit) are kept.
+    __device__ bool compact_into(uint4* dst, u32 c, float own_w, float own_n, u32& out_units) {
+        if (lane == 0) dst[0] = make_uint4(0u, __float_as_uint(own_w), __float_as_uint(own_n), 0u);
+        H h;
+        HL<W>::load(slab + c, h);
+        h.parent = 0; h.own_edge = 0; h.meta &= ~META_EXPANDED;
+        int n = META_NLEGAL(h.meta);
+        if (lane < HDR) HL<W>::store_unit(dst + ROOT_UNIT, lane, h);
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) { uint4 e = slab[c + HDR + k]; dst[ROOT_UNIT + HDR + k] = make_uint4(e.x, 0u, 0u, e.w); }
+        }
+        u32 alloc = ROOT_UNIT + HDR + n, scan = ROOT_UNIT;
+        __syncwarp();
+        while (scan < alloc) {
+            u32 meta = *HL<W>::meta_ptr(dst + scan);
+            int nn = META_NLEGAL(meta);
+            for (int base = 0; base < nn; base += 32) {
+                int k = base + lane;
+                u32 src_child = 0, ew = 0, size = 0;
+                H ch;
+                if (k < nn) {
+                    ew = dst[scan + HDR + k].w;
+                    src_child = EDGE_CHILD(ew);
+                    if (src_child) {
+                        HL<W>::load(slab + src_child, ch);
+                        size = HDR + META_NLEGAL(ch.meta);
+                    }
+                }
+                u32 incl = size;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                u32 total = __shfl_sync(FULL, incl, 31);
+                if (alloc + total + SLAB_SLACK > p.cap_units) return false;
+                if (src_child) {
+                    u32 nu = alloc + incl - size;
+                    ch.parent = scan; ch.own_edge = scan + HDR + k; ch.meta &= ~META_EXPANDED;
+                    for (int i = 0; i < HDR; ++i) HL<W>::store_unit(dst + nu, i, ch);
+                    int cn = META_NLEGAL(ch.meta);
+                    for (int j = 0; j < cn; ++j) { uint4 e = slab[src_child + HDR + j]; dst[nu + HDR + j] = make_uint4(e.x, 0u, 0u, e.w); }
+                    reinterpret_cast<u32*>(dst + scan + HDR + k)[3] = (ew & 0xff000000u) | nu;
+                }
+                alloc += total;
+                __syncwarp();
+            }
+            scan += HDR + nn;
+        }
+        out_units = alloc;
+        return true;
+    }
+
+    // ---- per-move finalisation of selfPlay (selfplay/SelfPlay.hpp:111-146) ----
+    __device__ void finalize_move() {
+        H h;
+        HL<W>::load(slab + ROOT_UNIT, h);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        const int n = META_NLEGAL(h.meta);
+        if (st.move_count >= p.max_moves) { st.status = ST_ERR_MOVES; return; }
+        const size_t ri = rec_index();
+        uint4 dummy = slab[0];
+        // visits into a dense action vector
+        for (int i = lane; i < G::ACTIONS; i += 32) sm.pol[i] = 0.0f;
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) {
+                uint4 e = slab[ROOT_UNIT + HDR + k];
+                int a = (int)EDGE_ACTION(e.w);
+                sm.pol[a] = __uint_as_float(e.z);
+                if (p.record_stats) {
+                    p.rec_N[ri * G::ACTIONS + a] = __uint_as_float(e.z);
+                    p.rec_W[ri * G::ACTIONS + a] = __uint_as_float(e.y);
+                    p.rec_P[ri * G::ACTIONS + a] = p.add_noise ? p.root_p[(size_t)tree * G::ACTIONS + k] : __uint_as_float(e.x);
+                }
+            }
+        }
+        __syncwarp();
+        if (p.record_stats && lane == 0) {
+            p.rec_root_W[ri] = __uint_as_float(dummy.y);
+            p.rec_root_N[ri] = __uint_as_float(dummy.z);
+            p.rec_trav[ri] = st.traversals;
+        }
+        // pdf = visits / sum; pdf = pow(pdf, e); pdf = pdf / sum; cdf = cumsum(pdf) / last
+        float sum = 0.0f;
+        for (int k = 0; k < n; ++k) sum += sm.pol[legal_action<G>(pos, k)];
+        float inv = 1.0f / sum;
+        const float ex = st.move_count < 15 ? 0.98f : 10.0f;       // constants.hpp:8-10
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) { int a = legal_action<G>(pos, k); sm.pol[a] = det_powf(sm.pol[a] * inv, ex); }
+        }
+        __syncwarp();
+        sum = 0.0f;
+        for (int k = 0; k < n; ++k) sum += sm.pol[legal_action<G>(pos, k)];
+        inv = 1.0f / sum;
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) {
+            int k = base + lane;
+            if (k < n) { int a = legal_action<G>(pos, k); sm.pol[a] = sm.pol[a] * inv; }
+        }
+        __syncwarp();
+        float run = 0.0f;
+        for (int k = 0; k < n; ++k) {
+            run = run + sm.pol[legal_action<G>(pos, k)];
+            if (lane == 0) sm.aux[k] = run;
+        }
+        const float inv_last = 1.0f / run;
+        __syncwarp();
+        // record the sample source: position, mover, pdf
+        for (int i = lane; i < G::ACTIONS; i += 32) p.rec_pdf[ri * G::ACTIONS + i] = sm.pol[i];
+        if (lane == 0) {
+            for (int w = 0; w < W; ++w) {
+                p.rec_board[ri * 2 * W + w] = h.b0.word(w);
+                p.rec_board[ri * 2 * W + W + w] = h.b1.word(w);
+            }
+            p.rec_player[ri] = (unsigned char)pos.player;
+        }
+        // Random::SampleCDF (utils/random.cpp:86-98)
+        float e;
+        do { e = rng_unit_f32(rng); } while (e == 0.0f);
+        const float x = (run * inv_last) * e;
+        int ksel = n - 1;
+        for (int k = n - 1; k >= 0; --k) if (sm.aux[k] * inv_last >= x) ksel = k;
+        const int action = legal_action<G>(pos, ksel);
+        if (p.record_stats && lane == 0) p.rec_action[ri] = action;
+        __syncwarp();
+
+        // UCTTree::advanceDecision
+        const u32 edge_unit = ROOT_UNIT + HDR + ksel;
+        uint4 es = slab[edge_unit];
+        u32 child = EDGE_CHILD(es.w);
+        float own_w = __uint_as_float(es.y), own_n = __uint_as_float(es.z);
+        if (child == 0) {
+            P cp;
+            make_child_pos(pos, ROOT_UNIT, action, cp);
+            u32 need = HDR + (cp.terminal ? 0u : (u32)cp.n_legal());
+            if (st.n_units + need + SLAB_SLACK > p.cap_units) { st.status = ST_ERR_CAPACITY; return; }
+            child = st.n_units;
+            st.n_units += need;
+            H ch;
+            write_node(slab, child, cp, ROOT_UNIT, edge_unit, ch);
+            own_w = (p.init_q == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
+            __syncwarp();
+        }
+        if (st.n_units > st.high_water) st.high_water = st.n_units;
+        uint4* dst = slab_ptr(st.slab ^ 1u);
+        u32 units = 0;
+        if (!compact_into(dst, child, own_w, own_n, units)) { st.status = ST_ERR_CAPACITY; return; }
+        st.slab ^= 1u;
+        slab = dst;
+        st.n_units = units;
+        st.traversals = 0;
+        st.move_count += 1;
+        st.moves += 1;
+        st.n_queued = 0;
+        __syncwarp();
+
+        u32 rmeta = *HL<W>::meta_ptr(slab + ROOT_UNIT);
+        if (META_TERMINAL(rmeta)) {
+            // game over: the outcome of every recorded move is filled in by the sample writer
+            if (lane == 0) {
+                p.rec_moves[st.game_index] = st.move_count;
+                p.rec_winner[st.game_index] = (unsigned char)META_WINNER(rmeta);
+                p.rec_draws[st.game_index] = rng.ctr;
+            }
+            st.games += 1;
+            st.game_index += p.n_slots;                  // static striding: game -> slot is deterministic
+            if (st.game_index < p.num_games) init_game();
+            else { st.status = ST_DONE; }
+        }
+    }
+};
+
+// ---- kernels -------------------------------------------------------------------------------------
+constexpr int WARPS_PER_BLOCK = 4;
+
+template <class G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) {
+    __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n_slots) return;
+    TreeWarp<G> t(p, warp, lane, scratch[threadIdx.x >> 5]);
+    t.st.game_index = warp;
+    t.st.status = ST_IDLE;
+    t.st.n_queued = 0;
+    if (t.st.game_index < p.num_games) { t.st.status = ST_PLAYING; t.init_game(); }
+    else { t.st.status = ST_DONE; }
+    t.save();
+}
+
+template <class G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_round(EngineParams p) {
+    __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n_slots) return;
+    if (p.trees[warp].status != ST_PLAYING) return;
+    TreeWarp<G> t(p, warp, lane, scratch[threadIdx.x >> 5]);
+    for (int iter = 0; iter < p.rounds_per_launch; ++iter) {
+        if (t.st.n_queued > 0) t.apply_leaves();
+        if (t.st.traversals >= p.sims) t.finalize_move();
+        if (t.st.status != ST_PLAYING) break;
+        t.search_batch();
+        if (t.st.status != ST_PLAYING) break;
+        if (p.evaluator == SPRL_EVAL_EXTERNAL) break;
+    }
+    if (t.st.status != ST_PLAYING && lane == 0) atomicAdd(&p.counters[t.st.status == ST_DONE ? 0 : 1], 1ULL);
+    t.save();
+}
+
+// ---- sample writer: selfPlay's symmetrised samples (selfplay/SelfPlay.hpp:86-96,127-136,
+//      148-189) embedded as in runWorker (selfplay/GridWorker.hpp:146-196) ----
+// One block per recorded move; writes S consecutive rows of states / distributions / outcomes.
+template <class G>
+__global__ void k_emit(EngineParams p, const long long* __restrict__ game_row0, int S,
+                       float* __restrict__ states, float* __restrict__ dists, float* __restrict__ outcomes) {
+    constexpr int W = G::W, PLANES = 2 * G::HISTORY + 1, ROW = PLANES * G::CELLS;
+    const long long g = blockIdx.x / p.max_moves;
+    const int m = (int)(blockIdx.x - g * p.max_moves);
+    if (m >= p.rec_moves[g]) return;
+    const size_t ri = (size_t)g * p.max_moves + m;
+    const int player = p.rec_player[ri];
+    const unsigned char wn = p.rec_winner[g];
+    const float outcome = (wn == WINNER_NONE) ? 0.0f : ((int)wn - 1 == player ? 1.0f : -1.0f);
+    const long long row0 = game_row0[g] + (long long)m * S;
+    for (int idx = threadIdx.x; idx < S * ROW; idx += blockDim.x) {
+        int s = idx / ROW, rem = idx - s * ROW, plane = rem / G::CELLS, to = rem - plane * G::CELLS;
+        float v;
+        if (plane == PLANES - 1) v = player == 0 ? 1.0f : 0.0f;
+        else {
+            int t = plane >> 1, which = plane & 1;       // 0: mover's stones, 1: opponent's
+            v = 0.0f;
+            if (t <= m) {
+                const unsigned long long* rb = p.rec_board + (ri - t) * 2 * W;
+                int colour = which == 0 ? player : 1 - player;
+                int from = S > 1 ? sym_cell<G>(sym_inverse<G>(s), to) : to;
+                v = ((rb[colour * W + (from >> 6)] >> (from & 63)) & 1ULL) ? 1.0f : 0.0f;
+            }
+        }
+        states[(row0 + s) * ROW + rem] = v;
+    }
+    for (int idx = threadIdx.x; idx < S * G::ACTIONS; idx += blockDim.x) {
+        int s = idx / G::ACTIONS, j = idx - s * G::ACTIONS;
+        int i = S > 1 ? sym_action<G>(sym_inverse<G>(s), j) : j;    // new[f_s(i)] = old[i]
+        dists[(row0 + s) * G::ACTIONS + j] = p.rec_pdf[ri * G::ACTIONS + i];
+    }
+    if (threadIdx.x < S) outcomes[row0 + threadIdx.x] = outcome;
+}
+
+// ---- launchers used by engine.cu ---------------------------------------------------------------
+template <class G> static void launch_begin(const EngineParams& p, cudaStream_t s) {
+    k_begin<G><<<ceil_div(p.n_slots, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(p);
+}
+template <class G> static void launch_round(const EngineParams& p, cudaStream_t s) {
+    k_round<G><<<ceil_div(p.n_slots, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(p);
+}
+template <class G> static void launch_emit(const EngineParams& p, const long long* row0, int S, float* st, float* di,
+                                           float* ou, cudaStream_t s) {
+    k_emit<G><<<(unsigned)(p.num_games * p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
+}
+
+#define GAME_SWITCH(game, STMT)                                   \
+    switch (game) {                                               \
+    case SPRL_GAME_OTHELLO: { typedef Othello G; STMT; break; }   \
+    case SPRL_GAME_C4: { typedef ConnectFour G; STMT; break; }    \
+    case SPRL_GAME_GO7: { typedef Go<7> G; STMT; break; }         \
+    case SPRL_GAME_GO9: { typedef Go<9> G; STMT; break; }         \
+    default: break;                                               \
+    }
+
+void search_launch_begin(int game, const EngineParams& p, cudaStream_t s) { GAME_SWITCH(game, launch_begin<G>(p, s)); }
+void search_launch_round(int game, const EngineParams& p, cudaStream_t s) { GAME_SWITCH(game, launch_round<G>(p, s)); }
+void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
+                        cudaStream_t s) { GAME_SWITCH(game, launch_emit<G>(p, row0, S, st, di, ou, s)); }
+int search_header_units(int game) { return (game == SPRL_GAME_GO9) ? 5 : 3; }
+
+}  // namespace sprl

@@ -1,0 +1,302 @@
+"""Host-side driver of the self-play engine (Python plumbing over the C ABI).
+
+Mirrors the call shapes of the reference's driver layer so that tests and
+benchmarks read like the reference's own code:
+
+    run_iteration(...)  ~ SPRL::runIteration   (cpp/src/selfplay/SelfPlay.hpp:203-248)
+    run_worker(...)     ~ SPRL::runWorker      (cpp/src/selfplay/GridWorker.hpp:84-198)
+    wait_model_path     ~ SPRL::waitModelPath  (cpp/src/selfplay/GridWorker.hpp:35-55)
+
+All compute happens in libsprl_b200.so on the GPU; torch is used only to own
+device buffers / streams and to run the reference's traced network.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+
+from . import capi
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- environment only
+def env_perft(game, depth, device=0):
+    """Leaf-count perft from the start position; returns (count, device milliseconds)."""
+    count, ms = C.c_uint64(), C.c_float()
+    capi.check(capi.load().sprl_env_perft(device, game, depth, C.byref(count), C.byref(ms)))
+    return count.value, ms.value
+
+
+def env_rollout(game, seed, first_game, ngames, record=False, device=0):
+    """Random playouts, one GPU thread per game.  With record=True returns the same
+    per-position trace the oracle's rollout produces."""
+    gi = capi.game_info(game)
+    steps = np.zeros(ngames, np.int32)
+    final_winner = np.zeros(ngames, np.int8)
+    total, ms = C.c_int64(), C.c_float()
+    out = dict(game_steps=steps, final_winner=final_winner)
+    if record:
+        cap = ngames * (gi.max_plies + 1)
+        tr = dict(cells=np.zeros((cap, gi.cells), np.int8), player=np.zeros(cap, np.int8),
+                  terminal=np.zeros(cap, np.int8), winner=np.zeros(cap, np.int8),
+                  mask=np.zeros((cap, gi.actions), np.int8), action=np.zeros(cap, np.int32))
+        capi.check(capi.load().sprl_env_rollout(device, game, seed, first_game, ngames, _ptr(steps), _ptr(final_winner),
+                                                cap, _ptr(tr["cells"]), _ptr(tr["player"]), _ptr(tr["terminal"]),
+                                                _ptr(tr["winner"]), _ptr(tr["mask"]), _ptr(tr["action"]),
+                                                C.byref(total), C.byref(ms)))
+        for k, v in tr.items():
+            out[k] = v[:total.value]
+    else:
+        capi.check(capi.load().sprl_env_rollout(device, game, seed, first_game, ngames, _ptr(steps), _ptr(final_winner),
+                                                0, None, None, None, None, None, None, C.byref(total), C.byref(ms)))
+    out["total_positions"] = total.value
+    out["elapsed_ms"] = ms.value
+    return out
+
+
+def env_step(game, cells, player, action, device=0):
+    gi = capi.game_info(game)
+    cells = np.ascontiguousarray(cells, np.int8).reshape(-1, gi.cells)
+    n = cells.shape[0]
+    player = np.ascontiguousarray(player, np.int8)
+    action = np.ascontiguousarray(action, np.int32)
+    out = dict(cells=np.zeros((n, gi.cells), np.int8), player=np.zeros(n, np.int8), terminal=np.zeros(n, np.int8),
+               winner=np.zeros(n, np.int8), mask=np.zeros((n, gi.actions), np.int8))
+    capi.check(capi.load().sprl_env_step(device, game, n, _ptr(cells), _ptr(player), _ptr(action), _ptr(out["cells"]),
+                                         _ptr(out["player"]), _ptr(out["terminal"]), _ptr(out["winner"]), _ptr(out["mask"])))
+    return out
+
+
+# ---------------------------------------------------------------------- the engine
+class Engine:
+    """One self-play engine = `num_slots` concurrent trees on one GPU."""
+
+    def __init__(self, game, evaluator=capi.EVAL_UNIFORM, device=0, **overrides):
+        self.lib = capi.load()
+        self.cfg = capi.default_config(game)
+        self.cfg.device = device
+        self.cfg.evaluator = evaluator
+        for k, v in overrides.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError(f"unknown engine option {k}")
+            setattr(self.cfg, k, v)
+        self.gi = capi.game_info(game)
+        self.handle = C.c_void_p()
+        capi.check(self.lib.sprl_create(C.byref(self.cfg), C.byref(self.handle)))
+        self.samples_per_move = self.gi.nsym if self.cfg.use_sym else 1
+        self._nn = None
+
+    def close(self):
+        if self.handle:
+            self.lib.sprl_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- low level ------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        capi.check(self.lib.sprl_set_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    @property
+    def eval_batch(self):
+        return self.lib.sprl_eval_batch(self.handle)
+
+    def begin_iteration(self, first_game, num_games):
+        capi.check(self.lib.sprl_begin_iteration(self.handle, first_game, num_games))
+
+    def round(self):
+        capi.check(self.lib.sprl_round(self.handle))
+
+    def poll(self):
+        playing, failed = C.c_int64(), C.c_int64()
+        capi.check(self.lib.sprl_poll(self.handle, C.byref(playing), C.byref(failed)))
+        return playing.value, failed.value
+
+    def stats(self):
+        s = capi.Stats()
+        capi.check(self.lib.sprl_get_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        capi.check(self.lib.sprl_reset_stats(self.handle))
+
+    # -- evaluator plumbing -----------------------------------------------------------
+    def attach_network(self, module, use_cuda_graph=True):
+        """Attach the reference's traced network (a torch.jit module on this GPU).  Leaf
+        planes are written by the search kernel straight into the tensor the module reads,
+        and its outputs are read in place by the next search launch: no host round trip."""
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        B, gi = self.eval_batch, self.gi
+        nn = dict(module=module, graph=None, torch=torch, dev=dev)
+        nn["inp"] = torch.zeros((B, 2 * gi.history + 1, gi.rows, gi.cols), dtype=torch.float32, device=dev)
+        nn["logits"] = torch.zeros((B, gi.actions), dtype=torch.float32, device=dev)
+        nn["value"] = torch.zeros((B,), dtype=torch.float32, device=dev)
+        capi.check(self.lib.sprl_bind_eval_buffers(self.handle, C.c_void_p(nn["inp"].data_ptr()),
+                                                    C.c_void_p(nn["logits"].data_ptr()), C.c_void_p(nn["value"].data_ptr())))
+        nn["use_graph"] = use_cuda_graph
+        self._nn = nn
+
+    def _forward(self):
+        nn = self._nn
+        torch = nn["torch"]
+        with torch.no_grad():
+            logits, value = nn["module"](nn["inp"])
+            nn["logits"].copy_(logits)
+            nn["value"].copy_(value.reshape(-1))
+
+    def _round_with_network(self):
+        self.round()
+        self._forward()
+
+    def _capture(self):
+        """Captures [search launch -> network forward -> output copy] as one CUDA graph."""
+        nn = self._nn
+        torch = nn["torch"]
+        side = torch.cuda.Stream(device=nn["dev"])
+        side.wait_stream(torch.cuda.current_stream(nn["dev"]))
+        with torch.cuda.stream(side):
+            for _ in range(3):                      # warm up cuDNN autotune / lazy init outside capture
+                self._forward()
+        torch.cuda.current_stream(nn["dev"]).wait_stream(side)
+        torch.cuda.synchronize(nn["dev"])
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
+            self._round_with_network()
+        self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
+        nn["graph"] = graph
+
+    # -- runIteration -------------------------------------------------------------------
+    def run_iteration(self, num_games, first_game=0, collect=True, poll_every=None):
+        """Plays games first_game .. first_game+num_games-1 to the end.  Returns
+        (states [n,2H+1,R,C], distributions [n,A], outcomes [n]) as numpy arrays in the
+        reference's order when collect=True."""
+        if self.cfg.evaluator == capi.EVAL_EXTERNAL:
+            if self._nn is None:
+                raise capi.SprlError(capi.SPRL_E_STATE, "attach_network() first")
+            nn = self._nn
+            torch = nn["torch"]
+            with torch.cuda.device(nn["dev"]):
+                self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
+                self.begin_iteration(first_game, num_games)
+                if nn["use_graph"] and nn["graph"] is None:
+                    self._capture()
+                every = poll_every or 64
+                while True:
+                    for _ in range(every):
+                        if nn["graph"] is not None:
+                            nn["graph"].replay()
+                        else:
+                            self._round_with_network()
+                    playing, failed = self.poll()
+                    if failed:
+                        self._raise_slot_failure()
+                    if playing == 0:
+                        break
+        else:
+            capi.check(self.lib.sprl_run_iteration(self.handle, first_game, num_games, None, None))
+        return self.collect_samples() if collect else None
+
+    def _raise_slot_failure(self):
+        # run_iteration's C path formats the message; reuse it through a zero-round call
+        raise capi.SprlError(capi.SPRL_E_CAPACITY, "a tree slot ran out of node units or moves; raise units_per_tree")
+
+    def iteration_counts(self):
+        m, s = C.c_int64(), C.c_int64()
+        capi.check(self.lib.sprl_iteration_counts(self.handle, C.byref(m), C.byref(s)))
+        return m.value, s.value
+
+    def collect_samples(self):
+        gi = self.gi
+        _, n = self.iteration_counts()
+        states = np.empty((n, 2 * gi.history + 1, gi.rows, gi.cols), np.float32)
+        dists = np.empty((n, gi.actions), np.float32)
+        outcomes = np.empty((n,), np.float32)
+        got = C.c_int64()
+        capi.check(self.lib.sprl_collect_samples(self.handle, n, _ptr(states), _ptr(dists), _ptr(outcomes), C.byref(got)))
+        assert got.value == n
+        return states, dists, outcomes
+
+    def move_stats(self, num_games):
+        """Per-move root statistics of the last iteration (engine created with record_stats=1)."""
+        gi = self.gi
+        m, _ = self.iteration_counts()
+        A = gi.actions
+        r = dict(move_N=np.zeros((m, A), np.float32), move_W=np.zeros((m, A), np.float32),
+                 move_P=np.zeros((m, A), np.float32), move_root_N=np.zeros(m, np.float32),
+                 move_root_W=np.zeros(m, np.float32), move_action=np.zeros(m, np.int32),
+                 move_traversals=np.zeros(m, np.int32), move_player=np.zeros(m, np.int8),
+                 game_moves=np.zeros(num_games, np.int32), game_rng_draws=np.zeros(num_games, np.uint64))
+        got = C.c_int64()
+        capi.check(self.lib.sprl_move_stats(self.handle, m, _ptr(r["move_N"]), _ptr(r["move_W"]), _ptr(r["move_P"]),
+                                            _ptr(r["move_root_N"]), _ptr(r["move_root_W"]), _ptr(r["move_action"]),
+                                            _ptr(r["move_traversals"]), _ptr(r["move_player"]), _ptr(r["game_moves"]),
+                                            _ptr(r["game_rng_draws"]), C.byref(got)))
+        return r
+
+
+def write_npy(path, array):
+    """npy::write_npy of the reference (float32, C order), through the library's writer."""
+    a = np.ascontiguousarray(array, np.float32)
+    shape = (C.c_uint64 * max(a.ndim, 1))(*a.shape)
+    capi.check(capi.load().sprl_write_npy_f32(path.encode(), _ptr(a), shape, a.ndim))
+
+
+def wait_model_path(iteration, run_name, interval=30.0, settle=5.0, root="."):
+    """SPRL::waitModelPath: "random" for iteration -1, else block until the controller's
+    traced model file exists (data/models/<run>/traced_<run>_iteration_<i>.pt)."""
+    if iteration == -1:
+        return "random"
+    path = os.path.join(root, "data", "models", run_name, f"traced_{run_name}_iteration_{iteration}.pt")
+    while not os.path.exists(path):
+        print(f"Spinning on traced model from iteration {iteration}...", flush=True)
+        time.sleep(interval)
+    time.sleep(settle)
+    return path
+
+
+def run_worker(run_name, save_dir, game, num_iters, init_games, init_sims, init_batch, init_queue,
+               games, sims, batch, queue, dir_eps, dir_alpha, num_slots=None, device=0, seed=0,
+               load_model=None, root=".", wait_interval=30.0, settle=5.0, first_game_of_iter=None):
+    """SPRL::runWorker: per iteration wait for the controller's model, play the games, write
+    <save_dir>/<run>_iteration_<i>_{states,distributions,outcomes}.npy.  Iteration 0 uses the
+    uniform evaluator (the reference passes RandomNetwork as initialNetwork, OTHWorker.cpp:51)
+    and the init* search parameters.  (The reference self-initialises maxBatchSize/maxQueueSize
+    for iter > 0, GridWorker.hpp:120-121, which is undefined behaviour; the intended values are used.)"""
+    os.makedirs(save_dir, exist_ok=True)
+    for it in range(num_iters):
+        print(f"Starting iteration {it}...", flush=True)
+        model_path = wait_model_path(it - 1, run_name, wait_interval, settle, root)
+        n_games = init_games if it == 0 else games
+        opts = dict(sims=init_sims if it == 0 else sims, max_batch=init_batch if it == 0 else batch,
+                    max_queue=init_queue if it == 0 else queue, dir_eps=dir_eps, dir_alpha=dir_alpha,
+                    num_slots=min(num_slots or n_games, n_games), max_games=n_games, seed=seed, device=device)
+        first = first_game_of_iter(it) if first_game_of_iter else it * max(init_games, games)
+        if model_path == "random":
+            print("Using initial network...", flush=True)
+            eng = Engine(game, capi.EVAL_UNIFORM, **opts)
+        else:
+            print("Using traced PyTorch network...", flush=True)
+            eng = Engine(game, capi.EVAL_EXTERNAL, **opts)
+            eng.attach_network(load_model(model_path))
+        with eng:
+            states, dists, outcomes = eng.run_iteration(n_games, first_game=first)
+        base = os.path.join(save_dir, f"{run_name}_iteration_{it}")
+        write_npy(base + "_states.npy", states)
+        write_npy(base + "_distributions.npy", dists)
+        write_npy(base + "_outcomes.npy", outcomes)
