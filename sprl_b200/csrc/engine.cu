@@ -143,10 +143,13 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (e->cfg.rounds_per_launch <= 0) e->cfg.rounds_per_launch = 8;
     const int hdr = search_header_units(cfg->game);
     if (e->cfg.units_per_tree <= 0) {
-        // a search adds at most one node per descent; the kept subtree is bounded in practice by a few
-        // searches' worth of nodes.  Average record = header + ~legal/2 edges.
-        int64_t avg = hdr + std::max(4, gi.actions / 3);
-        e->cfg.units_per_tree = std::max<int64_t>(4096, (int64_t)(cfg->sims + cfg->max_batch) * 4 * avg / 2);
+        // A search adds at most one node per descent and re-rooting keeps only the chosen subtree, so
+        // the live tree is bounded by sims / (1 - kept fraction); 6x covers kept fractions up to ~0.83
+        // (Connect Four with a uniform evaluator keeps the most).  A record = header + one edge per
+        // legal action; `typical` is a generous per-game average of the latter.
+        int typical = cfg->game == SPRL_GAME_OTHELLO ? 12 : (cfg->game == SPRL_GAME_C4 ? 7 : (cfg->game == SPRL_GAME_GO7 ? 45 : 75));
+        int64_t nodes = 6 * (int64_t)(cfg->sims + cfg->max_batch) + 64;
+        e->cfg.units_per_tree = std::max<int64_t>(4096, nodes * (hdr + typical));
     }
     if (e->cfg.units_per_tree > (1 << 24) - 1) e->cfg.units_per_tree = (1 << 24) - 1;       // child index is 24 bits
     if (e->cfg.units_per_tree < 2 * (hdr + gi.actions) + SLAB_SLACK + 2) { delete e; return fail(SPRL_E_INVALID, "units_per_tree too small"); }
