@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play hot path (BASELINE.json: Othello 8x8, 400 sims/move,
+8-fold symmetrised, virtual-loss leaf batching 8/4).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU worker on the host cores
+
+A *step* of our arm is `--rounds` search rounds of `--slots` concurrent games in
+continuous play (a slot starts its next game when one ends): every round is one
+search launch over all trees (select / expand / backup / re-root kernels), one forward
+of the reference's traced fp32 network on the leaf batch those trees produced, and the
+application of its outputs in the next launch.  `value` is MCTS simulations per second,
+whole job, from device counters over exactly K timed steps; moves/s etc. ride along.
+`e2e` is the same metric through the public API with host buffers: each e2e step loads
+the network weights from pinned host memory, plays `--e2e-games` full games from the
+start position to the end, and copies the sample arrays back to the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIMS, MAX_BATCH, MAX_QUEUE, EPS, ALPHA = 400, 8, 4, 0.25, 0.3
+WORKLOAD = "othello8x8_selfplay_400sims_batch8_queue4_d4sym_net2x64_fp32"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots", type=int, default=8192, help="concurrent games per GPU")
+    ap.add_argument("--rounds", type=int, default=256, help="search rounds per step")
+    ap.add_argument("--e2e-games", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU work per reference step (bounded sample)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bytes_per_sim(D, L, e, planes_cells=192, A=65):
+    """Algorithmic HBM bytes of one simulation: D select levels that each read a
+    16 B node header + 16 B board pair + 4 B link and 12 B of P/W/N per legal child, the leaf's
+    virtual loss, one step + new node, the evaluator-side traffic of the fraction e of
+    simulations that need an evaluation, and the backup."""
+    return D * (16 + 12 * L + 4 + 16) + 16 + (16 + 16 + 8 + 16) + e * (4 * planes_cells + 4 * (A + 1) + 16 * L) + (D + 1) * 8
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sprl_b200 import capi
+    from sprl_b200 import selfplay as SP
+    from sprl_b200.network import make_network, trace_network, num_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False          # the reference evaluates in fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- the evaluator: the reference's network shape, random init, traced as the controller does
+    net = make_network("othello", seed=0)
+    n_params = num_parameters(net)
+    module = trace_network(net, dev)
+    flat_params = [p for p in module.parameters()] + [b for b in module.buffers()]
+    weight_bytes = sum(t.numel() * t.element_size() for t in flat_params)
+
+    def broadcast_weights(generation):
+        """New generation: rank 0 draws fresh random-init weights, NCCL broadcasts the flat
+        parameter + buffer vector; every rank updates its module in place."""
+        if rank == 0:
+            fresh = make_network("othello", seed=1000 + generation)
+            src = [p for p in fresh.parameters()] + [b for b in fresh.buffers()]
+            flat = torch.cat([t.detach().reshape(-1).float() for t in src]).to(dev)
+        else:
+            flat = torch.empty(sum(t.numel() for t in flat_params), device=dev)
+        if world > 1:
+            dist.broadcast(flat, 0)
+        at = 0
+        with torch.no_grad():
+            for t in flat_params:
+                n = t.numel()
+                t.copy_(flat[at:at + n].reshape(t.shape).to(t.dtype))
+                at += n
+
+    # ---- steady-state engine: continuous play, games sharded by id % world
+    games_cap = args.slots * 24
+    eng = SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=0, sims=SIMS, max_batch=MAX_BATCH,
+                    max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=args.slots, max_games=games_cap)
+    eng.set_game_stride(world)
+    eng.attach_network(module, use_cuda_graph=not args.no_graph)
+    broadcast_weights(0)
+    with torch.cuda.device(dev):
+        eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        eng.begin_iteration(rank, games_cap)
+        if not args.no_graph:
+            eng._capture()
+        graph = eng._nn["graph"]
+
+        def step():
+            for _ in range(args.rounds):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    eng._round_with_network()
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        eng.reset_stats()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        st = eng.stats()
+        playing, failed = eng.poll()
+        assert failed == 0 and playing == args.slots, (playing, failed)
+
+        # ---- roofline leg: the search launch alone, timed with events on its stream
+        n_probe = 64
+        eng.reset_stats()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
+        for a, b in evs:
+            a.record()
+            eng.round()
+            b.record()
+            eng._forward()
+        torch.cuda.synchronize(dev)
+        k_ms = sum(a.elapsed_time(b) for a, b in evs) / n_probe
+        pst = eng.stats()
+        nn_evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        nn_evs[0].record()
+        for _ in range(8):
+            eng._forward()
+        nn_evs[1].record()
+        torch.cuda.synchronize(dev)
+        nn_ms = nn_evs[0].elapsed_time(nn_evs[1]) / 8
+    eng.close()
+
+    # totals over ranks
+    tot = torch.tensor([st["sims"], st["moves"], st["evals"], st["games"]], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    sims, moves, evals, games = [float(x) for x in tot.tolist()]
+    ms = float(tmax.item())
+    value = sims / (ms / 1e3)
+
+    D = pst["depth_sum"] / max(1, pst["sims"])
+    L = pst["legal_sum"] / max(1, pst["nodes_visited"])
+    ef = pst["evals"] / max(1, pst["sims"])
+    bps = bytes_per_sim(D, L, ef)
+    sims_per_launch = pst["sims"] / n_probe
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bps * sims_per_launch / (k_ms / 1e3) / 1e9
+    roofline = {"kernel": "k_round<Othello>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
+                "select_depth": round(D, 3), "legal_per_node": round(L, 3), "evals_per_sim": round(ef, 4),
+                "sampled_launches": n_probe, "network_forward_ms": round(nn_ms, 4),
+                "search_share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
+
+    result = {
+        "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(value, 1), "unit": "sims/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sims_per_move": SIMS, "max_batch": MAX_BATCH, "max_queue": MAX_QUEUE,
+                   "slots_per_gpu": args.slots, "rounds_per_step": args.rounds, "network_params": n_params,
+                   "sharding": "game_id % world, no data collective; NCCL broadcast of weights per generation",
+                   "l2": "working set (tree slabs %.1f GB + leaf batch) exceeds the 126 MB L2" % (st["device_bytes"] / 1e9),
+                   "cuda_graph": not args.no_graph},
+        "moves_per_sec": round(moves / (ms / 1e3), 1), "evals_per_sec": round(evals / (ms / 1e3), 1),
+        "samples_per_sec": round(8 * moves / (ms / 1e3), 1), "games_finished": int(games),
+        "gpu_launches": int(args.steps * args.rounds * world),
+        "roofline": roofline, "clocks": clocks,
+    }
+
+    if not args.no_e2e:
+        e2e = run_e2e(args, local, module, flat_params, weight_bytes, barrier)     # every rank, on its own shard
+        agg = torch.tensor([e2e.pop("_sims"), e2e.pop("_moves")], dtype=torch.float64, device=dev)
+        tm = torch.tensor([e2e.pop("_ms")], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(agg)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e["value"] = round(float(agg[0]) / (float(tm) / 1e3), 1)
+        e2e["moves_per_sec"] = round(float(agg[1]) / (float(tm) / 1e3), 1)
+        e2e["ms_per_step"] = round(float(tm) / args.e2e_steps, 1)
+        result["e2e"] = e2e
+    if rank == 0 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(args, threads=1, seconds=args.ref_seconds)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+def run_e2e(args, local, module, flat_params, weight_bytes, barrier):
+    """Full iterations through the public API with host buffers: weights H2D from pinned
+    memory, run_iteration of full games, samples D2H."""
+    import numpy as np
+    import torch
+    from sprl_b200 import capi
+    from sprl_b200 import selfplay as SP
+    dev = torch.device("cuda", local)
+    host_weights = [t.detach().cpu().pin_memory() for t in flat_params]
+    G = args.e2e_games
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=1, sims=SIMS, max_batch=MAX_BATCH,
+                   max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=G, max_games=G) as eng:
+        eng.attach_network(module, use_cuda_graph=not args.no_graph)
+
+        def one(first):
+            with torch.no_grad():
+                for t, h in zip(flat_params, host_weights):
+                    t.copy_(h, non_blocking=True)
+            return eng.run_iteration(G, first_game=first)
+
+        # warm-up: a short iteration with the same engine (graph capture, cuDNN autotune)
+        one(0) if args.e2e_steps > 1 else eng.run_iteration(min(G, 64), first_game=0)
+        barrier()
+        eng.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d2h = 0
+        e0.record()
+        for i in range(args.e2e_steps):
+            states, dists, outcomes = one(10_000 * (i + 1))
+            d2h += states.nbytes + dists.nbytes + outcomes.nbytes
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        st = eng.stats()
+    return {"value": None, "unit": "sims/s", "h2d_bytes_per_step": int(weight_bytes),
+            "d2h_bytes_per_step": int(d2h / args.e2e_steps), "moves_per_sec": None,
+            "games_per_step_per_gpu": G, "steps": args.e2e_steps, "ms_per_step": None,
+            "note": "public API with host buffers: weights H2D from pinned memory, full games start to finish "
+                    "(incl. the tail where few games are left), samples D2H",
+            "_sims": float(st["sims"]), "_moves": float(st["moves"]), "_ms": float(ms)}
+
+
+# ----------------------------------------------------------------- reference / CPU baseline
+def ref_worker_path():
+    return os.path.join(ROOT, "oracle", "_ref", "ref_worker")
+
+
+def traced_model_file():
+    import torch
+    from sprl_b200.network import make_network, trace_network
+    path = os.path.join(tempfile.gettempdir(), f"sprl_bench_othello_{os.getpid()}.pt")
+    trace_network(make_network("othello", seed=0), "cpu").save(path)
+    return path
+
+
+def cpu_baseline(args, threads, seconds):
+    """Times the reference's CPU worker path (oracle/_ref/ref_worker: unmodified reference
+    sources + LibTorch on the CPU), `threads` single-threaded processes, on a bounded sample:
+    each process plays the first moves of its own games until about `seconds` of work."""
+    if not os.path.exists(ref_worker_path()):
+        return cpu_baseline_port(seconds)
+    model = traced_model_file()
+    # ~1,100 sims/s/core with this network: size the sample in moves
+    moves = max(2, int(seconds * 1100 / SIMS))
+    games = max(1, (moves + 29) // 30)
+    per_game = (moves + games - 1) // games
+    procs = []
+    t0 = time.time()
+    for i in range(threads):
+        procs.append(subprocess.Popen([ref_worker_path(), "othello", model, "0", str(1000 * i), str(games), str(SIMS),
+                                       str(MAX_BATCH), str(MAX_QUEUE), str(EPS), str(ALPHA), str(per_game)],
+                                      stdout=subprocess.PIPE, text=True))
+    outs = [json.loads(p.communicate()[0].strip().split("\n")[-1]) for p in procs]
+    wall = time.time() - t0
+    os.unlink(model)
+    sims = sum(o["sims"] for o in outs)
+    moves_done = sum(o["moves"] for o in outs)
+    slowest = max(o["seconds"] for o in outs)
+    return {"value": round(sims / slowest, 1), "unit": "sims/s", "cores": threads, "kind": "reference",
+            "moves_per_sec": round(moves_done / slowest, 2), "per_core": round(sims / slowest / threads, 1),
+            "sample": f"{threads} process(es) x first {per_game} moves of {games} game(s), {SIMS} sims/move, "
+                      f"traced 2x64 net on CPU (LibTorch, 1 thread each); {wall:.1f}s wall",
+            "cpu": cpu_model(), "host_cores": os.cpu_count()}
+
+
+def cpu_baseline_port(seconds):
+    """Fallback when oracle/_ref was not built: the plain-C oracle port, one thread."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py as O
+    from sprl_b200.network import make_network
+    torch.set_num_threads(1)
+    net = make_network("othello", seed=0)
+
+    def fn(x):
+        with torch.no_grad():
+            lg, v = net(torch.from_numpy(np.array(x)))
+        return lg.numpy(), v.numpy().reshape(-1)
+
+    t0 = time.time()
+    r = O.selfplay(O.OG_OTHELLO, O.OE_CALLBACK, 0, 0, 1, 100, MAX_BATCH, MAX_QUEUE, EPS, ALPHA, eval_fn=fn)
+    dt = time.time() - t0
+    return {"value": round(r["stats"]["total_traversals"] / dt, 1), "unit": "sims/s", "cores": 1, "kind": "port",
+            "sample": "1 game at 100 sims/move through the C oracle with the network on CPU via a Python callback"}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    total = args.steps + args.warmup
+    per_step = max(3.0, min(args.ref_seconds, 150.0 / max(1, total)))
+    vals, last = [], None
+    for i in range(total):
+        last = cpu_baseline(args, threads, per_step)
+        if i >= args.warmup:
+            vals.append(last)
+    sims_s = sum(v["value"] for v in vals) / len(vals)
+    moves_s = sum(v["moves_per_sec"] for v in vals) / len(vals)
+    out = {"impl": "reference", "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(sims_s, 1), "unit": "sims/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "ms_per_step": round(per_step * 1e3, 1),
+           "config": {"workload": WORKLOAD, "sims_per_move": SIMS, "max_batch": MAX_BATCH, "max_queue": MAX_QUEUE},
+           "moves_per_sec": round(moves_s, 2),
+           "cpu_baseline": {"value": round(sims_s, 1), "unit": "sims/s", "cores": threads, "kind": last["kind"], "sample": last["sample"],
+                            "cpu": last.get("cpu")},
+           "e2e": {"value": round(sims_s, 1), "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

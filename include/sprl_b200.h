@@ -133,6 +133,11 @@ int64_t sprl_eval_batch(const sprl_engine* e);
  * stream (seed, g), slot s plays games s, s+num_slots, ... one after the other. */
 int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games);
 
+/* Sharding across GPUs (one engine per rank): game i of an iteration uses stream id
+ * first_game + i * stride, so rank r of `world` plays ids r, r+world, ... with
+ * first_game = base + r and stride = world.  Default stride 1. */
+int sprl_set_game_stride(sprl_engine* e, uint64_t stride);
+
 /* Enqueues one search launch: apply the evaluations of the previous launch, finish
  * moves whose traversal budget is spent (sample, re-root, compact), then run the next
  * searchAndGetLeaves batch of every live tree.  Asynchronous, capturable in a CUDA graph. */

@@ -19,7 +19,7 @@ INITQ_ZERO, INITQ_PARENT = 0, 1
 EXPORTS = [
     "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
     "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
-    "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_begin_iteration", "sprl_round", "sprl_poll",
+    "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
     "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
 ]
@@ -79,6 +79,7 @@ def load():
     lib.sprl_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.sprl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.sprl_bind_eval_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sprl_set_game_stride.argtypes = [C.c_void_p, C.c_uint64]
     lib.sprl_begin_iteration.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     lib.sprl_round.argtypes = [C.c_void_p]
     lib.sprl_poll.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -165,6 +165,7 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     p.add_noise = cfg->add_noise; p.use_sym = cfg->use_sym; p.init_q = cfg->init_q;
     p.rounds_per_launch = (cfg->evaluator == SPRL_EVAL_EXTERNAL) ? 1 : e->cfg.rounds_per_launch;
     p.record_stats = cfg->record_stats;
+    p.game_stride = 1;
 
     const size_t S = (size_t)cfg->num_slots, MG = (size_t)e->cfg.max_games, MM = (size_t)gi.max_plies, A = (size_t)gi.actions;
     rc = e->alloc(&p.pool, S * 2 * p.cap_units, false);
@@ -212,6 +213,13 @@ int sprl_bind_eval_buffers(sprl_engine* e, float* d_in, const float* d_logits, c
     if (e->cfg.evaluator != SPRL_EVAL_EXTERNAL) return fail(SPRL_E_STATE, "engine was not created with SPRL_EVAL_EXTERNAL");
     if (!d_in || !d_logits || !d_value) return fail(SPRL_E_INVALID, "null evaluator buffer");
     e->p.nn_in = d_in; e->p.nn_logits = d_logits; e->p.nn_value = d_value;
+    return SPRL_OK;
+}
+
+int sprl_set_game_stride(sprl_engine* e, uint64_t stride) {
+    ENGINE_CHECK(e);
+    if (stride == 0) return fail(SPRL_E_INVALID, "stride must be positive");
+    e->p.game_stride = stride;
     return SPRL_OK;
 }
 

@@ -99,13 +99,29 @@ template <> struct Bits<2> {
     }
 };
 
+// k-th (0-based) set bit of a 32-bit word by popcount bisection; k must be < popcount.
+// (__fns is a software loop over the bits and dominated the search kernel's instruction count.)
+__host__ __device__ __forceinline__ int nth_set_bit32(u32 x, int k) {
+#ifdef __CUDA_ARCH__
+    int r = 0, c;
+    c = __popc(x & 0xffffu); if (k >= c) { k -= c; r += 16; x >>= 16; }
+    c = __popc(x & 0xffu);   if (k >= c) { k -= c; r += 8;  x >>= 8; }
+    c = __popc(x & 0xfu);    if (k >= c) { k -= c; r += 4;  x >>= 4; }
+    c = __popc(x & 0x3u);    if (k >= c) { k -= c; r += 2;  x >>= 2; }
+    c = (int)(x & 1u);       if (k >= c) { r += 1; }
+    return r;
+#else
+    for (int i = 0; i < k; ++i) x &= x - 1;
+    return __builtin_ctz(x);
+#endif
+}
 // k-th (0-based) set bit of a 64-bit word; k must be < popcount.
-__host__ __device__ inline int nth_set_bit64(u64 x, int k) {
+__host__ __device__ __forceinline__ int nth_set_bit64(u64 x, int k) {
 #ifdef __CUDA_ARCH__
     u32 lo = (u32)x;
     int c = __popc(lo);
-    if (k < c) return (int)__fns(lo, 0, k + 1);
-    return 32 + (int)__fns((u32)(x >> 32), 0, k - c + 1);
+    if (k < c) return nth_set_bit32(lo, k);
+    return 32 + nth_set_bit32((u32)(x >> 32), k - c);
 #else
     for (int i = 0; i < k; ++i) x &= x - 1;
     return __builtin_ctzll(x);

@@ -132,24 +132,46 @@ struct TreeWarp {
     typedef Hdr<W> H;
     typedef typename G::P P;
 
+    // registers of the owning warp: the hot part of TreeState; counters are accumulated
+    // locally (32-bit) and added to the tree's record once per launch
+    struct Hot {
+        unsigned long long game_id;
+        u32 n_units, slab, high_water;
+        int traversals, move_count, status, n_queued;
+        long long game_index;
+    };
+    struct Acc { u32 sims, evals, moves, games, depth_sum, legal_sum, nodes_visited, leaves_terminal, leaves_gray, leaves_empty; };
+
     const EngineParams& p;
     const int tree, lane;
-    TreeState st;
+    Hot st;
+    Acc acc;
     Rng rng;
     uint4* slab;            // current slab
     WarpScratch& sm;
 
     __device__ TreeWarp(const EngineParams& p_, int tree_, int lane_, WarpScratch& sm_)
         : p(p_), tree(tree_), lane(lane_), sm(sm_) {
-        st = p.trees[tree];
-        rng.seed = p.seed; rng.game = st.game_id; rng.ctr = st.rng_ctr;
+        const TreeState& g = p.trees[tree];
+        st.game_id = g.game_id; st.n_units = g.n_units; st.slab = g.slab; st.high_water = g.high_water;
+        st.traversals = g.traversals; st.move_count = g.move_count; st.status = g.status; st.n_queued = g.n_queued;
+        st.game_index = g.game_index;
+        acc = Acc{ 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        rng.seed = p.seed; rng.game = st.game_id; rng.ctr = g.rng_ctr;
         slab = slab_ptr(st.slab);
     }
     __device__ uint4* slab_ptr(u32 which) const { return p.pool + ((size_t)tree * 2 + which) * p.cap_units; }
     __device__ void save() {
-        st.rng_ctr = rng.ctr;
         if (st.n_units > st.high_water) st.high_water = st.n_units;
-        if (lane == 0) p.trees[tree] = st;
+        if (lane == 0) {
+            TreeState& g = p.trees[tree];
+            g.game_id = st.game_id; g.rng_ctr = rng.ctr; g.n_units = st.n_units; g.slab = st.slab;
+            g.high_water = st.high_water; g.traversals = st.traversals; g.move_count = st.move_count;
+            g.status = st.status; g.n_queued = st.n_queued; g.game_index = st.game_index;
+            g.sims += acc.sims; g.evals += acc.evals; g.moves += acc.moves; g.games += acc.games;
+            g.depth_sum += acc.depth_sum; g.legal_sum += acc.legal_sum; g.nodes_visited += acc.nodes_visited;
+            g.leaves_terminal += acc.leaves_terminal; g.leaves_gray += acc.leaves_gray; g.leaves_empty += acc.leaves_empty;
+        }
     }
     __device__ size_t rec_index() const { return (size_t)st.game_index * p.max_moves + st.move_count; }
 
@@ -244,7 +266,7 @@ struct TreeWarp {
     }
 
     __device__ void init_game() {
-        st.game_id = p.first_game + (unsigned long long)st.game_index;
+        st.game_id = p.first_game + (unsigned long long)st.game_index * p.game_stride;
         rng.game = st.game_id; rng.ctr = 0;
         st.slab = 0; slab = slab_ptr(0);
         st.traversals = 0; st.move_count = 0; st.n_queued = 0;
@@ -322,7 +344,7 @@ struct TreeWarp {
             have = false;
             if (META_TERMINAL(h.meta) || !(h.meta & META_EXPANDED)) break;
             const int n = META_NLEGAL(h.meta);
-            st.nodes_visited += 1; st.legal_sum += n;
+            acc.nodes_visited += 1; acc.legal_sum += n;
             // UCTNode::bestAction (uct/UCTNode.hpp:221-251)
             const float sq = sqrtf(n_own);
             uint4 e[NCH];
@@ -357,7 +379,7 @@ struct TreeWarp {
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 int c = __popc(bal[ch]);
-                if (!found && r < c) { ksel = ch * 32 + (int)__fns(bal[ch], 0, r + 1); found = true; }
+                if (!found && r < c) { ksel = ch * 32 + (r == 0 ? __ffs((int)bal[ch]) - 1 : nth_set_bit32(bal[ch], r)); found = true; }
                 if (!found) r -= c;
             }
             uint4 es = e[0];
@@ -391,7 +413,7 @@ struct TreeWarp {
             ++depth;
             __syncwarp();
         }
-        st.depth_sum += depth;
+        acc.depth_sum += depth;
         leaf_hdr = h;
         return cur;
     }
@@ -409,22 +431,22 @@ struct TreeWarp {
                 u32 wn = META_WINNER(h.meta);
                 float value = (wn == WINNER_NONE) ? 0.0f : ((int)wn - 1 == player ? 1.0f : -1.0f);
                 backup(leaf, player, value);
-                st.leaves_terminal += 1;
+                acc.leaves_terminal += 1;
                 continue;
             } else if (h.meta & META_EVALUATED) {
                 expand(leaf, h.meta);
                 backup(leaf, player, h.net_value);
-                st.leaves_gray += 1;
+                acc.leaves_gray += 1;
                 continue;
             } else {
                 if (lane == 0) p.q_leaf[(size_t)tree * p.max_queue + nq] = leaf;
                 ++nq;
-                st.leaves_empty += 1;
+                acc.leaves_empty += 1;
             }
             if (nq >= p.max_queue) break;
         }
         st.traversals += trav;
-        st.sims += trav;
+        acc.sims += trav;
         st.n_queued = nq;
         __syncwarp();
         for (int q = 0; q < nq; ++q) {
@@ -432,7 +454,7 @@ struct TreeWarp {
             if (lane == 0) p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s;
             if (p.evaluator == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)tree * p.max_queue + q);
         }
-        st.evals += nq;
+        acc.evals += nq;
         __syncwarp();
     }
 
@@ -724,7 +746,7 @@ struct TreeWarp {
         st.n_units = units;
         st.traversals = 0;
         st.move_count += 1;
-        st.moves += 1;
+        acc.moves += 1;
         st.n_queued = 0;
         __syncwarp();
 
@@ -736,7 +758,7 @@ struct TreeWarp {
                 p.rec_winner[st.game_index] = (unsigned char)META_WINNER(rmeta);
                 p.rec_draws[st.game_index] = rng.ctr;
             }
-            st.games += 1;
+            acc.games += 1;
             st.game_index += p.n_slots;                  // static striding: game -> slot is deterministic
             if (st.game_index < p.num_games) init_game();
             else { st.status = ST_DONE; }
@@ -746,6 +768,7 @@ struct TreeWarp {
 
 // ---- kernels -------------------------------------------------------------------------------------
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr int MIN_BLOCKS_PER_SM = 8;       // 64 registers per thread -> 32 resident warps per SM
 
 template <class G>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) {
@@ -762,7 +785,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) 
 }
 
 template <class G>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_round(EngineParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_round(EngineParams p) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.n_slots) return;

@@ -82,6 +82,7 @@ struct EngineParams {
     // per-game records, game-major: [num_games][max_moves]
     long long num_games;
     unsigned long long first_game;
+    unsigned long long game_stride;  // stream id of game i = first_game + i * game_stride
     int max_moves;
     unsigned long long* rec_board;  // [..][2W]
     unsigned char* rec_player;      // [..]

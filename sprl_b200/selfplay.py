@@ -111,6 +111,9 @@ class Engine:
     def set_stream(self, cuda_stream):
         capi.check(self.lib.sprl_set_stream(self.handle, C.c_void_p(cuda_stream)))
 
+    def set_game_stride(self, stride):
+        capi.check(self.lib.sprl_set_game_stride(self.handle, stride))
+
     @property
     def eval_batch(self):
         return self.lib.sprl_eval_batch(self.handle)
