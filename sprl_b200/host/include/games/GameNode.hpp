@@ -1,0 +1,6 @@
+// games/GameNode.hpp -- include-path compatibility with the reference's cpp/src/games/GameNode.hpp: the
+// declarations a worker main uses live in sprl/veneer.hpp (a handle layer over libsprl_b200.so).
+#ifndef SPRL_B200_COMPAT_GAMES_GAMENODE_HPP
+#define SPRL_B200_COMPAT_GAMES_GAMENODE_HPP
+#include "../sprl/veneer.hpp"
+#endif

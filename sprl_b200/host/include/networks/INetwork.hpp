@@ -1,0 +1,6 @@
+// networks/INetwork.hpp -- include-path compatibility with the reference's cpp/src/networks/INetwork.hpp: the
+// declarations a worker main uses live in sprl/veneer.hpp (a handle layer over libsprl_b200.so).
+#ifndef SPRL_B200_COMPAT_NETWORKS_INETWORK_HPP
+#define SPRL_B200_COMPAT_NETWORKS_INETWORK_HPP
+#include "../sprl/veneer.hpp"
+#endif

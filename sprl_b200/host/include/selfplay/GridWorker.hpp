@@ -1,0 +1,6 @@
+// selfplay/GridWorker.hpp -- include-path compatibility with the reference's cpp/src/selfplay/GridWorker.hpp: the
+// declarations a worker main uses live in sprl/veneer.hpp (a handle layer over libsprl_b200.so).
+#ifndef SPRL_B200_COMPAT_SELFPLAY_GRIDWORKER_HPP
+#define SPRL_B200_COMPAT_SELFPLAY_GRIDWORKER_HPP
+#include "../sprl/veneer.hpp"
+#endif

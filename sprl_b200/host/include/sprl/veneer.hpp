@@ -1,0 +1,280 @@
+// veneer.hpp -- header-only C++ host layer over the C ABI (include/sprl_b200.h) that keeps
+// the names and signatures of the reference's driver API, so that a worker main written
+// against willwin4sure/sprl (cpp/src/OTHWorker.cpp, C4Worker.cpp, GoWorker.cpp) compiles
+// against this tree with only the include path changed:
+//
+//   SPRL::Player / Piece / ActionIdx / Value          games/GameNode.hpp:17-38, games/GridState.hpp:18-55
+//   SPRL::GridState<B,H>, GameActionDist<A>           tags: states live on the device as bitboards
+//   SPRL::OthelloNode / ConnectFourNode / GoNode      tags naming the device rules (games.cuh)
+//   SPRL::INetwork<State,A>, RandomNetwork            networks/INetwork.hpp, RandomNetwork.hpp
+//   SPRL::ISymmetrizer<State,A>, D4GridSymmetrizer,   symmetry/*.hpp
+//         ConnectFourSymmetrizer
+//   SPRL::InitQ                                       uct/UCTNode.hpp:24-28
+//   SPRL::runIteration<Impl,State,A>(...)             selfplay/SelfPlay.hpp:203-208
+//   SPRL::waitModelPath, SPRL::runWorker<NN,Impl,R,C,H,A>(...)   selfplay/GridWorker.hpp:35-55,84-91
+//
+// What changes underneath: runIteration plays all `numGames` games CONCURRENTLY on one GPU
+// (one warp per tree) instead of one after the other on a CPU core; the evaluator is a handle
+// (uniform on device, or a traced network run on the GPU from device buffers) rather than an
+// object whose evaluate() is called with host vectors; samples come back already embedded as
+// the float planes runWorker writes (selfplay/GridWorker.hpp:146-171).
+#ifndef SPRL_B200_VENEER_HPP
+#define SPRL_B200_VENEER_HPP
+
+#include "../../../../include/sprl_b200.h"
+
+#include <chrono>
+#include <cstdint>
+#include <filesystem>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+namespace SPRL {
+
+enum class Player : int8_t { NONE = -1, ZERO = 0, ONE = 1 };
+enum class Piece : int8_t { NONE = -1, ZERO = 0, ONE = 1 };
+using ActionIdx = int16_t;
+using Value = float;
+using SymmetryIdx = int8_t;
+
+enum class InitQ { ZERO, PARENT, DROP_PARENT };
+
+template <int ACTION_SIZE> struct GameActionDist { static constexpr int SIZE = ACTION_SIZE; };
+template <int BOARD_SIZE, int HISTORY_SIZE> struct GridState {
+    static constexpr int BOARD = BOARD_SIZE, HISTORY = HISTORY_SIZE;
+};
+
+// ---- games: constants of games/*.hpp and tags selecting the device rules ----
+constexpr int OTH_BOARD_WIDTH = 8;
+constexpr int OTH_BOARD_SIZE = OTH_BOARD_WIDTH * OTH_BOARD_WIDTH;
+constexpr int OTH_ACTION_SIZE = OTH_BOARD_SIZE + 1;
+constexpr int OTH_HISTORY_SIZE = 1;
+struct OthelloNode { static constexpr int GAME = SPRL_GAME_OTHELLO; };
+
+constexpr int C4_NUM_ROWS = 6;
+constexpr int C4_NUM_COLS = 7;
+constexpr int C4_BOARD_SIZE = C4_NUM_ROWS * C4_NUM_COLS;
+constexpr int C4_ACTION_SIZE = C4_NUM_COLS;
+constexpr int C4_HISTORY_SIZE = 1;
+struct ConnectFourNode { static constexpr int GAME = SPRL_GAME_C4; };
+
+#ifndef SPRL_GO_BOARD_WIDTH
+#define SPRL_GO_BOARD_WIDTH 7                 // games/GoNode.hpp:16; 9 selects the 9x9 / komi 7.5 rules
+#endif
+constexpr int GO_BOARD_WIDTH = SPRL_GO_BOARD_WIDTH;
+constexpr int GO_BOARD_SIZE = GO_BOARD_WIDTH * GO_BOARD_WIDTH;
+constexpr int GO_ACTION_SIZE = GO_BOARD_SIZE + 1;
+constexpr int GO_HISTORY_SIZE = 8;
+struct GoNode { static constexpr int GAME = (GO_BOARD_WIDTH == 9) ? SPRL_GAME_GO9 : SPRL_GAME_GO7; };
+
+// ---- evaluators ----
+// The reference's INetwork::evaluate(states, masks) is a host call per leaf batch.  Here an
+// evaluator is a handle the engine queries for (a) which on-device evaluator to use and
+// (b) for external networks, a forward function over device buffers.
+template <typename State, int ACTION_SIZE>
+class INetwork {
+public:
+    virtual ~INetwork() = default;
+    virtual int evaluatorKind() const = 0;                       // SPRL_EVAL_*
+    // External networks only.  prepare(): allocate the device buffers of a leaf batch
+    // (planes [batch, planes, rows, cols], logits [batch, actions], value [batch]) on `device`.
+    // forward(): run the network on d_in and leave its outputs in d_logits / d_value, on `stream`.
+    virtual int prepare(int /*device*/, int64_t /*batch*/, int /*planes*/, int /*rows*/, int /*cols*/, int /*actions*/,
+                        float** /*d_in*/, float** /*d_logits*/, float** /*d_value*/) { return -1; }
+    virtual int forward(const float*, int64_t, float*, float*, void* /*cudaStream_t*/) { return -1; }
+    virtual int getNumEvals() { return (int)m_numEvals; }
+    void addEvals(uint64_t n) { m_numEvals += n; }
+protected:
+    uint64_t m_numEvals { 0 };
+};
+
+template <typename State, int ACTION_SIZE>
+class RandomNetwork : public INetwork<State, ACTION_SIZE> {       // networks/RandomNetwork.hpp
+public:
+    int evaluatorKind() const override { return SPRL_EVAL_UNIFORM; }
+};
+
+// Deterministic test evaluator (parity runs), evaluated on the device.
+template <typename State, int ACTION_SIZE>
+class HashNetwork : public INetwork<State, ACTION_SIZE> {
+public:
+    int evaluatorKind() const override { return SPRL_EVAL_HASHNET; }
+};
+
+// ---- symmetrizers: presence selects the game's symmetry group on the device ----
+template <typename State, int ACTION_SIZE>
+class ISymmetrizer {
+public:
+    virtual ~ISymmetrizer() = default;
+    virtual int numSymmetries() const = 0;
+    virtual SymmetryIdx inverseSymmetry(SymmetryIdx symmetry) const = 0;
+};
+
+template <int BOARD_WIDTH, int HISTORY_SIZE>
+class D4GridSymmetrizer : public ISymmetrizer<GridState<BOARD_WIDTH * BOARD_WIDTH, HISTORY_SIZE>, BOARD_WIDTH * BOARD_WIDTH + 1> {
+public:
+    int numSymmetries() const override { return 8; }
+    SymmetryIdx inverseSymmetry(SymmetryIdx s) const override {
+        static constexpr SymmetryIdx inv[8] = { 0, 3, 2, 1, 4, 5, 6, 7 };     // symmetry/D4GridSymmetrizer.hpp:47-50
+        return inv[s];
+    }
+};
+
+class ConnectFourSymmetrizer : public ISymmetrizer<GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> {
+public:
+    int numSymmetries() const override { return 2; }
+    SymmetryIdx inverseSymmetry(SymmetryIdx s) const override { return s; }
+};
+
+// ---- engine handle -------------------------------------------------------------------------
+class EngineError : public std::runtime_error {
+public:
+    EngineError(int code, const std::string& what) : std::runtime_error(what), code(code) {}
+    int code;
+};
+
+inline void check(int rc) {
+    if (rc != SPRL_OK) throw EngineError(rc, std::string("libsprl_b200: ") + sprl_last_error());
+}
+
+// Run-wide knobs a reference main cannot express (it has no notion of a device).
+struct DeviceOptions {
+    int device = 0;
+    uint64_t seed = 0;
+    int numSlots = 0;          // 0 = one slot per game
+    uint64_t firstGame = 0;    // stream id of the first game of the next runIteration
+    uint64_t gameStride = 1;
+};
+inline DeviceOptions& deviceOptions() { static DeviceOptions o; return o; }
+
+// ---- runIteration (selfplay/SelfPlay.hpp:203-248) --------------------------------------------
+// Returns the embedded samples: states [n, 2H+1, R, C], distributions [n, A], outcomes [n].
+template <typename ImplNode, typename State, int ACTION_SIZE>
+std::tuple<std::vector<float>, std::vector<float>, std::vector<Value>>
+runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
+             int numTraversals, int maxBatchSize, int maxQueueSize,
+             float dirEps, float dirAlpha, InitQ initQMethod,
+             ISymmetrizer<State, ACTION_SIZE>* symmetrizer, bool addNoise = true) {
+    if (initQMethod == InitQ::DROP_PARENT) throw EngineError(SPRL_E_INVALID, "InitQ::DROP_PARENT is not selected by any reference caller and is not implemented");
+    const DeviceOptions& opt = deviceOptions();
+    sprl_config cfg;
+    check(sprl_default_config(ImplNode::GAME, &cfg));
+    cfg.device = opt.device; cfg.seed = opt.seed;
+    cfg.evaluator = network->evaluatorKind();
+    cfg.num_slots = opt.numSlots > 0 ? std::min(opt.numSlots, numGames) : numGames;
+    cfg.max_games = numGames;
+    cfg.sims = numTraversals; cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
+    cfg.dir_eps = dirEps; cfg.dir_alpha = dirAlpha;
+    cfg.init_q = (initQMethod == InitQ::PARENT) ? SPRL_INITQ_PARENT : SPRL_INITQ_ZERO;
+    cfg.add_noise = addNoise ? 1 : 0;
+    cfg.use_sym = symmetrizer != nullptr ? 1 : 0;
+    sprl_engine* e = nullptr;
+    check(sprl_create(&cfg, &e));
+    struct Guard { sprl_engine* e; ~Guard() { sprl_destroy(e); } } guard { e };
+    check(sprl_set_game_stride(e, opt.gameStride));
+
+    sprl_game_info gi;
+    check(sprl_game_info_get(ImplNode::GAME, &gi));
+    struct Ctx { INetwork<State, ACTION_SIZE>* net; } ctx { network };
+    sprl_forward_fn fwd = nullptr;
+    if (cfg.evaluator == SPRL_EVAL_EXTERNAL) {
+        fwd = [](void* user, const float* in, int64_t batch, float* logits, float* value, void* stream) -> int {
+            return static_cast<Ctx*>(user)->net->forward(in, batch, logits, value, stream);
+        };
+        // the evaluator buffers are owned by the network object
+        float *d_in = nullptr, *d_logits = nullptr, *d_value = nullptr;
+        if (network->prepare(cfg.device, sprl_eval_batch(e), 2 * gi.history + 1, gi.rows, gi.cols, gi.actions, &d_in, &d_logits, &d_value) != 0)
+            throw EngineError(SPRL_E_STATE, "network could not allocate its device buffers");
+        check(sprl_bind_eval_buffers(e, d_in, d_logits, d_value));
+    }
+    check(sprl_run_iteration(e, opt.firstGame, numGames, fwd, &ctx));
+
+    int64_t nMoves = 0, nSamples = 0;
+    check(sprl_iteration_counts(e, &nMoves, &nSamples));
+    const size_t row = (size_t)(2 * gi.history + 1) * gi.cells;
+    std::vector<float> states((size_t)nSamples * row), dists((size_t)nSamples * gi.actions);
+    std::vector<Value> outcomes((size_t)nSamples);
+    int64_t got = 0;
+    check(sprl_collect_samples(e, nSamples, states.data(), dists.data(), outcomes.data(), &got));
+    sprl_stats st;
+    check(sprl_get_stats(e, &st));
+    network->addEvals(st.evals);
+    std::cout << numGames << " games played, " << nSamples << " states collected.\n";
+    return { std::move(states), std::move(dists), std::move(outcomes) };
+}
+
+// ---- waitModelPath / runWorker (selfplay/GridWorker.hpp:35-55,84-198) ------------------------
+constexpr int MODEL_PATH_WAIT_INTERVAL = 30;
+
+inline std::string waitModelPath(int iteration, const std::string& runName) {
+    if (iteration == -1) return "random";
+    std::string modelPath;
+    do {
+        modelPath = "data/models/" + runName + "/traced_" + runName + "_iteration_" + std::to_string(iteration) + ".pt";
+        if (!std::filesystem::exists(modelPath)) {
+            std::cout << "Spinning on traced model from iteration " << iteration << "..." << std::endl;
+            std::this_thread::sleep_for(std::chrono::seconds(MODEL_PATH_WAIT_INTERVAL));
+        }
+    } while (!std::filesystem::exists(modelPath));
+    std::this_thread::sleep_for(std::chrono::seconds(5));
+    return modelPath;
+}
+
+inline void writeNpy(const std::string& path, const std::vector<float>& data, std::vector<uint64_t> shape) {
+    int rc = sprl_write_npy_f32(path.c_str(), data.data(), shape.data(), (int)shape.size());
+    if (rc != SPRL_OK) throw std::runtime_error("io error: failed to open a file.");      // utils/npy.hpp:633-636
+}
+
+template <typename NeuralNetwork, typename ImplNode, int NUM_ROWS, int NUM_COLS, int HISTORY_SIZE, int ACTION_SIZE>
+void runWorker(std::string runName, std::string saveDir,
+               INetwork<GridState<NUM_ROWS * NUM_COLS, HISTORY_SIZE>, ACTION_SIZE>* initialNetwork,
+               ISymmetrizer<GridState<NUM_ROWS * NUM_COLS, HISTORY_SIZE>, ACTION_SIZE>* symmetrizer,
+               int numIters,
+               int initNumGamesPerWorker, int initUctTraversals, int initMaxBatchSize, int initMaxQueueSize,
+               int numGamesPerWorker, int uctTraversals, int maxBatchSize, int maxQueueSize,
+               float dirEps, float dirAlpha) {
+    using State = GridState<NUM_ROWS * NUM_COLS, HISTORY_SIZE>;
+    try {
+        bool result = std::filesystem::create_directories(saveDir);
+        std::cout << (result ? "Created directory: " : "Directory already exists: ") << saveDir << std::endl;
+    } catch (std::exception& e) {
+        std::cerr << "Error creating directory: " << e.what() << std::endl;
+        return;
+    }
+    INetwork<State, ACTION_SIZE>* network;
+    for (int iter = 0; iter < numIters; ++iter) {
+        std::cout << "Starting iteration " << iter << "..." << std::endl;
+        std::string modelPath = waitModelPath(iter - 1, runName);
+        std::string savePath = saveDir + "/" + runName + "_iteration_" + std::to_string(iter);
+        // The reference shadows maxBatchSize / maxQueueSize here and self-initialises them for
+        // iter > 0 (GridWorker.hpp:120-121, undefined behaviour); the intended values are used.
+        int numGames = (iter == 0) ? initNumGamesPerWorker : numGamesPerWorker;
+        int numTraversals = (iter == 0) ? initUctTraversals : uctTraversals;
+        int batch = (iter == 0) ? initMaxBatchSize : maxBatchSize;
+        int queue = (iter == 0) ? initMaxQueueSize : maxQueueSize;
+
+        NeuralNetwork neuralNetwork { modelPath };
+        if (modelPath == "random") {
+            std::cout << "Using initial network..." << std::endl;
+            network = initialNetwork;
+        } else {
+            std::cout << "Using traced PyTorch network..." << std::endl;
+            network = &neuralNetwork;
+        }
+        auto [states, distributions, outcomes] = runIteration<ImplNode, State, ACTION_SIZE>(
+            network, numGames, numTraversals, batch, queue, dirEps, dirAlpha, InitQ::PARENT, symmetrizer, true);
+        deviceOptions().firstGame += (uint64_t)numGames * deviceOptions().gameStride;
+
+        const uint64_t n = outcomes.size();
+        writeNpy(savePath + "_states.npy", states, { n, (uint64_t)(2 * HISTORY_SIZE + 1), (uint64_t)NUM_ROWS, (uint64_t)NUM_COLS });
+        writeNpy(savePath + "_distributions.npy", distributions, { n, (uint64_t)ACTION_SIZE });
+        writeNpy(savePath + "_outcomes.npy", outcomes, { n });
+    }
+}
+
+}  // namespace SPRL
+#endif

@@ -1,0 +1,6 @@
+// symmetry/D4GridSymmetrizer.hpp -- include-path compatibility with the reference's cpp/src/symmetry/D4GridSymmetrizer.hpp: the
+// declarations a worker main uses live in sprl/veneer.hpp (a handle layer over libsprl_b200.so).
+#ifndef SPRL_B200_COMPAT_SYMMETRY_DGRIDSYMMETRIZER_HPP
+#define SPRL_B200_COMPAT_SYMMETRY_DGRIDSYMMETRIZER_HPP
+#include "../sprl/veneer.hpp"
+#endif
