@@ -172,3 +172,103 @@ def test_sample_round_trip_properties():
     assert (o == o[:, :1]).all()
     colour = s[:, 0, 2, 0, 0]                                                # 1.0 when player ZERO moved
     assert set(np.unique(colour)) <= {0.0, 1.0}
+
+
+# ------------------------------------------------- external evaluator (the traced-network path)
+class IntegerNet:
+    """A network whose outputs are exact in fp32 on any device: integer weights on 0/1 planes,
+    so every partial sum is a small integer and the summation order cannot matter.  Run by torch
+    on the GPU for the engine (the path a traced module takes: planes written by the search
+    kernel, logits/value read back in place) and by numpy for the oracle's callback evaluator."""
+
+    def __init__(self, planes, cells, actions, seed=0):
+        rs = np.random.RandomState(seed)
+        self.wp = rs.randint(-3, 4, size=(planes * cells, actions)).astype(np.float32)
+        self.wv = rs.randint(-2, 3, size=(planes * cells,)).astype(np.float32)
+        self.calls = 0
+
+    def numpy(self, x):
+        flat = np.asarray(x, np.float32).reshape(x.shape[0], -1)
+        return (flat @ self.wp) * np.float32(0.125), np.clip((flat @ self.wv) * np.float32(1.0 / 64), -1, 1)
+
+    def torch_fn(self, dev):
+        import torch
+        torch.backends.cuda.matmul.allow_tf32 = False
+        wp, wv = torch.from_numpy(self.wp).to(dev), torch.from_numpy(self.wv).to(dev)
+
+        def fn(x):
+            self.calls += 1
+            flat = x.reshape(x.shape[0], -1)
+            return (flat @ wp) * 0.125, torch.clamp((flat @ wv) * (1.0 / 64), -1, 1)
+        return fn
+
+
+@pytest.mark.parametrize("game,sims,b,q,alpha,ngames,graph", [
+    (capi.GAME_OTHELLO, 120, 8, 4, 0.3, 12, False),
+    (capi.GAME_OTHELLO, 64, 8, 4, 0.3, 6, True),           # search launch + forward replayed as one CUDA graph
+    (capi.GAME_C4, 100, 8, 4, 0.5, 8, False),
+    (capi.GAME_GO7, 48, 16, 8, 0.2, 3, False),             # 8 history boards: 17 input planes
+])
+def test_external_evaluator_bit_exact(game, sims, b, q, alpha, ngames, graph):
+    import torch
+    gi = capi.game_info(game)
+    net = IntegerNet(2 * gi.history + 1, gi.cells, gi.actions, seed=game)
+    ref = O.selfplay(game, O.OE_CALLBACK, 21, 0, ngames, sims, b, q, 0.25, alpha, eval_fn=net.numpy, max_moves_per_game=170)
+    with SP.Engine(game, capi.EVAL_EXTERNAL, seed=21, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=alpha,
+                   num_slots=ngames, max_games=ngames, record_stats=1) as eng:
+        eng.attach_network(net.torch_fn(torch.device("cuda", 0)), use_cuda_graph=graph)
+        states, dists, outcomes = eng.run_iteration(ngames)
+        got = eng.move_stats(ngames)
+        got.update(states=states, distributions=dists, outcomes=outcomes)
+        st = eng.stats()
+    assert net.calls > 0
+    compare_selfplay(ref, got)
+    assert st["sims"] == ref["stats"]["total_traversals"] and st["evals"] == ref["stats"]["total_evals"]
+
+
+def test_external_evaluator_needs_a_network():
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, num_slots=2, max_games=2, sims=16) as eng:
+        with pytest.raises(capi.SprlError):
+            eng.run_iteration(2)
+
+
+def test_traced_network_matches_cpu_forward():
+    """The LibTorch boundary (parity unpinned by the reference): the same traced
+    module in fp32 on the GPU (TF32 off) against its CPU forward, |dlogit| <= 1e-4."""
+    import torch
+    from sprl_b200.network import make_network, trace_network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = make_network("othello", 0)
+    x = (torch.rand(512, 3, 8, 8) > 0.5).float()
+    with torch.no_grad():
+        lg_cpu, v_cpu = net(x)
+        lg_gpu, v_gpu = trace_network(make_network("othello", 0), torch.device("cuda", 0))(x.cuda())
+    assert (lg_gpu.cpu() - lg_cpu).abs().max().item() <= 1e-4
+    assert (v_gpu.cpu() - v_cpu).abs().max().item() <= 1e-4
+
+
+# ---------------------------------------------------------------------- sharding across ranks
+def test_sharded_generation_equals_unsharded():
+    """Games are keyed by their id, not by the rank that plays them: two engines playing the
+    shards of world_size 2 (game_id % 2, as bench.py does per GPU) reproduce the unsharded run."""
+    from sprl_b200 import shard
+    n, world = 10, 2
+    kw = dict(seed=4, sims=60, max_batch=8, max_queue=4, dir_eps=0.25, dir_alpha=0.3, record_stats=1)
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, num_slots=n, max_games=n, **kw) as eng:
+        eng.run_iteration(n)
+        whole = eng.move_stats(n)
+    per_rank = []
+    for r in range(world):
+        first, stride, count = shard.shard_plan(n, r, world)
+        with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, num_slots=count, max_games=count, **kw) as eng:
+            eng.set_game_stride(stride)
+            eng.run_iteration(count, first_game=first)
+            ms = eng.move_stats(count)
+        bounds = np.concatenate([[0], np.cumsum(ms["game_moves"])])
+        per_rank.append([(ms["move_N"][bounds[k]:bounds[k + 1]], ms["move_action"][bounds[k]:bounds[k + 1]]) for k in range(count)])
+    merged = shard.merge_shards(per_rank, world)
+    bounds = np.concatenate([[0], np.cumsum(whole["game_moves"])])
+    for g in range(n):
+        assert np.array_equal(merged[g][0], whole["move_N"][bounds[g]:bounds[g + 1]]), g
+        assert np.array_equal(merged[g][1], whole["move_action"][bounds[g]:bounds[g + 1]]), g
