@@ -189,6 +189,45 @@ int sprl_reset_stats(sprl_engine* e);
 /* npy::write_npy (utils/npy.hpp:616-639) for float32 C-order data: byte-identical header. */
 int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* shape, int ndim);
 
+/* ------------------------------------------------------------------ evaluator network
+ * The forward pass of the controller's network (src/networks/grid_networks.py:30-80
+ * BasicGridNetwork, loaded by networks/GridNetwork.hpp:37-51 and run at :99) as one persistent
+ * tcgen05 kernel for 8x8 boards: conv tower on the tensor cores with the 3xTF32 split
+ * (fp32-level accuracy, fp32 accumulate), BatchNorm folded, heads fused.  Other board sizes
+ * keep using the traced module through sprl_forward_fn. */
+typedef struct {
+    const float *weight, *bias;                             /* conv: [out, in, 3, 3], [out] */
+    const float *bn_weight, *bn_bias, *bn_mean, *bn_var;    /* BatchNorm2d affine + running stats, [out] */
+} sprl_conv_bn_params;
+
+typedef struct {
+    int rows, cols, in_planes, channels, blocks, actions;   /* BasicGridNetwork(rows, cols, actions, (in_planes-1)/2, blocks, channels) */
+    int policy_channels, value_channels, value_hidden;      /* 2, 1, channels */
+    float bn_eps;                                           /* 0 = 1e-5 */
+    sprl_conv_bn_params stem;                               /* conv, bn */
+    const sprl_conv_bn_params* tower;                       /* [2 * blocks]: conv1/bn1, conv2/bn2 of every residual block */
+    const float *policy_conv_w, *policy_conv_b;             /* [policy_channels, channels, 1, 1], [policy_channels] */
+    const float *policy_fc_w, *policy_fc_b;                 /* [actions, policy_channels * rows * cols], [actions] */
+    const float *value_conv_w, *value_conv_b;               /* [1, channels, 1, 1], [1] */
+    const float *value_fc1_w, *value_fc1_b;                 /* [value_hidden, rows * cols], [value_hidden] */
+    const float *value_fc2_w, *value_fc2_b;                 /* [1, value_hidden], [1] */
+} sprl_network_params;                                      /* all pointers are HOST memory */
+
+typedef struct sprl_evalnet sprl_evalnet;
+
+int sprl_evalnet_create(int device, const sprl_network_params* h_params, sprl_evalnet** out);
+/* New generation's weights, same shape: overwritten in place (device addresses stay valid
+ * for captured CUDA graphs). */
+int sprl_evalnet_update(sprl_evalnet* net, const sprl_network_params* h_params);
+/* INetwork::evaluate's forward (networks/GridNetwork.hpp:99-102) on device buffers:
+ * d_in [batch, in_planes, 8, 8] -> d_logits [batch, actions], d_value [batch].  Asynchronous on
+ * `cuda_stream`; matches sprl_forward_fn so that it can serve as the engine's evaluator. */
+int sprl_evalnet_forward(sprl_evalnet* net, const float* d_in, int64_t batch, float* d_logits, float* d_value,
+                         void* cuda_stream);
+/* Synchronises the device and reports a kernel-side failure, if any. */
+int sprl_evalnet_status(sprl_evalnet* net, uint64_t* launches);
+void sprl_evalnet_destroy(sprl_evalnet* net);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,15 +13,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsprl_b200.so")
-SOURCES = ["env.cu", "search.cu", "engine.cu"]
+SOURCES = ["env.cu", "search.cu", "engine.cu", "evalnet.cu"]
 
-NVCC_FLAGS = [
+BASE_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    # bit-exact fp32/fp64 against the reference's x86-64 build: no FMA contraction,
-    # IEEE division and square root, denormals kept
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall,-Wno-unknown-pragmas",
 ]
+# bit-exact fp32/fp64 against the reference's x86-64 build: no FMA contraction,
+# IEEE division and square root, denormals kept
+EXACT_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+NVCC_FLAGS = BASE_FLAGS + EXACT_FLAGS
+# the evaluator network is a floating-point contraction (tolerance, not bit parity): FMA allowed
+FLAGS_OF = {"evalnet.cu": BASE_FLAGS}
 
 
 def _nvcc():
@@ -51,7 +54,7 @@ def build_library(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [_nvcc(), *FLAGS_OF.get(os.path.basename(src), NVCC_FLAGS), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

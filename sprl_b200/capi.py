@@ -22,6 +22,7 @@ EXPORTS = [
     "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
     "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
+    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_status", "sprl_evalnet_destroy",
 ]
 
 
@@ -51,6 +52,18 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class ConvBnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var")]
+
+
+class NetworkParams(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("rows", "cols", "in_planes", "channels", "blocks", "actions", "policy_channels",
+                                         "value_channels", "value_hidden")] +
+                [("bn_eps", C.c_float), ("stem", ConvBnParams), ("tower", C.POINTER(ConvBnParams))] +
+                [(n, C.c_void_p) for n in ("policy_conv_w", "policy_conv_b", "policy_fc_w", "policy_fc_b", "value_conv_w",
+                                           "value_conv_b", "value_fc1_w", "value_fc1_b", "value_fc2_w", "value_fc2_b")])
 
 
 FORWARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -96,6 +109,12 @@ def load():
                                      C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.sprl_env_perft.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
     lib.sprl_write_npy_f32.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    lib.sprl_evalnet_create.argtypes = [C.c_int, C.POINTER(NetworkParams), C.POINTER(C.c_void_p)]
+    lib.sprl_evalnet_update.argtypes = [C.c_void_p, C.POINTER(NetworkParams)]
+    lib.sprl_evalnet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sprl_evalnet_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.sprl_evalnet_destroy.restype = None
+    lib.sprl_evalnet_destroy.argtypes = [C.c_void_p]
     lib.sprl_default_config.argtypes = [C.c_int, C.POINTER(Config)]
     lib.sprl_game_info_get.argtypes = [C.c_int, C.POINTER(GameInfo)]
     _lib = lib

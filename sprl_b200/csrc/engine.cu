@@ -235,6 +235,13 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
     e->active_slots = std::min<int64_t>(num_games, e->cfg.num_slots);
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_moves, 0, (size_t)e->cfg.max_games * sizeof(int), e->stream));
+    if (e->cfg.record_stats) {
+        // only legal actions are written per move; the rest of each [A] row must read as 0
+        const size_t bytes = (size_t)e->cfg.max_games * e->p.max_moves * e->gi.actions * sizeof(float);
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_N, 0, bytes, e->stream));
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_W, 0, bytes, e->stream));
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_P, 0, bytes, e->stream));
+    }
     search_launch_begin(e->cfg.game, e->p, e->stream);
     e->launches += 1;
     ENGINE_CUDA(e, cudaGetLastError());

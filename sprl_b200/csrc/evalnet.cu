@@ -1,0 +1,601 @@
+// evalnet.cu -- the evaluator network's forward pass as one persistent tcgen05 kernel.
+//
+// Replaces, for 8x8 boards, the LibTorch forward of the reference's traced
+// `BasicGridNetwork` (/root/reference/cpp/src/networks/GridNetwork.hpp:99 calling the module
+// of /root/reference/src/networks/grid_networks.py:30-80): conv3x3+BN+ReLU stem, `blocks`
+// residual blocks of two conv3x3+BN, policy head (conv1x1 -> ReLU -> FC) and value head
+// (conv1x1 -> ReLU -> FC -> ReLU -> FC -> tanh).  It reads the leaf planes the search kernel
+// wrote (SPRL_EVAL_EXTERNAL buffers) and writes logits / value where the next search launch
+// reads them.
+//
+// Design (B200, sm_100a):
+//   * One CTA per SM, persistent over tiles of TWO boards = 128 cells = the M of one
+//     tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole tower on chip:
+//     activations never leave shared memory, the fp32 accumulator lives in TMEM (64 columns).
+//   * Every 3x3 convolution is an implicit GEMM with NO im2col copy: the activation image is
+//     kept in shared memory as [channel group of 4][padded cell slot][4 floats], rows of the two
+//     boards interleaved, so that the operand of tap (dy, dx) is the SAME image read through a
+//     K-major no-swizzle UMMA descriptor whose start address is shifted by (20*dy + dx) slots
+//     (8 cells of a board row = the 8 rows of a core matrix, SBO = one storage row = 160 B,
+//     LBO = one channel group = 3200 B).  Zero padding is part of the image.
+//   * fp32 accuracy on the tensor cores by the 3xTF32 split: x = hi + lo with hi = tf32(x);
+//     D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate.  (The reference evaluates in
+//     fp32; a single TF32 pass would lose 13 mantissa bits, the split keeps ~21.)
+//   * Weights (BN folded on the host in double, split hi/lo, pre-arranged as K-major UMMA
+//     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream from L2 through a 5-stage ring of 16 KB units filled by
+//     cp.async.bulk + mbarrier complete_tx; tcgen05.commit frees a unit.
+//   * Warp roles: warps 0-3 = epilogue (TMEM -> registers -> bias/residual/ReLU -> hi/lo ->
+//     activation image), warp 4 = MMA issuer (one lane), warp 5 = weight producer (one lane).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sprl {
+namespace evalnet {
+
+constexpr int TILE_M = 128;                  // cells per tile (two 8x8 boards)
+constexpr int CH = 64;                       // tower width
+constexpr int NCG = CH / 4;                  // channel groups of 4 floats (16 B)
+constexpr int SLOTS = 200;                   // 20 storage rows x 10 columns
+constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the image
+constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 51,200
+constexpr int RES_BYTES = NCG * TILE_M * 16; // 32,768
+constexpr int UNIT_BYTES = 16384;            // one weight unit: [K/4][64][4] floats, K = 64
+constexpr int NST = 5;                       // ring stages
+constexpr int MAX_LAYERS = 16;
+constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 128;                // accumulator: [0,n) hi*hi + lo*hi, [n,2n) hi*lo
+
+// shared memory map (bytes)
+constexpr int OFF_AHI = 0;
+constexpr int OFF_ALO = OFF_AHI + IMG_BYTES;
+constexpr int OFF_RES = OFF_ALO + IMG_BYTES;
+constexpr int OFF_RING = OFF_RES + RES_BYTES;
+constexpr int OFF_BIAS = OFF_RING + NST * UNIT_BYTES;            // [MAX_LAYERS][64] floats
+constexpr int OFF_PBUF = OFF_BIAS + MAX_LAYERS * CH * 4;         // [2][128]
+constexpr int OFF_VBUF = OFF_PBUF + 2 * 128 * 4;                 // [2][64]
+constexpr int OFF_HBUF = OFF_VBUF + 2 * 64 * 4;                  // [2][64]
+constexpr int OFF_BARS = OFF_HBUF + 2 * 64 * 4;                  // full[NST], empty[NST], acc
+constexpr int OFF_TMEM = OFF_BARS + (2 * NST + 1) * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+
+struct NetDev {
+    const float* wunits;     // packed weight units in consumption order
+    const float* bias;       // [n_layers][64]
+    const float* pfc_wt;     // [128][actions]  (policy_fc.weight transposed)
+    const float* pfc_b;      // [actions]
+    const float* vfc1_wt;    // [64][64]        (value_fc1.weight transposed)
+    const float* vfc1_b;     // [64]
+    const float* vfc2_w;     // [64] weights, then the bias
+    int n_layers;            // 1 stem + 2*blocks + 1 heads
+    int in_planes;
+    int in_ksteps;           // ceil(in_planes / 8)
+    int actions;
+    int policy_channels;     // 2
+    unsigned long long* error_flag;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must end as a reported error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* error_flag, int where) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 24)) {
+            if (error_flag) atomicExch(error_flag, 0xDEAD0000ULL | (unsigned)where);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* v, float* w) {
+    uint32_t r[16], q[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(ta) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+                   "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+                 : "r"(tb) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
+}
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+// K-major, no swizzle: rows of a core matrix 16 B apart, 8-row groups SBO apart, K chunks (16 B) LBO apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ULL << 46);
+}
+__device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Layer geometry shared by the producer, the MMA issuer and the host packer.  A weight unit is
+// one tap's operand for up to 4 k-steps (32 input channels): [K chunk of 4][2n rows][4 floats],
+// rows 0..n-1 = W_hi, rows n..2n-1 = W_lo, so that ONE MMA with N = 2n computes A_hi*W_hi into
+// accumulator columns [0,n) and A_hi*W_lo into [n,2n) from a single read of A_hi; a second MMA
+// with N = n adds A_lo*W_hi into [0,n).  The epilogue sums the two column ranges.
+struct LayerGeom { int taps, ksteps, n, units_per_tap, lo_pass; };
+__host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
+    LayerGeom g;
+    if (layer == 0) { g.taps = 9; g.ksteps = in_ksteps; g.n = CH; g.lo_pass = 0; }          // 0/1 planes are exact in tf32
+    else if (layer == n_layers - 1) { g.taps = 1; g.ksteps = CH / 8; g.n = HEAD_N; g.lo_pass = 1; }
+    else { g.taps = 9; g.ksteps = CH / 8; g.n = CH; g.lo_pass = 1; }
+    g.units_per_tap = (g.ksteps + 3) / 4;
+    return g;
+}
+__host__ __device__ inline int unit_ksteps(const LayerGeom& g, int u) { return g.ksteps - 4 * u < 4 ? g.ksteps - 4 * u : 4; }
+__host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return unit_ksteps(g, u) * 8 * 2 * g.n * 4; }
+
+// slot of cell m (TMEM lane m) in the activation image: rows of the two boards interleaved
+__device__ __forceinline__ int cell_slot(int m) { return ((m >> 3) + 2) * 10 + (m & 7) + 1; }
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __restrict__ logits, float* __restrict__ value) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar_full = s_base + OFF_BARS, bar_empty = bar_full + NST * 8, bar_acc = bar_empty + NST * 8;
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+    const long long n_tiles = (batch + 1) / 2;
+    const int n_layers = net.n_layers;
+
+    // ---- one-time setup ----
+    for (int i = threadIdx.x; i < (2 * IMG_BYTES + RES_BYTES) / 16; i += THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < n_layers * CH; i += THREADS) s_bias[i] = net.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+    if (warp == 5) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(net.wunits);
+                for (int layer = 0; layer < n_layers; ++layer) {
+                    const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
+                    for (int tap = 0; tap < g.taps; ++tap)
+                        for (int u = 0; u < g.units_per_tap; ++u, ++it) {
+                            const uint32_t s = it % NST, ph = (it / NST) & 1u, bytes = (uint32_t)unit_bytes(g, u);
+                            mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1);
+                            mbar_expect_tx(bar_full + 8 * s, bytes);
+                            bulk_g2s(s_base + OFF_RING + s * UNIT_BYTES, src, bytes, bar_full + 8 * s);
+                            src += bytes;
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int layer = 0; layer < n_layers; ++layer) {
+                const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
+                named_bar(1, 160);                       // the layer's input image is complete, the accumulator is drained
+                if (lane == 0) {
+                    tc_fence_after();
+                    const uint32_t idesc2 = instr_desc_tf32(TILE_M, 2 * g.n), idesc1 = instr_desc_tf32(TILE_M, g.n);
+                    const uint32_t b_lbo = (uint32_t)(2 * g.n) * 16u, b_kstep = (2u * b_lbo) >> 4;
+                    const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 160), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 160);
+                    const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
+                    constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
+                    uint32_t acc = 0;
+                    for (int tap = 0; tap < g.taps; ++tap) {
+                        const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dx = g.taps == 9 ? tap % 3 - 1 : 0;
+                        const uint32_t a_off = (uint32_t)(21 + 20 * dy + dx);           // in 16-byte slots
+                        for (int u = 0; u < g.units_per_tap; ++u, ++it) {
+                            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                            const int nks = unit_ksteps(g, u);
+                            mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2);
+                            tc_fence_after();
+                            const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
+                            const uint64_t ah = a_hi0 + a_off + (uint32_t)(4 * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(4 * u) * A_KSTEP;
+                            if (nks == 4) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) { umma_tf32(tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
+                                if (g.lo_pass) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
+                                }
+                            } else {
+                                for (int ks = 0; ks < nks; ++ks) { umma_tf32(tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
+                                if (g.lo_pass)
+                                    for (int ks = 0; ks < nks; ++ks) umma_tf32(tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
+                            }
+                            umma_commit(bar_empty + 8 * s);          // the unit may be refilled once these MMAs retire
+                        }
+                    }
+                    umma_commit(bar_acc);                            // accumulator of this layer is complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps: cell m = TMEM lane m =====
+        const int m = threadIdx.x;                                   // 0..127
+        const int slot = cell_slot(m);
+        const int g8 = m >> 3, c = m & 7, r = g8 >> 1, b = g8 & 1;
+        const int cell = r * 8 + c;
+        const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+        float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
+        float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
+        float4* res = reinterpret_cast<float4*>(smem + OFF_RES);
+        float* pbuf = reinterpret_cast<float*>(smem + OFF_PBUF);
+        float* vbuf = reinterpret_cast<float*>(smem + OFF_VBUF);
+        float* hbuf = reinterpret_cast<float*>(smem + OFF_HBUF);
+        const int cells = 64, planes = net.in_planes;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long board = tile * 2 + b;
+            // ---- input planes -> image (0/1 values: hi = value, lo = 0) ----
+            for (int cg = 0; cg < 2 * net.in_ksteps; ++cg) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int p = cg * 4 + j;
+                    v[j] = (p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
+                }
+                a_hi[cg * SLOTS + slot] = make_float4(v[0], v[1], v[2], v[3]);
+                a_lo[cg * SLOTS + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            proxy_fence();
+            for (int layer = 0; layer < n_layers; ++layer) {
+                tc_fence_before();
+                named_bar(1, 160);
+                mbar_wait(bar_acc, acc_phase, net.error_flag, 3);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                const float* bias = s_bias + layer * CH;
+                if (layer < n_layers - 1) {
+                    const bool add_res = layer > 0 && (layer & 1) == 0;      // second conv of a block
+                    const bool save_res = (layer & 1) == 0;                  // block input of the next block
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        float v[16], w[16];
+                        tmem_ld16x2(t_lane + q * 16, t_lane + CH + q * 16, v, w);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += w[i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cg = q * 4 + j;
+                            float4 x = make_float4(v[4 * j] + bias[4 * cg], v[4 * j + 1] + bias[4 * cg + 1],
+                                                   v[4 * j + 2] + bias[4 * cg + 2], v[4 * j + 3] + bias[4 * cg + 3]);
+                            if (add_res) { float4 rr = res[cg * TILE_M + m]; x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
+                            x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
+                            if (save_res) res[cg * TILE_M + m] = x;
+                            float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+                            a_hi[cg * SLOTS + slot] = h;
+                            a_lo[cg * SLOTS + slot] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                        }
+                    }
+                    proxy_fence();
+                } else {
+                    // ---- heads: columns 0..pc-1 = policy conv channels, column pc = value conv ----
+                    float v[16], w[16];
+                    tmem_ld16x2(t_lane, t_lane + HEAD_N, v, w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                    const int pc = net.policy_channels;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < pc) pbuf[b * 128 + j * 64 + cell] = fmaxf(v[j] + bias[j], 0.0f);
+                    float vv = pc == 1 ? v[1] : (pc == 2 ? v[2] : (pc == 3 ? v[3] : v[4]));
+                    vbuf[b * 64 + cell] = fmaxf(vv + bias[pc], 0.0f);
+                    tc_fence_before();
+                    named_bar(2, 128);
+                    // policy_fc: 2 boards x actions outputs over 128 threads
+                    const int A = net.actions, K = pc * 64;
+                    for (int item = m; item < 2 * A; item += 128) {
+                        const int bb = item / A, a = item - bb * A;
+                        float s = net.pfc_b[a];
+                        const float* x = pbuf + bb * 128;
+                        for (int k = 0; k < K; ++k) s = fmaf(net.pfc_wt[k * A + a], x[k], s);
+                        if (tile * 2 + bb < batch) logits[(tile * 2 + bb) * A + a] = s;
+                    }
+                    {   // value_fc1 + ReLU: 2 boards x 64 hidden units
+                        const int bb = m >> 6, j = m & 63;
+                        float s = net.vfc1_b[j];
+                        const float* x = vbuf + bb * 64;
+                        for (int k = 0; k < 64; ++k) s = fmaf(net.vfc1_wt[k * 64 + j], x[k], s);
+                        hbuf[bb * 64 + j] = fmaxf(s, 0.0f);
+                    }
+                    named_bar(2, 128);
+                    if (warp < 2) {  // value_fc2 + tanh: one warp per board
+                        float s = net.vfc2_w[lane] * hbuf[warp * 64 + lane] + net.vfc2_w[lane + 32] * hbuf[warp * 64 + lane + 32];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if (lane == 0 && tile * 2 + warp < batch) value[tile * 2 + warp] = tanhf(s + net.vfc2_w[64]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
+static inline float tf32_rna_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & 0xffffe000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+// appends one tap's units for B[n][k] (n < n_pad rows, k < kk): per unit of <= 32 input channels,
+// layout [K chunk of 4][2*n_pad rows][4], rows 0..n_pad-1 = tf32(w), rows n_pad.. = tf32(w - tf32(w))
+static void append_units(std::vector<float>& out, const std::vector<float>& b, int n_pad, int kk) {
+    for (int k0 = 0; k0 < kk; k0 += 32)
+        for (int kc = k0 / 4; kc < std::min(kk, k0 + 32) / 4; ++kc)
+            for (int row = 0; row < 2 * n_pad; ++row)
+                for (int j = 0; j < 4; ++j) {
+                    float w = b[(size_t)(row % n_pad) * kk + kc * 4 + j];
+                    float hi = tf32_rna_host(w);
+                    out.push_back(row < n_pad ? hi : tf32_rna_host(w - hi));
+                }
+}
+
+}  // namespace evalnet
+}  // namespace sprl
+
+using namespace sprl;
+using namespace sprl::evalnet;
+
+struct sprl_evalnet {
+    int device = 0;
+    int rows = 0, cols = 0, in_planes = 0, channels = 0, blocks = 0, actions = 0, policy_channels = 0, value_hidden = 0;
+    NetDev dev;
+    std::vector<void*> allocations;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    // First call allocates; later calls (a new generation's weights) overwrite in place, so device
+    // pointers captured in a CUDA graph stay valid.
+    template <typename T> int upload(const std::vector<T>& h, const T** out) {
+        void* p = (void*)*out;
+        cudaError_t err;
+        if (!p) {
+            err = cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(T));
+            if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc failed: %s", cudaGetErrorString(err));
+            allocations.push_back(p);
+        }
+        err = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(err));
+        *out = (const T*)p;
+        return SPRL_OK;
+    }
+    void release() {
+        for (void* p : allocations) cudaFree(p);
+        allocations.clear();
+    }
+};
+
+static int check_conv(const sprl_conv_bn_params& c, const char* what) {
+    if (!c.weight || !c.bias || !c.bn_weight || !c.bn_bias || !c.bn_mean || !c.bn_var)
+        return fail(SPRL_E_INVALID, "null parameter pointer in %s", what);
+    return SPRL_OK;
+}
+
+static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
+    const int C = CH, P = p->in_planes, L = 2 + 2 * p->blocks;
+    const int in_k = 8 * ((P + 7) / 8);
+    const double eps = p->bn_eps > 0 ? p->bn_eps : 1e-5;
+    std::vector<float> units, bias((size_t)L * C, 0.0f);
+    auto conv_layer = [&](const sprl_conv_bn_params& c, int cin, int kk, int layer) {
+        std::vector<double> scale(C);
+        for (int co = 0; co < C; ++co) {
+            scale[co] = (double)c.bn_weight[co] / std::sqrt((double)c.bn_var[co] + eps);
+            bias[(size_t)layer * C + co] = (float)(((double)c.bias[co] - (double)c.bn_mean[co]) * scale[co] + (double)c.bn_bias[co]);
+        }
+        for (int tap = 0; tap < 9; ++tap) {
+            std::vector<float> b((size_t)C * kk, 0.0f);
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    b[(size_t)co * kk + ci] = (float)((double)c.weight[((size_t)co * cin + ci) * 9 + tap] * scale[co]);
+            append_units(units, b, C, kk);
+        }
+    };
+    conv_layer(p->stem, P, in_k, 0);
+    for (int i = 0; i < 2 * p->blocks; ++i) conv_layer(p->tower[i], C, C, 1 + i);
+    {   // heads: rows 0..pc-1 policy_conv, row pc value_conv
+        const int pc = p->policy_channels;
+        std::vector<float> b((size_t)HEAD_N * C, 0.0f);
+        for (int j = 0; j < pc; ++j) {
+            for (int ci = 0; ci < C; ++ci) b[(size_t)j * C + ci] = p->policy_conv_w[(size_t)j * C + ci];
+            bias[(size_t)(L - 1) * C + j] = p->policy_conv_b[j];
+        }
+        for (int ci = 0; ci < C; ++ci) b[(size_t)pc * C + ci] = p->value_conv_w[ci];
+        bias[(size_t)(L - 1) * C + pc] = p->value_conv_b[0];
+        append_units(units, b, HEAD_N, C);
+    }
+    const int A = p->actions, K = p->policy_channels * 64;
+    std::vector<float> pfc_wt((size_t)K * A), pfc_b(p->policy_fc_b, p->policy_fc_b + A), vfc1_wt(64 * 64),
+        vfc1_b(p->value_fc1_b, p->value_fc1_b + 64), vfc2_w(p->value_fc2_w, p->value_fc2_w + 64);
+    for (int a = 0; a < A; ++a)
+        for (int k = 0; k < K; ++k) pfc_wt[(size_t)k * A + a] = p->policy_fc_w[(size_t)a * K + k];
+    for (int j = 0; j < 64; ++j)
+        for (int k = 0; k < 64; ++k) vfc1_wt[(size_t)k * 64 + j] = p->value_fc1_w[(size_t)j * 64 + k];
+    vfc2_w.push_back(p->value_fc2_b[0]);
+    int rc = e->upload(units, &e->dev.wunits);
+    if (!rc) rc = e->upload(bias, &e->dev.bias);
+    if (!rc) rc = e->upload(pfc_wt, &e->dev.pfc_wt);
+    if (!rc) rc = e->upload(pfc_b, &e->dev.pfc_b);
+    if (!rc) rc = e->upload(vfc1_wt, &e->dev.vfc1_wt);
+    if (!rc) rc = e->upload(vfc1_b, &e->dev.vfc1_b);
+    if (!rc) rc = e->upload(vfc2_w, &e->dev.vfc2_w);
+    std::vector<unsigned long long> flag(1, 0ULL);
+    const unsigned long long* fp = e->dev.error_flag;
+    if (!rc) rc = e->upload(flag, &fp);
+    if (rc) return rc;
+    e->dev.error_flag = const_cast<unsigned long long*>(fp);
+    e->dev.n_layers = L;
+    e->dev.in_planes = P;
+    e->dev.in_ksteps = in_k / 8;
+    e->dev.actions = A;
+    e->dev.policy_channels = p->policy_channels;
+    return SPRL_OK;
+}
+
+static int validate(const sprl_network_params* p) {
+    if (!p) return fail(SPRL_E_INVALID, "null network parameters");
+    if (p->rows != 8 || p->cols != 8)
+        return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles 8x8 boards (two per MMA); %dx%d boards run through the LibTorch module", p->rows, p->cols);
+    if (p->channels != CH) return fail(SPRL_E_INVALID, "tower width must be %d channels, got %d", CH, p->channels);
+    if (p->blocks < 0 || 2 + 2 * p->blocks > MAX_LAYERS) return fail(SPRL_E_INVALID, "unsupported number of residual blocks %d", p->blocks);
+    if (p->in_planes < 1 || p->in_planes > CH) return fail(SPRL_E_INVALID, "unsupported number of input planes %d", p->in_planes);
+    if (p->policy_channels < 1 || p->policy_channels > 2 || p->value_channels != 1 || p->value_hidden != 64)
+        return fail(SPRL_E_INVALID, "unsupported head shape (policy channels %d, value channels %d, value hidden %d)",
+                    p->policy_channels, p->value_channels, p->value_hidden);
+    if (p->actions < 1 || p->actions > 256) return fail(SPRL_E_INVALID, "unsupported action count %d", p->actions);
+    int rc = check_conv(p->stem, "stem");
+    if (rc) return rc;
+    if (p->blocks > 0 && !p->tower) return fail(SPRL_E_INVALID, "null tower");
+    for (int i = 0; i < 2 * p->blocks; ++i) { rc = check_conv(p->tower[i], "tower"); if (rc) return rc; }
+    if (!p->policy_conv_w || !p->policy_conv_b || !p->policy_fc_w || !p->policy_fc_b || !p->value_conv_w || !p->value_conv_b ||
+        !p->value_fc1_w || !p->value_fc1_b || !p->value_fc2_w || !p->value_fc2_b)
+        return fail(SPRL_E_INVALID, "null head parameter pointer");
+    return SPRL_OK;
+}
+
+extern "C" {
+
+int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_evalnet** out) {
+    if (!out) return fail(SPRL_E_INVALID, "null output");
+    *out = nullptr;
+    int rc = validate(params);
+    if (rc) return rc;
+    rc = use_device(device);
+    if (rc) return rc;
+    sprl_evalnet* e = new sprl_evalnet();
+    memset(&e->dev, 0, sizeof(e->dev));
+    e->device = device;
+    e->rows = params->rows; e->cols = params->cols; e->in_planes = params->in_planes; e->channels = params->channels;
+    e->blocks = params->blocks; e->actions = params->actions; e->policy_channels = params->policy_channels;
+    e->value_hidden = params->value_hidden;
+    cudaDeviceProp prop;
+    cudaError_t err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err)); }
+    if (prop.major != 10) { delete e; return fail(SPRL_E_NOGPU, "the tcgen05 evaluator needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
+    e->sm_count = prop.multiProcessorCount;
+    err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+    rc = pack_and_upload(e, params);
+    if (rc) { e->release(); delete e; return rc; }
+    *out = e;
+    return SPRL_OK;
+}
+
+int sprl_evalnet_update(sprl_evalnet* e, const sprl_network_params* params) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    int rc = validate(params);
+    if (rc) return rc;
+    if (params->in_planes != e->in_planes || params->blocks != e->blocks || params->actions != e->actions ||
+        params->policy_channels != e->policy_channels)
+        return fail(SPRL_E_INVALID, "sprl_evalnet_update: the network shape changed");
+    rc = use_device(e->device);
+    if (rc) return rc;
+    cudaDeviceSynchronize();
+    return pack_and_upload(e, params);
+}
+
+int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, float* d_logits, float* d_value, void* cuda_stream) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    if (batch < 0 || (batch > 0 && (!d_in || !d_logits || !d_value))) return fail(SPRL_E_INVALID, "bad argument to sprl_evalnet_forward");
+    if (batch == 0) return SPRL_OK;
+    cudaError_t err = cudaSetDevice(e->device);
+    if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
+    const long long tiles = (batch + 1) / 2;
+    const int grid = (int)std::min<long long>(tiles, e->sm_count);
+    k_evalnet<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(e->dev, d_in, (long long)batch, d_logits, d_value);
+    e->launches += 1;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SPRL_E_CUDA, "k_evalnet launch failed: %s", cudaGetErrorString(err));
+    return SPRL_OK;
+}
+
+int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    cudaError_t err = cudaSetDevice(e->device);
+    if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
+    unsigned long long flag = 0;
+    err = cudaMemcpy(&flag, e->dev.error_flag, sizeof(flag), cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) return fail(SPRL_E_CUDA, "evaluator kernel failed: %s", cudaGetErrorString(err));
+    if (flag) return fail(SPRL_E_CUDA, "evaluator kernel timed out on a pipeline barrier (code %llx)", flag);
+    if (launches) *launches = e->launches;
+    return SPRL_OK;
+}
+
+void sprl_evalnet_destroy(sprl_evalnet* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    e->release();
+    delete e;
+}
+
+}  // extern "C"

@@ -154,9 +154,19 @@ class Engine:
         nn["use_graph"] = use_cuda_graph
         self._nn = nn
 
+    def attach_evalnet(self, evalnet, use_cuda_graph=True):
+        """Attach the library's own evaluator (sprl_b200.evalnet.EvalNet, csrc/evalnet.cu): the search
+        kernel writes leaf planes, the tcgen05 tower reads them and writes logits / value in place."""
+        self.attach_network(None, use_cuda_graph)
+        self._nn["evalnet"] = evalnet
+
     def _forward(self):
         nn = self._nn
         torch = nn["torch"]
+        if nn.get("evalnet") is not None:
+            nn["evalnet"].forward_ptr(nn["inp"].data_ptr(), nn["inp"].shape[0], nn["logits"].data_ptr(),
+                                      nn["value"].data_ptr(), torch.cuda.current_stream(nn["dev"]).cuda_stream)
+            return
         with torch.no_grad():
             logits, value = nn["module"](nn["inp"])
             nn["logits"].copy_(logits)
