@@ -11,23 +11,29 @@
 // Design (B200, sm_100a):
 //   * One CTA per SM, persistent over tiles of TWO boards = 128 cells = the M of one
 //     tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole tower on chip:
-//     activations never leave shared memory, the fp32 accumulator lives in TMEM (64 columns).
-//   * Every 3x3 convolution is an implicit GEMM with NO im2col copy: the activation image is
-//     kept in shared memory as [channel group of 4][padded cell slot][4 floats], rows of the two
-//     boards interleaved, so that the operand of tap (dy, dx) is the SAME image read through a
-//     K-major no-swizzle UMMA descriptor whose start address is shifted by (20*dy + dx) slots
-//     (8 cells of a board row = the 8 rows of a core matrix, SBO = one storage row = 160 B,
-//     LBO = one channel group = 3200 B).  Zero padding is part of the image.
+//     activations never leave shared memory, fp32 accumulators live in TMEM.
+//   * Every 3x3 convolution is an implicit GEMM with NO im2col copy.  The activation image is
+//     kept in shared memory as [channel group of 4][storage row][8 cells][4 floats], the rows of
+//     the two boards interleaved and two zero rows above and below, so that a board row is one
+//     128-byte, 128-byte-aligned UMMA core matrix (K-major, no swizzle: SBO = 128 B, LBO = one
+//     channel group) and the operand of a tap with vertical offset dy is the SAME image with
+//     the descriptor's start address moved by 2*dy storage rows.  Horizontal offsets are NOT
+//     applied to the operand (a 16-byte shift would leave every core matrix straddling two
+//     128-byte lines, measured 2x slower operand fetch): the taps of each dx accumulate into
+//     their own TMEM accumulator Z_dx, and the epilogue forms out[c] = Z_-1[c-1] + Z_0[c] +
+//     Z_+1[c+1] with two warp shuffles per value (cells of a board row are adjacent lanes).
 //   * fp32 accuracy on the tensor cores by the 3xTF32 split: x = hi + lo with hi = tf32(x);
 //     D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate.  (The reference evaluates in
 //     fp32; a single TF32 pass would lose 13 mantissa bits, the split keeps ~21.)
 //   * Weights (BN folded on the host in double, split hi/lo, pre-arranged as K-major UMMA
-//     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream from L2 through a 5-stage ring of 16 KB units filled by
-//     cp.async.bulk + mbarrier complete_tx; tcgen05.commit frees a unit.
-//   * Warp roles: warps 0-3 = epilogue (TMEM -> registers -> bias/residual/ReLU -> hi/lo ->
-//     activation image), warp 4 = MMA issuer (one lane), warp 5 = weight producer (one lane).
+//     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream
+//     from L2 through a ring of 16 KB units filled by cp.async.bulk (multicast to the CTAs of a
+//     cluster) + mbarrier complete_tx; tcgen05.commit frees a unit.
+//   * Warp roles: warps 0-3 = epilogue (TMEM -> registers -> shuffles/bias/residual/ReLU ->
+//     hi/lo -> activation image), warp 4 = MMA issuer, warp 5 = weight producer.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -39,32 +45,36 @@ namespace evalnet {
 constexpr int TILE_M = 128;                  // cells per tile (two 8x8 boards)
 constexpr int CH = 64;                       // tower width
 constexpr int NCG = CH / 4;                  // channel groups of 4 floats (16 B)
-constexpr int SLOTS = 200;                   // 20 storage rows x 10 columns
+constexpr int SLOTS = 160;                   // 20 storage rows x 8 cells
 constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the image
-constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 51,200
+constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 40,960
 constexpr int RES_BYTES = NCG * TILE_M * 16; // 32,768
-constexpr int UNIT_BYTES = 16384;            // one weight unit: [K/4][64][4] floats, K = 64
-constexpr int NST = 5;                       // ring stages
+constexpr int UNIT_BYTES = 16384;            // one weight unit: [K/4 <= 8][2*64][4] floats
+constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 128;                // accumulator: [0,n) hi*hi + lo*hi, [n,2n) hi*lo
+#ifndef SPRL_EVALNET_CLUSTER
+#define SPRL_EVALNET_CLUSTER 2
+#endif
+constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
+constexpr int ACC_COLS = 128;                // one accumulator: [0,n) hi*hi + lo*hi, [n,2n) hi*lo
+constexpr int TMEM_COLS = 512;               // three accumulators (dx = -1, 0, +1)
+constexpr int MAX_SMEM = 232448;             // 227 KB
 
-// shared memory map (bytes)
+// shared memory map (bytes); the ring, the biases and the barriers follow at run-time offsets
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + IMG_BYTES;
 constexpr int OFF_RES = OFF_ALO + IMG_BYTES;
-constexpr int OFF_RING = OFF_RES + RES_BYTES;
-constexpr int OFF_BIAS = OFF_RING + NST * UNIT_BYTES;            // [MAX_LAYERS][64] floats
-constexpr int OFF_PBUF = OFF_BIAS + MAX_LAYERS * CH * 4;         // [2][128]
+constexpr int OFF_PBUF = OFF_RES;                                // head scratch aliases the residual buffer
 constexpr int OFF_VBUF = OFF_PBUF + 2 * 128 * 4;                 // [2][64]
 constexpr int OFF_HBUF = OFF_VBUF + 2 * 64 * 4;                  // [2][64]
-constexpr int OFF_BARS = OFF_HBUF + 2 * 64 * 4;                  // full[NST], empty[NST], acc
-constexpr int OFF_TMEM = OFF_BARS + (2 * NST + 1) * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int OFF_RING = OFF_RES + RES_BYTES;                    // 114,688
 
 struct NetDev {
-    const float* wunits;     // packed weight units in consumption order
+    const float* wunits;     // packed weight units in consumption order, `replicas` copies back to back
+    long long wunits_bytes;  // bytes of one copy
+    int replicas;
     const float* bias;       // [n_layers][64]
     const float* pfc_wt;     // [128][actions]  (policy_fc.weight transposed)
     const float* pfc_b;      // [actions]
@@ -76,8 +86,15 @@ struct NetDev {
     int in_ksteps;           // ceil(in_planes / 8)
     int actions;
     int policy_channels;     // 2
+    int nst;                 // ring stages
     unsigned long long* error_flag;
+    long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
+    int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue
 };
+
+__host__ __device__ inline int smem_bytes_for(int n_layers, int nst) {
+    return OFF_RING + nst * UNIT_BYTES + n_layers * CH * 4 + (2 * nst + 1) * 8 + 16;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,14 +106,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#ifdef SPRL_EVALNET_TESTWAIT
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a protocol bug must end as a reported error, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* error_flag, int where) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 24)) {
+        if (spins > (1u << 26)) {
             if (error_flag) atomicExch(error_flag, 0xDEAD0000ULL | (unsigned)where);
             __trap();
         }
@@ -106,12 +128,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// Slice of a weight unit to the same shared-memory offset of every CTA in the cluster; each
+// destination's mbarrier (same CTA-relative offset) receives complete_tx for the slice.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One lane of a converged warp (elect.sync).  The issuing warp runs its loops convergently so that
+// descriptors and addresses stay in uniform registers; only the issue itself is predicated.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if (elect_one()) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (elect_one()) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+}
+// arrives on the mbarrier at the same offset in every CTA of `mask` once this CTA's MMAs retire
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    if (elect_one()) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -172,102 +222,139 @@ __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_
 __host__ __device__ inline int unit_ksteps(const LayerGeom& g, int u) { return g.ksteps - 4 * u < 4 ? g.ksteps - 4 * u : 4; }
 __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return unit_ksteps(g, u) * 8 * 2 * g.n * 4; }
 
-// slot of cell m (TMEM lane m) in the activation image: rows of the two boards interleaved
-__device__ __forceinline__ int cell_slot(int m) { return ((m >> 3) + 2) * 10 + (m & 7) + 1; }
+// slot of cell m (TMEM lane m) in the activation image: rows of the two boards interleaved,
+// two zero rows first
+__device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __restrict__ logits, float* __restrict__ value) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_layers = net.n_layers, nst = net.nst;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar_full = s_base + OFF_BARS, bar_empty = bar_full + NST * 8, bar_acc = bar_empty + NST * 8;
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+    const int off_bias = OFF_RING + nst * UNIT_BYTES, off_bars = off_bias + n_layers * CH * 4, off_tmem = off_bars + (2 * nst + 1) * 8;
+    const uint32_t bar_full = s_base + off_bars, bar_empty = bar_full + nst * 8, bar_acc = bar_empty + nst * 8;
+    float* s_bias = reinterpret_cast<float*>(smem + off_bias);
     const long long n_tiles = (batch + 1) / 2;
-    const int n_layers = net.n_layers;
+    // every CTA of a cluster walks the same number of tiles (the multicast ring is shared);
+    // tiles past the end are dummies: zero input, no output
+    const long long n_iters = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long tile_end = (long long)blockIdx.x + n_iters * gridDim.x;
+    const uint32_t crank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / CLUSTER;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1u);
 
     // ---- one-time setup ----
     for (int i = threadIdx.x; i < (2 * IMG_BYTES + RES_BYTES) / 16; i += THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < n_layers * CH; i += THREADS) s_bias[i] = net.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CLUSTER); }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + off_tmem), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     proxy_fence();
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                               // peers' barriers exist before anything is multicast
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + off_tmem), 0);
 
     if (warp == 5) {
         // ===== weight producer =====
         if (lane == 0) {
-            uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(net.wunits);
+            uint32_t s = 0, ph = 0;
+            long long t_wait = 0, t0 = clock64();
+            for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+                // Every tile needs the whole 1.2 MB of weights (shared memory has no room to keep
+                // them).  The CTAs of a cluster share ONE stream: each loads 1/CLUSTER of every unit
+                // and multicasts it to all.  Clusters read different replicas and walk the taps of a
+                // layer in different rotations (the accumulation order of taps is free) so that the
+                // chip is not pulling the same L2 lines at the same moment.
+                const unsigned char* layer_src = reinterpret_cast<const unsigned char*>(net.wunits) +
+                                                 (size_t)(cluster_id % net.replicas) * net.wunits_bytes;
                 for (int layer = 0; layer < n_layers; ++layer) {
                     const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
-                    for (int tap = 0; tap < g.taps; ++tap)
-                        for (int u = 0; u < g.units_per_tap; ++u, ++it) {
-                            const uint32_t s = it % NST, ph = (it / NST) & 1u, bytes = (uint32_t)unit_bytes(g, u);
-                            mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1);
-                            mbar_expect_tx(bar_full + 8 * s, bytes);
-                            bulk_g2s(s_base + OFF_RING + s * UNIT_BYTES, src, bytes, bar_full + 8 * s);
+                    int tap_bytes = 0;
+                    for (int u = 0; u < g.units_per_tap; ++u) tap_bytes += unit_bytes(g, u);
+                    for (int t = 0; t < g.taps; ++t) {
+                        const int tap = (t + cluster_id) % g.taps;
+                        const unsigned char* src = layer_src + (size_t)tap * tap_bytes;
+                        for (int u = 0; u < g.units_per_tap; ++u) {
+                            const uint32_t bytes = (uint32_t)unit_bytes(g, u);
+                            { long long a = clock64(); mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1); t_wait += clock64() - a; }
+                            mbar_expect_tx(bar_full + 8 * s, bytes);       // the whole unit: one slice from every CTA of the cluster
+                            const uint32_t slice = bytes / CLUSTER;
+                            bulk_g2s_multicast(s_base + OFF_RING + s * UNIT_BYTES + crank * slice, src + crank * slice, slice,
+                                               bar_full + 8 * s, CMASK);
                             src += bytes;
+                            if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                         }
+                    }
+                    layer_src += (size_t)g.taps * tap_bytes;
                 }
             }
+            if (net.timing) { net.timing[blockIdx.x * 12 + 8] = t_wait; net.timing[blockIdx.x * 12 + 9] = clock64() - t0; }
         }
         __syncwarp();
     } else if (warp == 4) {
-        // ===== MMA issuer =====
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) =====
+        uint32_t s = 0, ph = 0;
+        long long t_bar = 0, t_full = 0, t0 = clock64();
+        for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer) {
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
-                named_bar(1, 160);                       // the layer's input image is complete, the accumulator is drained
-                if (lane == 0) {
-                    tc_fence_after();
-                    const uint32_t idesc2 = instr_desc_tf32(TILE_M, 2 * g.n), idesc1 = instr_desc_tf32(TILE_M, g.n);
-                    const uint32_t b_lbo = (uint32_t)(2 * g.n) * 16u, b_kstep = (2u * b_lbo) >> 4;
-                    const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 160), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 160);
-                    const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
-                    constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
-                    uint32_t acc = 0;
-                    for (int tap = 0; tap < g.taps; ++tap) {
-                        const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dx = g.taps == 9 ? tap % 3 - 1 : 0;
-                        const uint32_t a_off = (uint32_t)(21 + 20 * dy + dx);           // in 16-byte slots
-                        for (int u = 0; u < g.units_per_tap; ++u, ++it) {
-                            const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                            const int nks = unit_ksteps(g, u);
-                            mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2);
-                            tc_fence_after();
-                            const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
-                            const uint64_t ah = a_hi0 + a_off + (uint32_t)(4 * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(4 * u) * A_KSTEP;
-                            if (nks == 4) {
+                { long long a = clock64(); named_bar(1, 160); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
+                tc_fence_after();
+                const uint32_t idesc2 = instr_desc_tf32(TILE_M, 2 * g.n), idesc1 = instr_desc_tf32(TILE_M, g.n);
+                const bool lo_pass = g.lo_pass && net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
+                const uint32_t b_lbo = (uint32_t)(2 * g.n) * 16u, b_kstep = (2u * b_lbo) >> 4;
+                const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
+                const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
+                constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
+                uint32_t started = 0;                    // accumulators that already hold a partial sum
+                for (int t = 0; t < g.taps; ++t) {
+                    const int tap = (t + cluster_id) % g.taps;                   // same rotation as the producer
+                    const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dxi = g.taps == 9 ? tap % 3 : 1;
+                    const uint32_t a_off = (uint32_t)(16 + 16 * dy);             // in 16-byte slots: two storage rows per board row
+                    const uint32_t d_tmem = tmem + (uint32_t)dxi * ACC_COLS;
+                    for (int u = 0; u < g.units_per_tap; ++u) {
+                        const int nks = unit_ksteps(g, u);
+                        { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
+                        tc_fence_after();
+                        const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
+                        const uint64_t ah = a_hi0 + a_off + (uint32_t)(4 * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(4 * u) * A_KSTEP;
+                        uint32_t acc = (started >> dxi) & 1u;
+                        if (nks == 4) {
+                            if (hi_pass) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) { umma_tf32(tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
-                                if (g.lo_pass) {
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
-                                }
-                            } else {
-                                for (int ks = 0; ks < nks; ++ks) { umma_tf32(tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
-                                if (g.lo_pass)
-                                    for (int ks = 0; ks < nks; ++ks) umma_tf32(tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
+                                for (int ks = 0; ks < 4; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
                             }
-                            umma_commit(bar_empty + 8 * s);          // the unit may be refilled once these MMAs retire
+                            if (lo_pass) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
+                            }
+                        } else {
+                            if (hi_pass)
+                                for (int ks = 0; ks < nks; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
+                            if (lo_pass)
+                                for (int ks = 0; ks < nks; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
                         }
+                        started |= 1u << dxi;
+                        umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
+                        if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                     }
-                    umma_commit(bar_acc);                            // accumulator of this layer is complete
                 }
+                umma_commit(bar_acc);                            // the accumulators of this layer are complete
                 __syncwarp();
             }
+        }
+        if (lane == 0 && net.timing) {
+            net.timing[blockIdx.x * 12 + 0] = t_bar; net.timing[blockIdx.x * 12 + 1] = t_full; net.timing[blockIdx.x * 12 + 2] = clock64() - t0;
         }
     } else {
         // ===== epilogue warps: cell m = TMEM lane m =====
@@ -275,6 +362,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         const int slot = cell_slot(m);
         const int g8 = m >> 3, c = m & 7, r = g8 >> 1, b = g8 & 1;
         const int cell = r * 8 + c;
+        const bool has_left = c > 0, has_right = c < 7;
         const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
         float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
         float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
@@ -284,7 +372,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         float* hbuf = reinterpret_cast<float*>(smem + OFF_HBUF);
         const int cells = 64, planes = net.in_planes;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
+        for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = tile * 2 + b;
             // ---- input planes -> image (0/1 values: hi = value, lo = 0) ----
             for (int cg = 0; cg < 2 * net.in_ksteps; ++cg) {
@@ -300,25 +389,41 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
             proxy_fence();
             for (int layer = 0; layer < n_layers; ++layer) {
                 tc_fence_before();
-                named_bar(1, 160);
-                mbar_wait(bar_acc, acc_phase, net.error_flag, 3);
+                { long long a = clock64(); named_bar(1, 160); t_bar += clock64() - a; }
+                { long long a = clock64(); mbar_wait(bar_acc, acc_phase, net.error_flag, 3); t_acc += clock64() - a; }
+                const long long t_layer = clock64();
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float* bias = s_bias + layer * CH;
-                if (layer < n_layers - 1) {
+                if (layer < n_layers - 1 && net.debug >= 5) {
+                    // timing experiment: no epilogue work
+                } else if (layer < n_layers - 1) {
                     const bool add_res = layer > 0 && (layer & 1) == 0;      // second conv of a block
                     const bool save_res = (layer & 1) == 0;                  // block input of the next block
 #pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
-                        float v[16], w[16];
+                        // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = hi half + lo half of accumulator dx
+                        float o[16], v[16], w[16];
+                        tmem_ld16x2(t_lane + ACC_COLS + q * 16, t_lane + ACC_COLS + CH + q * 16, v, w);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = v[i] + w[i];
                         tmem_ld16x2(t_lane + q * 16, t_lane + CH + q * 16, v, w);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += w[i];
+                        for (int i = 0; i < 16; ++i) {
+                            const float z = __shfl_up_sync(0xffffffffu, v[i] + w[i], 1);
+                            o[i] += has_left ? z : 0.0f;
+                        }
+                        tmem_ld16x2(t_lane + 2 * ACC_COLS + q * 16, t_lane + 2 * ACC_COLS + CH + q * 16, v, w);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float z = __shfl_down_sync(0xffffffffu, v[i] + w[i], 1);
+                            o[i] += has_right ? z : 0.0f;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int cg = q * 4 + j;
-                            float4 x = make_float4(v[4 * j] + bias[4 * cg], v[4 * j + 1] + bias[4 * cg + 1],
-                                                   v[4 * j + 2] + bias[4 * cg + 2], v[4 * j + 3] + bias[4 * cg + 3]);
+                            float4 x = make_float4(o[4 * j] + bias[4 * cg], o[4 * j + 1] + bias[4 * cg + 1],
+                                                   o[4 * j + 2] + bias[4 * cg + 2], o[4 * j + 3] + bias[4 * cg + 3]);
                             if (add_res) { float4 rr = res[cg * TILE_M + m]; x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
                             x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
                             if (save_res) res[cg * TILE_M + m] = x;
@@ -329,9 +434,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     }
                     proxy_fence();
                 } else {
-                    // ---- heads: columns 0..pc-1 = policy conv channels, column pc = value conv ----
+                    // ---- heads (1x1: centre accumulator): columns 0..pc-1 = policy conv channels, column pc = value conv ----
                     float v[16], w[16];
-                    tmem_ld16x2(t_lane, t_lane + HEAD_N, v, w);
+                    tmem_ld16x2(t_lane + ACC_COLS, t_lane + ACC_COLS + HEAD_N, v, w);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                     const int pc = net.policy_channels;
@@ -365,12 +470,22 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                         if (lane == 0 && tile * 2 + warp < batch) value[tile * 2 + warp] = tanhf(s + net.vfc2_w[64]);
                     }
+                    named_bar(2, 128);           // head scratch aliases the residual buffer of the next tile
+                    t_head += clock64() - t_layer;
                 }
             }
         }
+        if (m == 0 && net.timing) {
+            net.timing[blockIdx.x * 12 + 4] = t_bar; net.timing[blockIdx.x * 12 + 5] = t_acc; net.timing[blockIdx.x * 12 + 6] = t_head;
+            net.timing[blockIdx.x * 12 + 7] = clock64() - t0;
+        }
+    }
+    if (threadIdx.x == 0 && net.timing) {
+        // (only reached by the epilogue branch's thread 0)
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                               // no CTA leaves while peers may still signal its barriers
     if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -481,6 +596,20 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     for (int j = 0; j < 64; ++j)
         for (int k = 0; k < 64; ++k) vfc1_wt[(size_t)k * 64 + j] = p->value_fc1_w[(size_t)j * 64 + k];
     vfc2_w.push_back(p->value_fc2_b[0]);
+    constexpr int REPLICAS = 8;
+    const size_t one = units.size();
+    units.resize(one * REPLICAS);
+    for (int r = 1; r < REPLICAS; ++r) std::copy(units.begin(), units.begin() + one, units.begin() + r * one);
+    e->dev.wunits_bytes = (long long)(one * sizeof(float));
+    e->dev.replicas = REPLICAS;
+    e->dev.debug = getenv("SPRL_EVALNET_DEBUG") ? atoi(getenv("SPRL_EVALNET_DEBUG")) : 0;
+    if (getenv("SPRL_EVALNET_TIMING") && !e->dev.timing) {
+        std::vector<long long> z(1024 * 12, 0);
+        const long long* tp = nullptr;
+        if (!e->upload(z, &tp)) e->dev.timing = const_cast<long long*>(tp);
+    }
+    e->dev.nst = MAX_NST;
+    while (e->dev.nst > 2 && smem_bytes_for(L, e->dev.nst) > MAX_SMEM) e->dev.nst -= 1;
     int rc = e->upload(units, &e->dev.wunits);
     if (!rc) rc = e->upload(bias, &e->dev.bias);
     if (!rc) rc = e->upload(pfc_wt, &e->dev.pfc_wt);
@@ -542,7 +671,7 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err)); }
     if (prop.major != 10) { delete e; return fail(SPRL_E_NOGPU, "the tcgen05 evaluator needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
     e->sm_count = prop.multiProcessorCount;
-    err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     rc = pack_and_upload(e, params);
     if (rc) { e->release(); delete e; return rc; }
@@ -570,10 +699,21 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     cudaError_t err = cudaSetDevice(e->device);
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
     const long long tiles = (batch + 1) / 2;
-    const int grid = (int)std::min<long long>(tiles, e->sm_count);
-    k_evalnet<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(e->dev, d_in, (long long)batch, d_logits, d_value);
+    const int max_grid = e->sm_count / CLUSTER * CLUSTER;
+    const int grid = (int)std::min<long long>((tiles + CLUSTER - 1) / CLUSTER * CLUSTER, max_grid);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes_for(e->dev.n_layers, e->dev.nst);
+    cfg.stream = (cudaStream_t)cuda_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, k_evalnet, e->dev, d_in, (long long)batch, d_logits, d_value);
     e->launches += 1;
-    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "k_evalnet launch failed: %s", cudaGetErrorString(err));
     return SPRL_OK;
 }
@@ -586,6 +726,13 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
     err = cudaMemcpy(&flag, e->dev.error_flag, sizeof(flag), cudaMemcpyDeviceToHost);
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "evaluator kernel failed: %s", cudaGetErrorString(err));
     if (flag) return fail(SPRL_E_CUDA, "evaluator kernel timed out on a pipeline barrier (code %llx)", flag);
+    if (e->dev.timing) {
+        std::vector<long long> t(12 * 4);
+        cudaMemcpy(t.data(), e->dev.timing, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int b = 0; b < 2; ++b)
+            fprintf(stderr, "[evalnet timing, CTA %d, last launch] mma: bar %lld full %lld total %lld | epi: bar %lld acc %lld heads %lld total %lld | producer: empty %lld total %lld\n",
+                    b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 2], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9]);
+    }
     if (launches) *launches = e->launches;
     return SPRL_OK;
 }
