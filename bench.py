@@ -7,9 +7,11 @@
 
 A *step* of our arm is `--rounds` search rounds of `--slots` concurrent games in
 continuous play (a slot starts its next game when one ends): every round is one
-search launch over all trees (select / expand / backup / re-root kernels), one forward
-of the reference's traced fp32 network on the leaf batch those trees produced, and the
-application of its outputs in the next launch.  `value` is MCTS simulations per second,
+search launch over all trees (select / expand / backup / re-root), one forward of the
+reference's network (same architecture and weights as the traced module; run by the
+library's tcgen05 kernel with fp32-level 3xTF32 arithmetic, or by LibTorch/cuDNN fp32
+with --evaluator libtorch) on the leaf batch those trees produced, and the application
+of its outputs in the next launch.  `value` is MCTS simulations per second,
 whole job, from device counters over exactly K timed steps; moves/s etc. ride along.
 `e2e` is the same metric through the public API with host buffers: each e2e step loads
 the network weights from pinned host memory, plays `--e2e-games` full games from the
@@ -29,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 SIMS, MAX_BATCH, MAX_QUEUE, EPS, ALPHA = 400, 8, 4, 0.25, 0.3
 WORKLOAD = "othello8x8_selfplay_400sims_batch8_queue4_d4sym_net2x64_fp32"
+NET_FLOP_PER_LEAF = 2 * (64 * 27 * 64 + 4 * 64 * 64 * 9 * 64 + 3 * 64 * 64 + 128 * 65 + 64 * 64 + 64)   # 19.1 MFLOP
 
 
 def parse():
@@ -44,6 +47,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--evaluator", default="evalnet", choices=["evalnet", "libtorch"],
+                    help="network forward: the library's tcgen05 kernel (default) or the traced module through LibTorch/cuDNN")
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU work per reference step (bounded sample)")
     return ap.parse_args()
 
@@ -135,6 +140,15 @@ def run_ours(args):
     flat_params = [p for p in module.parameters()] + [b for b in module.buffers()]
     weight_bytes = sum(t.numel() * t.element_size() for t in flat_params)
 
+    from sprl_b200.evalnet import EvalNet
+    evalnet = EvalNet(net, device=local) if args.evaluator == "evalnet" else None
+
+    def attach(engine):
+        if evalnet is not None:
+            engine.attach_evalnet(evalnet, use_cuda_graph=not args.no_graph)
+        else:
+            engine.attach_network(module, use_cuda_graph=not args.no_graph)
+
     def broadcast_weights(generation):
         """New generation: rank 0 draws fresh random-init weights, NCCL broadcasts the flat
         parameter + buffer vector; every rank updates its module in place."""
@@ -152,13 +166,25 @@ def run_ours(args):
                 n = t.numel()
                 t.copy_(flat[at:at + n].reshape(t.shape).to(t.dtype))
                 at += n
+        if evalnet is not None:
+            evalnet.update(module)          # fold BN, split hi/lo, re-pack in place (device addresses stay valid)
+
+    # ---- evaluator accuracy on this box: ours vs the fp64 forward of the same network (CPU)
+    eval_err = None
+    if evalnet is not None and rank == 0:
+        xs = (torch.rand(512, 3, 8, 8) > 0.5).float()
+        with torch.no_grad():
+            want = make_network("othello", seed=0).double()(xs.double())[0]
+            got = evalnet(xs.to(dev))[0].cpu().double()
+        eval_err = float((got - want).abs().max())
+        assert eval_err < 1e-4, f"evaluator deviates from the fp64 forward by {eval_err}"
 
     # ---- steady-state engine: continuous play, games sharded by id % world
     games_cap = args.slots * 24
     eng = SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=0, sims=SIMS, max_batch=MAX_BATCH,
                     max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=args.slots, max_games=games_cap)
     eng.set_game_stride(world)
-    eng.attach_network(module, use_cuda_graph=not args.no_graph)
+    attach(eng)
     broadcast_weights(0)
     with torch.cuda.device(dev):
         eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
@@ -235,33 +261,47 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bps * sims_per_launch / (k_ms / 1e3) / 1e9
-    roofline = {"kernel": "k_round<Othello>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": None,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
-                "select_depth": round(D, 3), "legal_per_node": round(L, 3), "evals_per_sim": round(ef, 4),
-                "sampled_launches": n_probe, "network_forward_ms": round(nn_ms, 4),
-                "search_share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
-
+    roofline_search = {"kernel": "k_round<Othello>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                       "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                       "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
+                       "select_depth": round(D, 3), "legal_per_node": round(L, 3), "evals_per_sim": round(ef, 4),
+                       "sampled_launches": n_probe, "share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
+    batch_rows = args.slots * MAX_QUEUE
+    if evalnet is not None:
+        # dominant kernel of the step: the evaluator's forward (every row of the leaf batch is computed)
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        tf = batch_rows * NET_FLOP_PER_LEAF / (nn_ms / 1e3) / 1e12
+        roofline = {"kernel": "k_evalnet", "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": round(tf / tpeak, 5), "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                    "launch_ms": round(nn_ms, 4), "leaves_per_launch": batch_rows, "flop_per_leaf": NET_FLOP_PER_LEAF,
+                    "note": "achieved = algorithmic fp32 FLOPs / time; the kernel issues 3x that on the tensor cores (3xTF32 split) "
+                            "at the TF32 rate, which is half the bf16 peak: tensor-pipe-equivalent fraction = 6 x frac",
+                    "tensor_pipe_equivalent_frac": round(6 * tf / tpeak, 4), "share_of_round": round(nn_ms / (k_ms + nn_ms), 4)}
+    else:
+        roofline = dict(roofline_search, network_forward_ms=round(nn_ms, 4))
     result = {
         "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(value, 1), "unit": "sims/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 (tree statistics fp32; network 3xTF32 split on tcgen05, fp32 accumulate)" if evalnet is not None else "fp32",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "sims_per_move": SIMS, "max_batch": MAX_BATCH, "max_queue": MAX_QUEUE,
                    "slots_per_gpu": args.slots, "rounds_per_step": args.rounds, "network_params": n_params,
                    "sharding": "game_id % world, no data collective; NCCL broadcast of weights per generation",
                    "l2": "working set (tree slabs %.1f GB + leaf batch) exceeds the 126 MB L2" % (st["device_bytes"] / 1e9),
-                   "cuda_graph": not args.no_graph},
+                   "cuda_graph": not args.no_graph, "evaluator": args.evaluator,
+                   "evaluator_max_abs_logit_err_vs_fp64": eval_err},
         "moves_per_sec": round(moves / (ms / 1e3), 1), "evals_per_sec": round(evals / (ms / 1e3), 1),
         "samples_per_sec": round(8 * moves / (ms / 1e3), 1), "games_finished": int(games),
-        "gpu_launches": int(args.steps * args.rounds * world),
-        "roofline": roofline, "clocks": clocks,
+        "gpu_launches": int(args.steps * args.rounds * world * (2 if evalnet is not None else 1)),
+        "roofline": roofline, "roofline_search": roofline_search, "clocks": clocks,
     }
 
     if not args.no_e2e:
-        e2e = run_e2e(args, local, module, flat_params, weight_bytes, barrier)     # every rank, on its own shard
+        e2e = run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet)     # every rank, on its own shard
         agg = torch.tensor([e2e.pop("_sims"), e2e.pop("_moves")], dtype=torch.float64, device=dev)
         tm = torch.tensor([e2e.pop("_ms")], dtype=torch.float64, device=dev)
         if world > 1:
@@ -280,7 +320,7 @@ def run_ours(args):
         print(json.dumps(result))
 
 
-def run_e2e(args, local, module, flat_params, weight_bytes, barrier):
+def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
     """Full iterations through the public API with host buffers: weights H2D from pinned
     memory, run_iteration of full games, samples D2H."""
     import numpy as np
@@ -292,12 +332,20 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier):
     G = args.e2e_games
     with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=1, sims=SIMS, max_batch=MAX_BATCH,
                    max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=G, max_games=G) as eng:
-        eng.attach_network(module, use_cuda_graph=not args.no_graph)
+        if evalnet is not None:
+            eng.attach_evalnet(evalnet, use_cuda_graph=not args.no_graph)
+            host_state = {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+            weight_bytes = evalnet.info()["upload_bytes"]
+        else:
+            eng.attach_network(module, use_cuda_graph=not args.no_graph)
 
         def one(first):
-            with torch.no_grad():
-                for t, h in zip(flat_params, host_weights):
-                    t.copy_(h, non_blocking=True)
+            if evalnet is not None:
+                evalnet.update(host_state)          # host weights -> folded / packed -> device, inside the timed region
+            else:
+                with torch.no_grad():
+                    for t, h in zip(flat_params, host_weights):
+                        t.copy_(h, non_blocking=True)
             return eng.run_iteration(G, first_game=first)
 
         # warm-up: a short iteration with the same engine (graph capture, cuDNN autotune)

@@ -226,6 +226,8 @@ int sprl_evalnet_forward(sprl_evalnet* net, const float* d_in, int64_t batch, fl
                          void* cuda_stream);
 /* Synchronises the device and reports a kernel-side failure, if any. */
 int sprl_evalnet_status(sprl_evalnet* net, uint64_t* launches);
+/* Bytes copied host -> device by one create / update, weight-ring depth and shared memory per CTA. */
+int sprl_evalnet_info(sprl_evalnet* net, int64_t* upload_bytes, int32_t* ring_stages, int32_t* smem_bytes);
 void sprl_evalnet_destroy(sprl_evalnet* net);
 
 #ifdef __cplusplus

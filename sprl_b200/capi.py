@@ -22,7 +22,7 @@ EXPORTS = [
     "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
     "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
-    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_status", "sprl_evalnet_destroy",
+    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_destroy",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.sprl_evalnet_update.argtypes = [C.c_void_p, C.POINTER(NetworkParams)]
     lib.sprl_evalnet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sprl_evalnet_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.sprl_evalnet_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.sprl_evalnet_destroy.restype = None
     lib.sprl_evalnet_destroy.argtypes = [C.c_void_p]
     lib.sprl_default_config.argtypes = [C.c_int, C.POINTER(Config)]

@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
 struct LayerGeom { int taps, ksteps, n, units_per_tap, lo_pass; };
 __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
     LayerGeom g;
-    if (layer == 0) { g.taps = 9; g.ksteps = in_ksteps; g.n = CH; g.lo_pass = 0; }          // 0/1 planes are exact in tf32
+    if (layer == 0) { g.taps = 9; g.ksteps = in_ksteps; g.n = CH; g.lo_pass = 1; }
     else if (layer == n_layers - 1) { g.taps = 1; g.ksteps = CH / 8; g.n = HEAD_N; g.lo_pass = 1; }
     else { g.taps = 9; g.ksteps = CH / 8; g.n = CH; g.lo_pass = 1; }
     g.units_per_tap = (g.ksteps + 3) / 4;
@@ -375,7 +375,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = tile * 2 + b;
-            // ---- input planes -> image (0/1 values: hi = value, lo = 0) ----
+            // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split) ----
             for (int cg = 0; cg < 2 * net.in_ksteps; ++cg) {
                 float v[4];
 #pragma unroll
@@ -383,8 +383,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     const int p = cg * 4 + j;
                     v[j] = (p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
                 }
-                a_hi[cg * SLOTS + slot] = make_float4(v[0], v[1], v[2], v[3]);
-                a_lo[cg * SLOTS + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float4 h = make_float4(tf32_round(v[0]), tf32_round(v[1]), tf32_round(v[2]), tf32_round(v[3]));
+                a_hi[cg * SLOTS + slot] = h;
+                a_lo[cg * SLOTS + slot] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
             }
             proxy_fence();
             for (int layer = 0; layer < n_layers; ++layer) {
@@ -529,6 +530,7 @@ struct sprl_evalnet {
     std::vector<void*> allocations;
     int sm_count = 0;
     uint64_t launches = 0;
+    int64_t upload_bytes = 0;      // host -> device bytes of one weight load
     // First call allocates; later calls (a new generation's weights) overwrite in place, so device
     // pointers captured in a CUDA graph stay valid.
     template <typename T> int upload(const std::vector<T>& h, const T** out) {
@@ -540,6 +542,7 @@ struct sprl_evalnet {
             allocations.push_back(p);
         }
         err = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        upload_bytes += (int64_t)(h.size() * sizeof(T));
         if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(err));
         *out = (const T*)p;
         return SPRL_OK;
@@ -596,7 +599,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     for (int j = 0; j < 64; ++j)
         for (int k = 0; k < 64; ++k) vfc1_wt[(size_t)k * 64 + j] = p->value_fc1_w[(size_t)j * 64 + k];
     vfc2_w.push_back(p->value_fc2_b[0]);
-    constexpr int REPLICAS = 8;
+    e->upload_bytes = 0;
+    constexpr int REPLICAS = 2;
     const size_t one = units.size();
     units.resize(one * REPLICAS);
     for (int r = 1; r < REPLICAS; ++r) std::copy(units.begin(), units.begin() + one, units.begin() + r * one);
@@ -734,6 +738,14 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
                     b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 2], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9]);
     }
     if (launches) *launches = e->launches;
+    return SPRL_OK;
+}
+
+int sprl_evalnet_info(sprl_evalnet* e, int64_t* upload_bytes, int32_t* ring_stages, int32_t* smem_bytes) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    if (upload_bytes) *upload_bytes = e->upload_bytes;
+    if (ring_stages) *ring_stages = e->dev.nst;
+    if (smem_bytes) *smem_bytes = smem_bytes_for(e->dev.n_layers, e->dev.nst);
     return SPRL_OK;
 }
 

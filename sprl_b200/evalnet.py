@@ -87,6 +87,11 @@ class EvalNet:
                          torch.cuda.current_stream(x.device).cuda_stream)
         return logits, value.reshape(-1, 1)
 
+    def info(self):
+        up, st, sm = C.c_int64(), C.c_int32(), C.c_int32()
+        capi.check(self.lib.sprl_evalnet_info(self.handle, C.byref(up), C.byref(st), C.byref(sm)))
+        return dict(upload_bytes=up.value, ring_stages=st.value, smem_bytes=sm.value)
+
     def status(self):
         n = C.c_uint64()
         capi.check(self.lib.sprl_evalnet_status(self.handle, C.byref(n)))

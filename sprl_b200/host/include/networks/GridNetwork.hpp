@@ -3,8 +3,10 @@
 // constructor (a TorchScript path, or "random" to load nothing).  The reference moves the
 // module to torch::kCPU and fills a host tensor element by element (:70-97); here the module
 // lives on the engine's GPU and is run directly on the leaf-batch buffer the search kernel
-// wrote (torch::from_blob, no copy, no host round trip).  exp / mask / normalise of the
-// outputs (:107-142) happen in the next search launch, on the device.
+// wrote (no copy, no host round trip).  For 8x8 boards the forward pass itself is the library's
+// tcgen05 kernel (sprl_evalnet_*, csrc/evalnet.cu) fed with the module's parameters; other
+// boards, or SPRL_EVALUATOR=libtorch, run the TorchScript module through LibTorch/cuDNN.
+// exp / mask / normalise of the outputs (:107-142) happen in the next search launch, on the device.
 #ifndef SPRL_GRID_NETWORK_HPP
 #define SPRL_GRID_NETWORK_HPP
 
@@ -14,6 +16,10 @@
 #include <torch/torch.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
 
 namespace SPRL {
 
@@ -49,11 +55,15 @@ public:
         *d_in = m_input.data_ptr<float>();
         *d_logits = m_logits.data_ptr<float>();
         *d_value = m_value.data_ptr<float>();
+        const char* ev = std::getenv("SPRL_EVALUATOR");
+        if (!(ev && std::strcmp(ev, "libtorch") == 0)) createEvalnet(device, planes, rows, cols, actions);
         return 0;
     }
 
+    ~GridNetwork() { if (m_evalnet) sprl_evalnet_destroy(m_evalnet); }
+
     int forward(const float* d_in, int64_t batch, float* d_logits, float* d_value, void* stream) override {
-        (void)batch;
+        if (m_evalnet) return sprl_evalnet_forward(m_evalnet, d_in, batch, d_logits, d_value, stream);
         if (d_in != m_input.data_ptr<float>() || d_logits != m_logits.data_ptr<float>() || d_value != m_value.data_ptr<float>()) return -2;
         torch::NoGradGuard no_grad;
         c10::cuda::CUDAStream s = c10::cuda::getStreamFromExternal((cudaStream_t)stream, m_device.index());
@@ -65,6 +75,45 @@ public:
     }
 
 private:
+    // Hands the module's parameters (names of src/networks/grid_networks.py:30-80) to the library's
+    // evaluator; on any mismatch (board size, head shape) the TorchScript forward stays in use.
+    void createEvalnet(int device, int planes, int rows, int cols, int actions) {
+        std::map<std::string, torch::Tensor> sd;
+        for (const auto& p : m_model->named_parameters()) sd[p.name] = p.value.detach().to(torch::kCPU).to(torch::kFloat32).contiguous();
+        for (const auto& b : m_model->named_buffers()) sd[b.name] = b.value.detach().to(torch::kCPU).to(torch::kFloat32).contiguous();
+        auto ptr = [&](const std::string& k) -> const float* { auto it = sd.find(k); return it == sd.end() ? nullptr : it->second.data_ptr<float>(); };
+        auto convbn = [&](const std::string& c, const std::string& b) {
+            sprl_conv_bn_params q { ptr(c + ".weight"), ptr(c + ".bias"), ptr(b + ".weight"), ptr(b + ".bias"), ptr(b + ".running_mean"), ptr(b + ".running_var") };
+            return q;
+        };
+        if (!sd.count("conv.weight") || !sd.count("policy_fc.weight") || !sd.count("value_fc1.weight")) return;
+        int blocks = 0;
+        while (sd.count("residual_blocks." + std::to_string(blocks) + ".conv1.weight")) ++blocks;
+        std::vector<sprl_conv_bn_params> tower;
+        for (int i = 0; i < blocks; ++i) {
+            const std::string b = "residual_blocks." + std::to_string(i);
+            tower.push_back(convbn(b + ".conv1", b + ".bn1"));
+            tower.push_back(convbn(b + ".conv2", b + ".bn2"));
+        }
+        sprl_network_params p {};
+        p.rows = rows; p.cols = cols; p.in_planes = planes; p.channels = (int)sd["conv.weight"].size(0); p.blocks = blocks; p.actions = actions;
+        p.policy_channels = (int)sd["policy_conv.weight"].size(0); p.value_channels = (int)sd["value_conv.weight"].size(0);
+        p.value_hidden = (int)sd["value_fc1.weight"].size(0); p.bn_eps = 1e-5f;
+        p.stem = convbn("conv", "bn"); p.tower = tower.data();
+        p.policy_conv_w = ptr("policy_conv.weight"); p.policy_conv_b = ptr("policy_conv.bias");
+        p.policy_fc_w = ptr("policy_fc.weight"); p.policy_fc_b = ptr("policy_fc.bias");
+        p.value_conv_w = ptr("value_conv.weight"); p.value_conv_b = ptr("value_conv.bias");
+        p.value_fc1_w = ptr("value_fc1.weight"); p.value_fc1_b = ptr("value_fc1.bias");
+        p.value_fc2_w = ptr("value_fc2.weight"); p.value_fc2_b = ptr("value_fc2.bias");
+        if (sprl_evalnet_create(device, &p, &m_evalnet) != SPRL_OK) {
+            m_evalnet = nullptr;
+            std::cout << "Evaluator: TorchScript module through LibTorch (" << sprl_last_error() << ")" << std::endl;
+        } else {
+            std::cout << "Evaluator: tcgen05 network kernel of libsprl_b200" << std::endl;
+        }
+    }
+
+    sprl_evalnet* m_evalnet { nullptr };
     std::string m_path;
     torch::Device m_device { torch::kCPU };
     std::shared_ptr<torch::jit::script::Module> m_model;

@@ -1,0 +1,137 @@
+"""The library's evaluator network (csrc/evalnet.cu, sprl_evalnet_*) against the fp64 / fp32
+PyTorch forward of the same `BasicGridNetwork` (the module the reference traces,
+src/networks/grid_networks.py:30-80).  Floating-point kernel: tolerance, stated per test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from sprl_b200 import capi
+from sprl_b200.evalnet import EvalNet, network_params
+from sprl_b200.network import BasicGridNetwork, make_network
+
+
+def randomized(net, seed):
+    """Non-trivial BatchNorm statistics so that the folding is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.rand(mod.running_mean.shape, generator=g) - 0.5)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 1.5 + 0.5)
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+                mod.bias.copy_(torch.rand(mod.bias.shape, generator=g) - 0.5)
+    return net
+
+
+# ------------------------------------------------------------------ CPU: argument validation
+def test_evalnet_rejects_unsupported_shapes():
+    lib = capi.load()
+    h = C.c_void_p()
+    # Connect Four board (6x7): stays on the TorchScript path
+    p, keep = network_params(make_network("c4", 0).state_dict(), rows=6, cols=7)
+    assert lib.sprl_evalnet_create(0, C.byref(p), C.byref(h)) == capi.SPRL_E_INVALID and not h
+    assert b"8x8" in lib.sprl_last_error()
+    # wrong tower width
+    p, keep = network_params(BasicGridNetwork(8, 8, 65, 1, 1, 32).state_dict())
+    assert lib.sprl_evalnet_create(0, C.byref(p), C.byref(h)) == capi.SPRL_E_INVALID
+    # null pointer inside the parameter block
+    p, keep = network_params(make_network("othello", 0).state_dict())
+    p.policy_fc_w = None
+    assert lib.sprl_evalnet_create(0, C.byref(p), C.byref(h)) == capi.SPRL_E_INVALID
+    assert lib.sprl_evalnet_create(0, None, C.byref(h)) == capi.SPRL_E_INVALID
+    assert lib.sprl_evalnet_forward(None, None, 4, None, None, None) == capi.SPRL_E_INVALID
+
+
+def test_network_params_follow_the_state_dict():
+    net = make_network("othello", 3)
+    p, keep = network_params(net.state_dict())
+    assert (p.rows, p.cols, p.in_planes, p.channels, p.blocks, p.actions) == (8, 8, 3, 64, 2, 65)
+    assert (p.policy_channels, p.value_channels, p.value_hidden) == (2, 1, 64)
+    w = np.ctypeslib.as_array(C.cast(p.tower[3].weight, C.POINTER(C.c_float)), shape=(64 * 64 * 9,))
+    assert np.array_equal(w, net.residual_blocks[1].conv2.weight.detach().numpy().reshape(-1))
+
+
+# ------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,blocks,planes", [(1, 2, 3), (2, 2, 3), (257, 2, 3), (4099, 2, 3), (64, 0, 3), (130, 6, 3), (96, 1, 17)])
+def test_evalnet_matches_fp64_forward(batch, blocks, planes):
+    """|dlogit| and |dvalue| <= 2e-6 against the fp64 forward (the fp32 PyTorch forward itself is
+    within ~2e-7); odd batches, tower depths 0..6 and multi-k-step stems (17 planes)."""
+    torch.manual_seed(blocks * 7 + planes)
+    net = randomized(BasicGridNetwork(8, 8, 65, (planes - 1) // 2, blocks, 64).eval(), 5)
+    x = (torch.rand(batch, planes, 8, 8) > 0.5).float()
+    with torch.no_grad():
+        want_l, want_v = net.double()(x.double())
+        net.float()
+    ev = EvalNet(net, device=0)
+    got_l, got_v = ev(x.cuda())
+    ev.status()
+    assert got_l.shape == (batch, 65) and got_v.shape == (batch, 1)
+    assert (got_l.cpu().double() - want_l).abs().max().item() <= 2e-6
+    assert (got_v.cpu().double() - want_v).abs().max().item() <= 2e-6
+    ev.close()
+
+
+@pytest.mark.gpu
+def test_evalnet_real_valued_inputs():
+    """The reference's planes are 0/1, but the kernel splits any fp32 input into hi + lo."""
+    net = randomized(make_network("othello", 1), 2)
+    x = torch.rand(64, 3, 8, 8)
+    with torch.no_grad():
+        want = net(x)[0]
+    got = EvalNet(net, device=0)(x.cuda())[0].cpu()
+    assert (got - want).abs().max().item() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_evalnet_update_in_place_and_batches_in_a_row():
+    a, b = randomized(make_network("othello", 1), 1), randomized(make_network("othello", 2), 2)
+    x = (torch.rand(300, 3, 8, 8) > 0.5).float()
+    ev = EvalNet(a, device=0)
+    xg = x.cuda()
+    la = ev(xg)[0].cpu()
+    ev.update(b)
+    lb = ev(xg)[0].cpu()
+    with torch.no_grad():
+        assert (la - a(x)[0]).abs().max().item() <= 2e-6 and (lb - b(x)[0]).abs().max().item() <= 2e-6
+    assert (la - lb).abs().max().item() > 1e-3
+    for n in (1, 7, 300, 33):                      # different grid sizes back to back
+        assert torch.equal(ev(xg[:n])[0].cpu(), lb[:n])
+    assert ev.status() >= 6
+    with pytest.raises(capi.SprlError):
+        ev.update(make_network("c4", 0))           # shape change is refused
+
+
+@pytest.mark.gpu
+def test_selfplay_with_evalnet_tracks_libtorch():
+    """Same games through both evaluators: the tree statistics are discontinuous in the priors, so
+    compare what is continuous -- the first move's root priors (one forward) -- and that whole
+    games finish with well-formed samples."""
+    from sprl_b200 import selfplay as SP
+    from sprl_b200.network import trace_network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = randomized(make_network("othello", 4), 4)
+    kw = dict(seed=8, sims=48, max_batch=8, max_queue=4, num_slots=16, max_games=16, record_stats=1, add_noise=0)
+    out = {}
+    for kind in ("evalnet", "libtorch"):
+        with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, **kw) as eng:
+            if kind == "evalnet":
+                ev = EvalNet(net, device=0)
+                eng.attach_evalnet(ev, use_cuda_graph=True)
+            else:
+                eng.attach_network(trace_network(net, torch.device("cuda", 0)), use_cuda_graph=False)
+            states, dists, outcomes = eng.run_iteration(16)
+            ms = eng.move_stats(16)
+            out[kind] = (ms, states, dists, outcomes)
+        if kind == "evalnet":
+            ev.status()
+    (ma, sa, da, oa), (mb, sb, db, ob) = out["evalnet"], out["libtorch"]
+    first_a = np.concatenate([[0], np.cumsum(ma["game_moves"])[:-1]])
+    first_b = np.concatenate([[0], np.cumsum(mb["game_moves"])[:-1]])
+    assert np.allclose(ma["move_P"][first_a], mb["move_P"][first_b], atol=1e-5)
+    for s, d, o in ((sa, da, oa), (sb, db, ob)):
+        assert s.shape[0] == d.shape[0] == o.shape[0] and s.shape[0] % 8 == 0
+        assert np.allclose(d.sum(1), 1.0, atol=1e-5) and set(np.unique(o)) <= {-1.0, 0.0, 1.0}

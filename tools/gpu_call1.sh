@@ -1,7 +1,7 @@
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 bash tools/worker_smoke.sh > gpurun_out/worker_smoke.log 2>&1; echo worker rc=$?
-bash tools/worker_smoke.sh sprl_b200/host/bin/ref_OTHWorker > gpurun_out/worker_smoke_ref.log 2>&1; echo refworker rc=$?
+
 python tools/explore_nn.py 32768 > gpurun_out/explore_nn.log 2>&1
 python bench.py > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; echo bench rc=$?
 python bench.py --steps 1 --warmup 3 --rounds 16 --no-e2e --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --rounds 16 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
