@@ -49,7 +49,11 @@ constexpr int SLOTS = 160;                   // 20 storage rows x 8 cells
 constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the image
 constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 40,960
 constexpr int RES_BYTES = NCG * TILE_M * 16; // 32,768
-constexpr int UNIT_BYTES = 16384;            // one weight unit: [K/4 <= 8][2*64][4] floats
+#ifndef SPRL_EVALNET_UNIT_KSTEPS
+#define SPRL_EVALNET_UNIT_KSTEPS 8
+#endif
+constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (8 input channels each) per weight unit
+constexpr int UNIT_BYTES = UNIT_KS * 8 * 2 * CH * 4;   // [K/4][2*64][4] floats: 32 KB for a whole tap
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
@@ -66,9 +70,6 @@ constexpr int MAX_SMEM = 232448;             // 227 KB
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + IMG_BYTES;
 constexpr int OFF_RES = OFF_ALO + IMG_BYTES;
-constexpr int OFF_PBUF = OFF_RES;                                // head scratch aliases the residual buffer
-constexpr int OFF_VBUF = OFF_PBUF + 2 * 128 * 4;                 // [2][64]
-constexpr int OFF_HBUF = OFF_VBUF + 2 * 64 * 4;                  // [2][64]
 constexpr int OFF_RING = OFF_RES + RES_BYTES;                    // 114,688
 
 struct NetDev {
@@ -87,6 +88,7 @@ struct NetDev {
     int actions;
     int policy_channels;     // 2
     int nst;                 // ring stages
+    float* head_act;         // [batch][(policy_channels + 1) * 64]: ReLU'd 1x1-conv head activations, consumed by k_heads
     unsigned long long* error_flag;
     long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
     int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue
@@ -216,10 +218,10 @@ __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_
     if (layer == 0) { g.taps = 9; g.ksteps = in_ksteps; g.n = CH; g.lo_pass = 1; }
     else if (layer == n_layers - 1) { g.taps = 1; g.ksteps = CH / 8; g.n = HEAD_N; g.lo_pass = 1; }
     else { g.taps = 9; g.ksteps = CH / 8; g.n = CH; g.lo_pass = 1; }
-    g.units_per_tap = (g.ksteps + 3) / 4;
+    g.units_per_tap = (g.ksteps + UNIT_KS - 1) / UNIT_KS;
     return g;
 }
-__host__ __device__ inline int unit_ksteps(const LayerGeom& g, int u) { return g.ksteps - 4 * u < 4 ? g.ksteps - 4 * u : 4; }
+__host__ __device__ inline int unit_ksteps(const LayerGeom& g, int u) { return g.ksteps - UNIT_KS * u < UNIT_KS ? g.ksteps - UNIT_KS * u : UNIT_KS; }
 __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return unit_ksteps(g, u) * 8 * 2 * g.n * 4; }
 
 // slot of cell m (TMEM lane m) in the activation image: rows of the two boards interleaved,
@@ -304,7 +306,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
     } else if (warp == 4) {
         // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) =====
         uint32_t s = 0, ph = 0;
-        long long t_bar = 0, t_full = 0, t0 = clock64();
+        long long t_bar = 0, t_full = 0, t_issue = 0, t_commit = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer) {
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
@@ -326,17 +328,18 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                         const int nks = unit_ksteps(g, u);
                         { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
                         tc_fence_after();
+                        const long long t_i0 = clock64();
                         const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
-                        const uint64_t ah = a_hi0 + a_off + (uint32_t)(4 * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(4 * u) * A_KSTEP;
+                        const uint64_t ah = a_hi0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP;
                         uint32_t acc = (started >> dxi) & 1u;
-                        if (nks == 4) {
+                        if (nks == UNIT_KS) {
                             if (hi_pass) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
+                                for (int ks = 0; ks < UNIT_KS; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
                             }
                             if (lo_pass) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
+                                for (int ks = 0; ks < UNIT_KS; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
                             }
                         } else {
                             if (hi_pass)
@@ -345,7 +348,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                                 for (int ks = 0; ks < nks; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
                         }
                         started |= 1u << dxi;
-                        umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
+                        const long long t_i1 = clock64();
+                        umma_commit_multicast(bar_empty + 8 * s, CMASK);
+                        t_issue += t_i1 - t_i0; t_commit += clock64() - t_i1;   // every CTA's producer learns that this CTA is done with the unit
                         if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -354,7 +359,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
             }
         }
         if (lane == 0 && net.timing) {
-            net.timing[blockIdx.x * 12 + 0] = t_bar; net.timing[blockIdx.x * 12 + 1] = t_full; net.timing[blockIdx.x * 12 + 2] = clock64() - t0;
+            net.timing[blockIdx.x * 12 + 0] = t_bar; net.timing[blockIdx.x * 12 + 1] = t_full; net.timing[blockIdx.x * 12 + 2] = clock64() - t0; net.timing[blockIdx.x * 12 + 3] = t_issue; net.timing[blockIdx.x * 12 + 10] = t_commit;
         }
     } else {
         // ===== epilogue warps: cell m = TMEM lane m =====
@@ -367,9 +372,6 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
         float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
         float4* res = reinterpret_cast<float4*>(smem + OFF_RES);
-        float* pbuf = reinterpret_cast<float*>(smem + OFF_PBUF);
-        float* vbuf = reinterpret_cast<float*>(smem + OFF_VBUF);
-        float* hbuf = reinterpret_cast<float*>(smem + OFF_HBUF);
         const int cells = 64, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
@@ -435,43 +437,20 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     }
                     proxy_fence();
                 } else {
-                    // ---- heads (1x1: centre accumulator): columns 0..pc-1 = policy conv channels, column pc = value conv ----
+                    // ---- heads (1x1: centre accumulator): columns 0..pc-1 = policy conv channels, column pc = value conv.
+                    // The ReLU'd activations go to global memory; the fully connected layers run in k_heads
+                    // (they need 49 KB of weights that this kernel's shared memory has no room for).
                     float v[16], w[16];
                     tmem_ld16x2(t_lane + ACC_COLS, t_lane + ACC_COLS + HEAD_N, v, w);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                     const int pc = net.policy_channels;
+                    if (board < batch) {
+                        float* dst = net.head_act + board * (long long)((pc + 1) * 64);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < pc) pbuf[b * 128 + j * 64 + cell] = fmaxf(v[j] + bias[j], 0.0f);
-                    float vv = pc == 1 ? v[1] : (pc == 2 ? v[2] : (pc == 3 ? v[3] : v[4]));
-                    vbuf[b * 64 + cell] = fmaxf(vv + bias[pc], 0.0f);
-                    tc_fence_before();
-                    named_bar(2, 128);
-                    // policy_fc: 2 boards x actions outputs over 128 threads
-                    const int A = net.actions, K = pc * 64;
-                    for (int item = m; item < 2 * A; item += 128) {
-                        const int bb = item / A, a = item - bb * A;
-                        float s = net.pfc_b[a];
-                        const float* x = pbuf + bb * 128;
-                        for (int k = 0; k < K; ++k) s = fmaf(net.pfc_wt[k * A + a], x[k], s);
-                        if (tile * 2 + bb < batch) logits[(tile * 2 + bb) * A + a] = s;
+                        for (int j = 0; j < 3; ++j)
+                            if (j <= pc) dst[j * 64 + cell] = fmaxf(v[j] + bias[j], 0.0f);
                     }
-                    {   // value_fc1 + ReLU: 2 boards x 64 hidden units
-                        const int bb = m >> 6, j = m & 63;
-                        float s = net.vfc1_b[j];
-                        const float* x = vbuf + bb * 64;
-                        for (int k = 0; k < 64; ++k) s = fmaf(net.vfc1_wt[k * 64 + j], x[k], s);
-                        hbuf[bb * 64 + j] = fmaxf(s, 0.0f);
-                    }
-                    named_bar(2, 128);
-                    if (warp < 2) {  // value_fc2 + tanh: one warp per board
-                        float s = net.vfc2_w[lane] * hbuf[warp * 64 + lane] + net.vfc2_w[lane + 32] * hbuf[warp * 64 + lane + 32];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        if (lane == 0 && tile * 2 + warp < batch) value[tile * 2 + warp] = tanhf(s + net.vfc2_w[64]);
-                    }
-                    named_bar(2, 128);           // head scratch aliases the residual buffer of the next tile
                     t_head += clock64() - t_layer;
                 }
             }
@@ -493,6 +472,81 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
     }
 }
 
+// ---- heads: policy_fc and value_fc1/fc2 over the 1x1-conv activations k_evalnet left in HBM ----
+// 64 boards per CTA, weights staged once in shared memory, 4 boards x 4 outputs per thread.
+constexpr int HB = 64;                        // boards per CTA
+constexpr int HP_STRIDE = 68;                 // policy weight row stride in floats (65 actions padded for float4 loads)
+
+__global__ void __launch_bounds__(256)
+k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restrict__ value) {
+    extern __shared__ __align__(16) float hs[];
+    const int pc = net.policy_channels, K = pc * 64, A = net.actions, IN = (pc + 1) * 64;
+    float* wp = hs;                           // [K][HP_STRIDE]
+    float* wv = wp + K * HP_STRIDE;           // [64][64]
+    float* x = wv + 64 * 64;                  // [HB][IN]
+    float* hid = x + HB * IN;                 // [HB][64]
+    const int t = threadIdx.x;
+    for (int i = t; i < K * HP_STRIDE; i += 256) { const int k = i / HP_STRIDE, a = i - k * HP_STRIDE; wp[i] = a < A ? net.pfc_wt[k * A + a] : 0.0f; }
+    for (int i = t; i < 64 * 64; i += 256) wv[i] = net.vfc1_wt[i];
+    const int ag = t & 15, bg = t >> 4;       // 16 output groups x 16 board groups
+    for (long long b0 = (long long)blockIdx.x * HB; b0 < batch; b0 += (long long)gridDim.x * HB) {
+        __syncthreads();
+        const int nb = (int)(batch - b0 < HB ? batch - b0 : HB);
+        for (int i = t; i < HB * IN; i += 256) x[i] = i < nb * IN ? net.head_act[b0 * IN + i] : 0.0f;
+        __syncthreads();
+        // policy_fc: outputs 4*ag .. 4*ag+3 for boards 4*bg .. 4*bg+3 (+ the outputs beyond 64, one per thread row)
+        for (int a0 = 4 * ag; a0 < A; a0 += 64) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int k = 0; k < K; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(wp + k * HP_STRIDE + a0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xv = x[(4 * bg + i) * IN + k];
+                    acc[i][0] = fmaf(xv, w.x, acc[i][0]); acc[i][1] = fmaf(xv, w.y, acc[i][1]);
+                    acc[i][2] = fmaf(xv, w.z, acc[i][2]); acc[i][3] = fmaf(xv, w.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * bg + i < nb && a0 + j < A) logits[(b0 + 4 * bg + i) * A + a0 + j] = acc[i][j] + net.pfc_b[a0 + j];
+        }
+        {   // value_fc1 + ReLU
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int k = 0; k < 64; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(wv + k * 64 + 4 * ag);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xv = x[(4 * bg + i) * IN + K + k];
+                    acc[i][0] = fmaf(xv, w.x, acc[i][0]); acc[i][1] = fmaf(xv, w.y, acc[i][1]);
+                    acc[i][2] = fmaf(xv, w.z, acc[i][2]); acc[i][3] = fmaf(xv, w.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hid[(4 * bg + i) * 64 + 4 * ag + j] = fmaxf(acc[i][j] + net.vfc1_b[4 * ag + j], 0.0f);
+        }
+        __syncthreads();
+        if (t < nb) {   // value_fc2 + tanh
+            float s = net.vfc2_w[64];
+            for (int j = 0; j < 64; ++j) { const int jj = (j + t) & 63; s = fmaf(net.vfc2_w[jj], hid[t * 64 + jj], s); }   // rotated start: no bank conflicts
+            value[b0 + t] = tanhf(s);
+        }
+    }
+}
+
+static inline size_t heads_smem_bytes(int pc) { return (size_t)(pc * 64 * HP_STRIDE + 64 * 64 + HB * (pc + 1) * 64 + HB * 64) * sizeof(float); }
+
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
 static inline float tf32_rna_host(float x) {
     uint32_t u;
@@ -504,11 +558,11 @@ static inline float tf32_rna_host(float x) {
     return y;
 }
 
-// appends one tap's units for B[n][k] (n < n_pad rows, k < kk): per unit of <= 32 input channels,
+// appends one tap's units for B[n][k] (n < n_pad rows, k < kk): per unit of <= UNIT_KS*8 input channels,
 // layout [K chunk of 4][2*n_pad rows][4], rows 0..n_pad-1 = tf32(w), rows n_pad.. = tf32(w - tf32(w))
 static void append_units(std::vector<float>& out, const std::vector<float>& b, int n_pad, int kk) {
-    for (int k0 = 0; k0 < kk; k0 += 32)
-        for (int kc = k0 / 4; kc < std::min(kk, k0 + 32) / 4; ++kc)
+    for (int k0 = 0; k0 < kk; k0 += UNIT_KS * 8)
+        for (int kc = k0 / 4; kc < std::min(kk, k0 + UNIT_KS * 8) / 4; ++kc)
             for (int row = 0; row < 2 * n_pad; ++row)
                 for (int j = 0; j < 4; ++j) {
                     float w = b[(size_t)(row % n_pad) * kk + kc * 4 + j];
@@ -531,6 +585,8 @@ struct sprl_evalnet {
     int sm_count = 0;
     uint64_t launches = 0;
     int64_t upload_bytes = 0;      // host -> device bytes of one weight load
+    float* head_act = nullptr;     // [head_cap][(policy_channels + 1) * 64]
+    int64_t head_cap = 0;
     // First call allocates; later calls (a new generation's weights) overwrite in place, so device
     // pointers captured in a CUDA graph stay valid.
     template <typename T> int upload(const std::vector<T>& h, const T** out) {
@@ -550,6 +606,8 @@ struct sprl_evalnet {
     void release() {
         for (void* p : allocations) cudaFree(p);
         allocations.clear();
+        if (head_act) cudaFree(head_act);
+        head_act = nullptr; head_cap = 0;
     }
 };
 
@@ -644,7 +702,7 @@ static int validate(const sprl_network_params* p) {
     if (p->policy_channels < 1 || p->policy_channels > 2 || p->value_channels != 1 || p->value_hidden != 64)
         return fail(SPRL_E_INVALID, "unsupported head shape (policy channels %d, value channels %d, value hidden %d)",
                     p->policy_channels, p->value_channels, p->value_hidden);
-    if (p->actions < 1 || p->actions > 256) return fail(SPRL_E_INVALID, "unsupported action count %d", p->actions);
+    if (p->actions < 1 || p->actions > HP_STRIDE) return fail(SPRL_E_INVALID, "unsupported action count %d", p->actions);
     int rc = check_conv(p->stem, "stem");
     if (rc) return rc;
     if (p->blocks > 0 && !p->tower) return fail(SPRL_E_INVALID, "null tower");
@@ -677,6 +735,8 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     e->sm_count = prop.multiProcessorCount;
     err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes(params->policy_channels));
+    if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     rc = pack_and_upload(e, params);
     if (rc) { e->release(); delete e; return rc; }
     *out = e;
@@ -702,6 +762,19 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     if (batch == 0) return SPRL_OK;
     cudaError_t err = cudaSetDevice(e->device);
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
+    if (batch > e->head_cap) {
+        // grows outside of stream capture only (a captured graph must have seen its batch size before)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing((cudaStream_t)cuda_stream, &cap);
+        if (cap != cudaStreamCaptureStatusNone) return fail(SPRL_E_STATE, "sprl_evalnet_forward: first call with batch %lld inside a stream capture; run one forward of this size before capturing", (long long)batch);
+        cudaDeviceSynchronize();
+        if (e->head_act) cudaFree(e->head_act);
+        e->head_act = nullptr; e->head_cap = 0;
+        err = cudaMalloc((void**)&e->head_act, (size_t)batch * (e->policy_channels + 1) * 64 * sizeof(float));
+        if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of the head activations failed: %s", cudaGetErrorString(err));
+        e->head_cap = batch;
+    }
+    e->dev.head_act = e->head_act;
     const long long tiles = (batch + 1) / 2;
     const int max_grid = e->sm_count / CLUSTER * CLUSTER;
     const int grid = (int)std::min<long long>((tiles + CLUSTER - 1) / CLUSTER * CLUSTER, max_grid);
@@ -718,6 +791,12 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     err = cudaLaunchKernelEx(&cfg, k_evalnet, e->dev, d_in, (long long)batch, d_logits, d_value);
     e->launches += 1;
     if (err == cudaSuccess) err = cudaGetLastError();
+    if (err == cudaSuccess) {
+        const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, 2LL * e->sm_count);
+        k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, d_logits, d_value);
+        e->launches += 1;
+        err = cudaGetLastError();
+    }
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "k_evalnet launch failed: %s", cudaGetErrorString(err));
     return SPRL_OK;
 }
@@ -734,8 +813,8 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
         std::vector<long long> t(12 * 4);
         cudaMemcpy(t.data(), e->dev.timing, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         for (int b = 0; b < 2; ++b)
-            fprintf(stderr, "[evalnet timing, CTA %d, last launch] mma: bar %lld full %lld total %lld | epi: bar %lld acc %lld heads %lld total %lld | producer: empty %lld total %lld\n",
-                    b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 2], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9]);
+            fprintf(stderr, "[evalnet timing, CTA %d, last launch] mma: bar %lld full %lld issue %lld commit %lld total %lld | epi: bar %lld acc %lld heads %lld total %lld | producer: empty %lld total %lld\n",
+                    b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 3], t[b * 12 + 10], t[b * 12 + 2], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9]);
     }
     if (launches) *launches = e->launches;
     return SPRL_OK;
