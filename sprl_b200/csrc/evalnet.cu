@@ -50,10 +50,10 @@ constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the i
 constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 40,960
 constexpr int RES_BYTES = NCG * TILE_M * 16; // 32,768
 #ifndef SPRL_EVALNET_UNIT_KSTEPS
-#define SPRL_EVALNET_UNIT_KSTEPS 8
+#define SPRL_EVALNET_UNIT_KSTEPS 2
 #endif
 constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (8 input channels each) per weight unit
-constexpr int UNIT_BYTES = UNIT_KS * 8 * 2 * CH * 4;   // [K/4][2*64][4] floats: 32 KB for a whole tap
+constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 4][3 dx x (hi, lo) x 64 rows][4 floats]: 24 KB
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
@@ -62,8 +62,7 @@ constexpr int THREADS = 192;
 #define SPRL_EVALNET_CLUSTER 2
 #endif
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
-constexpr int ACC_COLS = 128;                // one accumulator: [0,n) hi*hi + lo*hi, [n,2n) hi*lo
-constexpr int TMEM_COLS = 512;               // three accumulators (dx = -1, 0, +1)
+constexpr int TMEM_COLS = 512;               // accumulators: [0, 3n) = Z_dx main (hi*hi + lo*hi), [3n, 6n) = Z_dx hi*lo; n = 64
 constexpr int MAX_SMEM = 232448;             // 227 KB
 
 // shared memory map (bytes); the ring, the biases and the barriers follow at run-time offsets
@@ -207,22 +206,25 @@ __device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Layer geometry shared by the producer, the MMA issuer and the host packer.  A weight unit is
-// one tap's operand for up to 4 k-steps (32 input channels): [K chunk of 4][2n rows][4 floats],
-// rows 0..n-1 = W_hi, rows n..2n-1 = W_lo, so that ONE MMA with N = 2n computes A_hi*W_hi into
-// accumulator columns [0,n) and A_hi*W_lo into [n,2n) from a single read of A_hi; a second MMA
-// with N = n adds A_lo*W_hi into [0,n).  The epilogue sums the two column ranges.
-struct LayerGeom { int taps, ksteps, n, units_per_tap, lo_pass; };
+// Layer geometry shared by the producer, the MMA issuer and the host packer.
+// The three horizontal taps of a vertical offset dy read the SAME operand A (horizontal shifts are
+// applied to the outputs, see the header), so their weights are stacked along N: one weight unit
+// holds, for one dy and up to UNIT_KS k-steps, [K chunk of 4][rows][4 floats] with rows =
+// W_hi(dx=-1) | W_hi(0) | W_hi(+1) | W_lo(-1) | W_lo(0) | W_lo(+1), n rows each.  Per k-step three
+// MMAs with N = 3n: A_hi*[W_hi x3] and A_lo*[W_hi x3] into accumulator columns [0,3n), A_hi*[W_lo x3]
+// into [3n,6n) -- each 4 KB read of A feeds 192 output columns.  The 1x1 head convolution is the
+// same with one dx.
+struct LayerGeom { int ndy, ndx, ksteps, n, units_per_dy; };
 __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
     LayerGeom g;
-    if (layer == 0) { g.taps = 9; g.ksteps = in_ksteps; g.n = CH; g.lo_pass = 1; }
-    else if (layer == n_layers - 1) { g.taps = 1; g.ksteps = CH / 8; g.n = HEAD_N; g.lo_pass = 1; }
-    else { g.taps = 9; g.ksteps = CH / 8; g.n = CH; g.lo_pass = 1; }
-    g.units_per_tap = (g.ksteps + UNIT_KS - 1) / UNIT_KS;
+    if (layer == 0) { g.ndy = 3; g.ndx = 3; g.ksteps = in_ksteps; g.n = CH; }
+    else if (layer == n_layers - 1) { g.ndy = 1; g.ndx = 1; g.ksteps = CH / 8; g.n = HEAD_N; }
+    else { g.ndy = 3; g.ndx = 3; g.ksteps = CH / 8; g.n = CH; }
+    g.units_per_dy = (g.ksteps + UNIT_KS - 1) / UNIT_KS;
     return g;
 }
 __host__ __device__ inline int unit_ksteps(const LayerGeom& g, int u) { return g.ksteps - UNIT_KS * u < UNIT_KS ? g.ksteps - UNIT_KS * u : UNIT_KS; }
-__host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return unit_ksteps(g, u) * 8 * 2 * g.n * 4; }
+__host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return unit_ksteps(g, u) * 2 * (2 * g.ndx * g.n) * 16; }
 
 // slot of cell m (TMEM lane m) in the activation image: rows of the two boards interleaved,
 // two zero rows first
@@ -281,12 +283,12 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                                                  (size_t)(cluster_id % net.replicas) * net.wunits_bytes;
                 for (int layer = 0; layer < n_layers; ++layer) {
                     const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
-                    int tap_bytes = 0;
-                    for (int u = 0; u < g.units_per_tap; ++u) tap_bytes += unit_bytes(g, u);
-                    for (int t = 0; t < g.taps; ++t) {
-                        const int tap = (t + cluster_id) % g.taps;
-                        const unsigned char* src = layer_src + (size_t)tap * tap_bytes;
-                        for (int u = 0; u < g.units_per_tap; ++u) {
+                    int dy_bytes = 0;
+                    for (int u = 0; u < g.units_per_dy; ++u) dy_bytes += unit_bytes(g, u);
+                    for (int t = 0; t < g.ndy; ++t) {
+                        const int dyi = (t + cluster_id) % g.ndy;
+                        const unsigned char* src = layer_src + (size_t)dyi * dy_bytes;
+                        for (int u = 0; u < g.units_per_dy; ++u) {
                             const uint32_t bytes = (uint32_t)unit_bytes(g, u);
                             { long long a = clock64(); mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1); t_wait += clock64() - a; }
                             mbar_expect_tx(bar_full + 8 * s, bytes);       // the whole unit: one slice from every CTA of the cluster
@@ -297,7 +299,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                             if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                         }
                     }
-                    layer_src += (size_t)g.taps * tap_bytes;
+                    layer_src += (size_t)g.ndy * dy_bytes;
                 }
             }
             if (net.timing) { net.timing[blockIdx.x * 12 + 8] = t_wait; net.timing[blockIdx.x * 12 + 9] = clock64() - t0; }
@@ -312,45 +314,47 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
                 { long long a = clock64(); named_bar(1, 160); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
                 tc_fence_after();
-                const uint32_t idesc2 = instr_desc_tf32(TILE_M, 2 * g.n), idesc1 = instr_desc_tf32(TILE_M, g.n);
-                const bool lo_pass = g.lo_pass && net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
-                const uint32_t b_lbo = (uint32_t)(2 * g.n) * 16u, b_kstep = (2u * b_lbo) >> 4;
+                const int n1 = g.ndx * g.n;                                      // output columns of one MMA
+                const uint32_t idesc = instr_desc_tf32(TILE_M, n1);
+                const bool lo_pass = net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
+                const uint32_t b_lbo = (uint32_t)(2 * n1) * 16u, b_kstep = (2u * b_lbo) >> 4, b_lo_off = ((uint32_t)n1 * 16u) >> 4;
                 const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
                 const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
                 constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
-                uint32_t started = 0;                    // accumulators that already hold a partial sum
-                for (int t = 0; t < g.taps; ++t) {
-                    const int tap = (t + cluster_id) % g.taps;                   // same rotation as the producer
-                    const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dxi = g.taps == 9 ? tap % 3 : 1;
+                const uint32_t d_main = tmem, d_lo = tmem + (uint32_t)n1;
+                uint32_t acc = 0;                        // 0 until the layer's first k-step has initialised both accumulators
+                for (int t = 0; t < g.ndy; ++t) {
+                    const int dyi = (t + cluster_id) % g.ndy;                    // same rotation as the producer
+                    const int dy = g.ndy == 3 ? dyi - 1 : 0;
                     const uint32_t a_off = (uint32_t)(16 + 16 * dy);             // in 16-byte slots: two storage rows per board row
-                    const uint32_t d_tmem = tmem + (uint32_t)dxi * ACC_COLS;
-                    for (int u = 0; u < g.units_per_tap; ++u) {
+                    for (int u = 0; u < g.units_per_dy; ++u) {
                         const int nks = unit_ksteps(g, u);
                         { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
                         tc_fence_after();
                         const long long t_i0 = clock64();
                         const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
                         const uint64_t ah = a_hi0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP;
-                        uint32_t acc = (started >> dxi) & 1u;
-                        if (nks == UNIT_KS) {
-                            if (hi_pass) {
+                        if (hi_pass) {
+                            if (nks == UNIT_KS) {
 #pragma unroll
-                                for (int ks = 0; ks < UNIT_KS; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
+                                for (int ks = 0; ks < UNIT_KS; ++ks) {
+                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    umma_tf32(d_lo, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, acc);
+                                    if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    acc = 1;
+                                }
+                            } else {
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    umma_tf32(d_lo, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, acc);
+                                    if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    acc = 1;
+                                }
                             }
-                            if (lo_pass) {
-#pragma unroll
-                                for (int ks = 0; ks < UNIT_KS; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
-                            }
-                        } else {
-                            if (hi_pass)
-                                for (int ks = 0; ks < nks; ++ks) { umma_tf32(d_tmem, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc2, acc); acc = 1; }
-                            if (lo_pass)
-                                for (int ks = 0; ks < nks; ++ks) umma_tf32(d_tmem, al + ks * A_KSTEP, bd + ks * b_kstep, idesc1, 1u);
                         }
-                        started |= 1u << dxi;
                         const long long t_i1 = clock64();
-                        umma_commit_multicast(bar_empty + 8 * s, CMASK);
-                        t_issue += t_i1 - t_i0; t_commit += clock64() - t_i1;   // every CTA's producer learns that this CTA is done with the unit
+                        umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
+                        t_issue += t_i1 - t_i0; t_commit += clock64() - t_i1;
                         if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -407,16 +411,16 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     for (int q = 0; q < 4; ++q) {
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = hi half + lo half of accumulator dx
                         float o[16], v[16], w[16];
-                        tmem_ld16x2(t_lane + ACC_COLS + q * 16, t_lane + ACC_COLS + CH + q * 16, v, w);
+                        tmem_ld16x2(t_lane + CH + q * 16, t_lane + 4 * CH + q * 16, v, w);           // dx = 0: main, hi*lo
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = v[i] + w[i];
-                        tmem_ld16x2(t_lane + q * 16, t_lane + CH + q * 16, v, w);
+                        tmem_ld16x2(t_lane + q * 16, t_lane + 3 * CH + q * 16, v, w);                // dx = -1
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float z = __shfl_up_sync(0xffffffffu, v[i] + w[i], 1);
                             o[i] += has_left ? z : 0.0f;
                         }
-                        tmem_ld16x2(t_lane + 2 * ACC_COLS + q * 16, t_lane + 2 * ACC_COLS + CH + q * 16, v, w);
+                        tmem_ld16x2(t_lane + 2 * CH + q * 16, t_lane + 5 * CH + q * 16, v, w);       // dx = +1
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float z = __shfl_down_sync(0xffffffffu, v[i] + w[i], 1);
@@ -437,11 +441,11 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     }
                     proxy_fence();
                 } else {
-                    // ---- heads (1x1: centre accumulator): columns 0..pc-1 = policy conv channels, column pc = value conv.
+                    // ---- heads (1x1): columns 0..pc-1 = policy conv channels, column pc = value conv.
                     // The ReLU'd activations go to global memory; the fully connected layers run in k_heads
                     // (they need 49 KB of weights that this kernel's shared memory has no room for).
                     float v[16], w[16];
-                    tmem_ld16x2(t_lane + ACC_COLS, t_lane + ACC_COLS + HEAD_N, v, w);
+                    tmem_ld16x2(t_lane, t_lane + HEAD_N, v, w);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                     const int pc = net.policy_channels;
@@ -558,17 +562,20 @@ static inline float tf32_rna_host(float x) {
     return y;
 }
 
-// appends one tap's units for B[n][k] (n < n_pad rows, k < kk): per unit of <= UNIT_KS*8 input channels,
-// layout [K chunk of 4][2*n_pad rows][4], rows 0..n_pad-1 = tf32(w), rows n_pad.. = tf32(w - tf32(w))
-static void append_units(std::vector<float>& out, const std::vector<float>& b, int n_pad, int kk) {
+// appends the units of one vertical offset: b[dx][n][k] (n < n_pad rows, k < kk), per unit of <= UNIT_KS*8
+// input channels the layout [K chunk of 4][hi rows of every dx | lo rows of every dx][4]
+static void append_units(std::vector<float>& out, const std::vector<std::vector<float>>& b, int n_pad, int kk) {
+    const int ndx = (int)b.size();
     for (int k0 = 0; k0 < kk; k0 += UNIT_KS * 8)
         for (int kc = k0 / 4; kc < std::min(kk, k0 + UNIT_KS * 8) / 4; ++kc)
-            for (int row = 0; row < 2 * n_pad; ++row)
-                for (int j = 0; j < 4; ++j) {
-                    float w = b[(size_t)(row % n_pad) * kk + kc * 4 + j];
-                    float hi = tf32_rna_host(w);
-                    out.push_back(row < n_pad ? hi : tf32_rna_host(w - hi));
-                }
+            for (int part = 0; part < 2; ++part)
+                for (int dx = 0; dx < ndx; ++dx)
+                    for (int n = 0; n < n_pad; ++n)
+                        for (int j = 0; j < 4; ++j) {
+                            float w = b[dx][(size_t)n * kk + kc * 4 + j];
+                            float hi = tf32_rna_host(w);
+                            out.push_back(part == 0 ? hi : tf32_rna_host(w - hi));
+                        }
 }
 
 }  // namespace evalnet
@@ -628,11 +635,12 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
             scale[co] = (double)c.bn_weight[co] / std::sqrt((double)c.bn_var[co] + eps);
             bias[(size_t)layer * C + co] = (float)(((double)c.bias[co] - (double)c.bn_mean[co]) * scale[co] + (double)c.bn_bias[co]);
         }
-        for (int tap = 0; tap < 9; ++tap) {
-            std::vector<float> b((size_t)C * kk, 0.0f);
-            for (int co = 0; co < C; ++co)
-                for (int ci = 0; ci < cin; ++ci)
-                    b[(size_t)co * kk + ci] = (float)((double)c.weight[((size_t)co * cin + ci) * 9 + tap] * scale[co]);
+        for (int dy = 0; dy < 3; ++dy) {
+            std::vector<std::vector<float>> b(3, std::vector<float>((size_t)C * kk, 0.0f));
+            for (int dx = 0; dx < 3; ++dx)
+                for (int co = 0; co < C; ++co)
+                    for (int ci = 0; ci < cin; ++ci)
+                        b[dx][(size_t)co * kk + ci] = (float)((double)c.weight[((size_t)co * cin + ci) * 9 + dy * 3 + dx] * scale[co]);
             append_units(units, b, C, kk);
         }
     };
@@ -640,14 +648,15 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     for (int i = 0; i < 2 * p->blocks; ++i) conv_layer(p->tower[i], C, C, 1 + i);
     {   // heads: rows 0..pc-1 policy_conv, row pc value_conv
         const int pc = p->policy_channels;
-        std::vector<float> b((size_t)HEAD_N * C, 0.0f);
+        std::vector<std::vector<float>> bb(1, std::vector<float>((size_t)HEAD_N * C, 0.0f));
+        std::vector<float>& b = bb[0];
         for (int j = 0; j < pc; ++j) {
             for (int ci = 0; ci < C; ++ci) b[(size_t)j * C + ci] = p->policy_conv_w[(size_t)j * C + ci];
             bias[(size_t)(L - 1) * C + j] = p->policy_conv_b[j];
         }
         for (int ci = 0; ci < C; ++ci) b[(size_t)pc * C + ci] = p->value_conv_w[ci];
         bias[(size_t)(L - 1) * C + pc] = p->value_conv_b[0];
-        append_units(units, b, HEAD_N, C);
+        append_units(units, bb, HEAD_N, C);
     }
     const int A = p->actions, K = p->policy_channels * 64;
     std::vector<float> pfc_wt((size_t)K * A), pfc_b(p->policy_fc_b, p->policy_fc_b + A), vfc1_wt(64 * 64),
