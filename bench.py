@@ -296,7 +296,7 @@ def run_ours(args):
                    "evaluator_max_abs_logit_err_vs_fp64": eval_err},
         "moves_per_sec": round(moves / (ms / 1e3), 1), "evals_per_sec": round(evals / (ms / 1e3), 1),
         "samples_per_sec": round(8 * moves / (ms / 1e3), 1), "games_finished": int(games),
-        "gpu_launches": int(args.steps * args.rounds * world * (2 if evalnet is not None else 1)),
+        "gpu_launches": int(args.steps * args.rounds * world * (4 if evalnet is not None else 2)),
         "roofline": roofline, "roofline_search": roofline_search, "clocks": clocks,
     }
 

@@ -180,6 +180,11 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (!rc) rc = e->alloc(&p.rec_winner, MG, true);
     if (!rc) rc = e->alloc(&p.rec_draws, MG, true);
     if (!rc) rc = e->alloc(&p.counters, 4, true);
+    p.cq_cap = (u32)(p.cap_units / (unsigned long long)hdr + 1);
+    if (!rc) rc = e->alloc(&p.cq, S * p.cq_cap, false);
+    if (!rc) rc = e->alloc(&p.order, S * 2, true);
+    if (!rc) rc = e->alloc(&p.order_cnt, 4, true);
+    if (!rc) rc = e->alloc(&p.order_parity, 1, true);
     if (!rc && cfg->record_stats) {
         rc = e->alloc(&p.rec_N, MG * MM * A, false);
         if (!rc) rc = e->alloc(&p.rec_W, MG * MM * A, false);
@@ -254,7 +259,7 @@ int sprl_round(sprl_engine* e) {
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration in progress");
     if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
     search_launch_round(e->cfg.game, e->p, e->stream);
-    e->launches += 1;
+    e->launches += 2;               // the search kernel and the order flip
     ENGINE_CUDA(e, cudaGetLastError());
     return SPRL_OK;
 }

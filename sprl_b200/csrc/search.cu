@@ -72,6 +72,11 @@ template <> struct HL<1> {
     }
     __device__ static u32* meta_ptr(uint4* p) { return reinterpret_cast<u32*>(p + 2) + 1; }
     __device__ static float* value_ptr(uint4* p) { return reinterpret_cast<float*>(p + 2); }
+    // header unit `u` of a record moved by re-rooting: new links, expanded bit cleared
+    __device__ static void relink_unit(int u, uint4& x, u32 parent, u32 own_edge) {
+        if (u == 1) { x.z = parent; x.w = own_edge; }
+        else if (u == 2) x.y &= ~META_EXPANDED;
+    }
     __device__ static void load_links(const uint4* p, u32& parent, u32& own_edge) { uint4 b = p[1]; parent = b.z; own_edge = b.w; }
     __device__ static void load_boards(const uint4* p, Bits<1>& b0, Bits<1>& b1) {
         uint4 a = p[0];
@@ -97,6 +102,9 @@ template <> struct HL<2> {
     }
     __device__ static u32* meta_ptr(uint4* p) { return reinterpret_cast<u32*>(p + 3) + 3; }
     __device__ static float* value_ptr(uint4* p) { return reinterpret_cast<float*>(p + 3) + 2; }
+    __device__ static void relink_unit(int u, uint4& x, u32 parent, u32 own_edge) {
+        if (u == 3) { x.x = parent; x.y = own_edge; x.w &= ~META_EXPANDED; }
+    }
     __device__ static void load_links(const uint4* p, u32& parent, u32& own_edge) { uint4 d = p[3]; parent = d.x; own_edge = d.y; }
     __device__ static void load_boards(const uint4* p, Bits<2>& b0, Bits<2>& b1) { b0 = bits(p[0]); b1 = bits(p[1]); }
 };
@@ -586,57 +594,91 @@ struct TreeWarp {
 
     // ---- copies the subtree below src unit `c` into the other slab (UCTTree::advanceDecision,
     //      pruneChildrenExcept + clearSubtree, uct/UCTTree.hpp:197-210,283-298) ----
-    // Breadth-first, so parents precede children and siblings end up adjacent.  Every
-    // copied edge restarts with W = N = 0 and every node un-expanded; cached evaluations
-    // (netP, net_value, evaluated bit) are kept.
+    // Breadth-first, so parents precede children and siblings end up adjacent.  Every copied edge
+    // restarts with W = N = 0 and every node un-expanded; cached evaluations (netP, net_value,
+    // evaluated bit) are kept.  The frontier is a FIFO of child links (parent record << 8 | edge
+    // slot) in HBM; each step takes up to 32 links, sizes the 32 child records with one warp scan,
+    // copies all their units with the whole warp (flat unit index -> record by a shuffle binary
+    // search, so the loads of a step are independent) and appends the links found in them.
     __device__ bool compact_into(uint4* dst, u32 c, float own_w, float own_n, u32& out_units) {
         if (lane == 0) dst[0] = make_uint4(0u, __float_as_uint(own_w), __float_as_uint(own_n), 0u);
-        H h;
-        HL<W>::load(slab + c, h);
-        h.parent = 0; h.own_edge = 0; h.meta &= ~META_EXPANDED;
-        int n = META_NLEGAL(h.meta);
-        if (lane < HDR) HL<W>::store_unit(dst + ROOT_UNIT, lane, h);
-        for (int base = 0; base < n; base += 32) {
-            int k = base + lane;
-            if (k < n) { uint4 e = slab[c + HDR + k]; dst[ROOT_UNIT + HDR + k] = make_uint4(e.x, 0u, 0u, e.w); }
-        }
-        u32 alloc = ROOT_UNIT + HDR + n, scan = ROOT_UNIT;
-        __syncwarp();
-        while (scan < alloc) {
-            u32 meta = *HL<W>::meta_ptr(dst + scan);
-            int nn = META_NLEGAL(meta);
-            for (int base = 0; base < nn; base += 32) {
-                int k = base + lane;
-                u32 src_child = 0, ew = 0, size = 0;
-                H ch;
-                if (k < nn) {
-                    ew = dst[scan + HDR + k].w;
-                    src_child = EDGE_CHILD(ew);
-                    if (src_child) {
-                        HL<W>::load(slab + src_child, ch);
-                        size = HDR + META_NLEGAL(ch.meta);
-                    }
+        u32* q = p.cq + (size_t)tree * p.cq_cap;
+        u32 head = 0, tail = 0, alloc = ROOT_UNIT;
+        bool root_step = true;
+        for (;;) {
+            const int n = root_step ? 1 : (int)min(32u, tail - head);
+            // ---- one record per lane: where it comes from, how big it is
+            u32 src = 0, size = 0, parent = 0, own_edge = 0, ew = 0;
+            if (lane < n) {
+                if (root_step) src = c;
+                else {
+                    const u32 link = q[head + lane];
+                    parent = link >> 8;
+                    own_edge = parent + HDR + (link & 0xffu);
+                    ew = dst[own_edge].w;
+                    src = EDGE_CHILD(ew);
                 }
-                u32 incl = size;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    u32 v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                u32 total = __shfl_sync(FULL, incl, 31);
-                if (alloc + total + SLAB_SLACK > p.cap_units) return false;
-                if (src_child) {
-                    u32 nu = alloc + incl - size;
-                    ch.parent = scan; ch.own_edge = scan + HDR + k; ch.meta &= ~META_EXPANDED;
-                    for (int i = 0; i < HDR; ++i) HL<W>::store_unit(dst + nu, i, ch);
-                    int cn = META_NLEGAL(ch.meta);
-                    for (int j = 0; j < cn; ++j) { uint4 e = slab[src_child + HDR + j]; dst[nu + HDR + j] = make_uint4(e.x, 0u, 0u, e.w); }
-                    reinterpret_cast<u32*>(dst + scan + HDR + k)[3] = (ew & 0xff000000u) | nu;
-                }
-                alloc += total;
-                __syncwarp();
+                size = HDR + META_NLEGAL(*HL<W>::meta_ptr(slab + src));
             }
-            scan += HDR + nn;
+            u32 incl = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const u32 total = __shfl_sync(FULL, incl, 31);
+            if (alloc + total + SLAB_SLACK > p.cap_units) return false;
+            const u32 nu = alloc + incl - size;                          // new home of this lane's record
+            if (lane < n && !root_step) reinterpret_cast<u32*>(dst + own_edge)[3] = (ew & 0xff000000u) | nu;
+            // ---- copy: flat unit x of the step belongs to the first record r with incl[r] > x
+#pragma unroll 2
+            for (u32 x0 = 0; x0 < total; x0 += 32) {                     // every lane runs every trip (shuffles)
+                const u32 x = x0 + lane;
+                int lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const u32 v = __shfl_sync(FULL, incl, mid);
+                    if (v > x) hi = mid; else lo = mid + 1;
+                }
+                const u32 r_incl = __shfl_sync(FULL, incl, lo), r_size = __shfl_sync(FULL, size, lo);
+                const u32 r_src = __shfl_sync(FULL, src, lo), r_nu = __shfl_sync(FULL, nu, lo);
+                const u32 r_parent = __shfl_sync(FULL, parent, lo), r_edge = __shfl_sync(FULL, own_edge, lo);
+                if (x < total) {
+                    const u32 u = x - (r_incl - r_size);
+                    uint4 v = slab[r_src + u];
+                    if (u < (u32)HDR) HL<W>::relink_unit((int)u, v, r_parent, r_edge);
+                    else { v.y = 0u; v.z = 0u; }
+                    dst[r_nu + u] = v;
+                }
+            }
+            __syncwarp();
+            // ---- links of the copied records, in record order then edge order
+            u32 links = 0;
+            if (lane < n) {
+                const int cn = (int)size - HDR;
+                for (int j = 0; j < cn; ++j) links += EDGE_CHILD(slab[src + HDR + j].w) != 0u;
+            }
+            u32 lincl = links;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 v = __shfl_up_sync(FULL, lincl, o);
+                if (lane >= o) lincl += v;
+            }
+            const u32 ltotal = __shfl_sync(FULL, lincl, 31);
+            if (tail + ltotal > p.cq_cap) return false;
+            if (lane < n && links) {
+                u32 at = tail + lincl - links;
+                const int cn = (int)size - HDR;
+                for (int j = 0; j < cn; ++j)
+                    if (EDGE_CHILD(slab[src + HDR + j].w) != 0u) q[at++] = (nu << 8) | (u32)j;
+            }
+            tail += ltotal;
+            alloc += total;
+            if (!root_step) head += (u32)n;
+            root_step = false;
+            __syncwarp();
+            if (head >= tail) break;
         }
         out_units = alloc;
         return true;
@@ -767,8 +809,8 @@ struct TreeWarp {
 };
 
 // ---- kernels -------------------------------------------------------------------------------------
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int MIN_BLOCKS_PER_SM = 8;       // 64 registers per thread -> 32 resident warps per SM
+constexpr int WARPS_PER_BLOCK = 1;         // one tree per block: a finished tree frees its slot at once
+constexpr int MIN_BLOCKS_PER_SM = 32;      // 64 registers per thread -> 32 resident warps per SM
 
 template <class G>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) {
@@ -782,14 +824,39 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) 
     if (t.st.game_index < p.num_games) { t.st.status = ST_PLAYING; t.init_game(); }
     else { t.st.status = ST_DONE; }
     t.save();
+    if (lane == 0) {
+        p.order[warp] = (u32)warp;
+        if (warp == 0) { *p.order_parity = 0u; p.order_cnt[0] = p.order_cnt[1] = p.order_cnt[2] = p.order_cnt[3] = 0u; }
+    }
+}
+
+// Lists `tree` for the next launch: front when it will finish a move there, back otherwise.
+__device__ __forceinline__ void order_next(const EngineParams& p, u32 parity, int tree, bool heavy) {
+    u32* cnt = p.order_cnt + (parity ^ 1u) * 2u;
+    u32* dst = p.order + (size_t)(parity ^ 1u) * p.n_slots;
+    if (heavy) dst[atomicAdd(cnt, 1u)] = (u32)tree;
+    else dst[(u32)p.n_slots - 1u - atomicAdd(cnt + 1, 1u)] = (u32)tree;
+}
+
+// After every search launch: the list just written becomes current, the other one is emptied.
+__global__ void k_flip(EngineParams p) {
+    const u32 parity = *p.order_parity;
+    p.order_cnt[parity * 2u] = 0u;
+    p.order_cnt[parity * 2u + 1u] = 0u;
+    *p.order_parity = parity ^ 1u;
 }
 
 template <class G>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_round(EngineParams p) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= p.n_slots) return;
-    if (p.trees[warp].status != ST_PLAYING) return;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= p.n_slots) return;
+    const u32 parity = *p.order_parity;
+    const int warp = (int)p.order[(size_t)parity * p.n_slots + slot];        // the tree this warp serves
+    if (p.trees[warp].status != ST_PLAYING) {
+        if (lane == 0) order_next(p, parity, warp, false);
+        return;
+    }
     TreeWarp<G> t(p, warp, lane, scratch[threadIdx.x >> 5]);
     for (int iter = 0; iter < p.rounds_per_launch; ++iter) {
         if (t.st.n_queued > 0) t.apply_leaves();
@@ -801,6 +868,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_rou
     }
     if (t.st.status != ST_PLAYING && lane == 0) atomicAdd(&p.counters[t.st.status == ST_DONE ? 0 : 1], 1ULL);
     t.save();
+    if (lane == 0) order_next(p, parity, warp, t.st.status == ST_PLAYING && t.st.traversals >= p.sims);
 }
 
 // ---- sample writer: selfPlay's symmetrised samples (selfplay/SelfPlay.hpp:86-96,127-136,
@@ -848,6 +916,7 @@ template <class G> static void launch_begin(const EngineParams& p, cudaStream_t 
 }
 template <class G> static void launch_round(const EngineParams& p, cudaStream_t s) {
     k_round<G><<<ceil_div(p.n_slots, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(p);
+    k_flip<<<1, 1, 0, s>>>(p);
 }
 template <class G> static void launch_emit(const EngineParams& p, const long long* row0, int S, float* st, float* di,
                                            float* ou, cudaStream_t s) {

@@ -103,6 +103,15 @@ struct EngineParams {
     int add_noise, use_sym, init_q;
     int rounds_per_launch;
     unsigned long long* counters;   // [0] slots that finished all their games, [1] slots in error
+    // launch order of the trees (longest first): warp w of a launch serves tree order[parity][w].  Trees
+    // that will finish a move in the next launch (sample + re-root = several times the work of a plain
+    // search batch) are listed from the front, all others from the back, by the previous launch.
+    u32* order;                     // [2][n_slots]
+    u32* order_cnt;                 // [2][2] front / back fill counters of each list
+    u32* order_parity;              // which list the next launch reads
+    // re-rooting frontier (compact_into): per tree a FIFO of child links
+    u32* cq;                        // [n_slots][cq_cap]
+    u32 cq_cap;
 };
 
 }  // namespace sprl
