@@ -29,8 +29,9 @@
 //     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream
 //     from L2 through a ring of 16 KB units filled by cp.async.bulk (multicast to the CTAs of a
 //     cluster) + mbarrier complete_tx; tcgen05.commit frees a unit.
-//   * Warp roles: warps 0-3 = epilogue (TMEM -> registers -> shuffles/bias/residual/ReLU ->
-//     hi/lo -> activation image), warp 4 = MMA issuer, warp 5 = weight producer.
+//   * Warp roles: warps 0-7 = epilogue (TMEM -> registers -> shuffles/bias/residual/ReLU ->
+//     hi/lo -> activation image; two warps per TMEM lane quarter, half of the channels each),
+//     warp 8 = MMA issuer, warp 9 = weight producer.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -57,7 +58,10 @@ constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 4][3 dx x
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the channels
+constexpr int MMA_WARP = EPI_WARPS, PRODUCER_WARP = EPI_WARPS + 1;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA warp
 #ifndef SPRL_EVALNET_CLUSTER
 #define SPRL_EVALNET_CLUSTER 2
 #endif
@@ -257,7 +261,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + off_tmem), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -268,7 +272,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + off_tmem), 0);
 
-    if (warp == 5) {
+    if (warp == PRODUCER_WARP) {
         // ===== weight producer =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
@@ -305,14 +309,14 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
             if (net.timing) { net.timing[blockIdx.x * 12 + 8] = t_wait; net.timing[blockIdx.x * 12 + 9] = clock64() - t0; }
         }
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) =====
         uint32_t s = 0, ph = 0;
         long long t_bar = 0, t_full = 0, t_issue = 0, t_commit = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer) {
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
-                { long long a = clock64(); named_bar(1, 160); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
+                { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
                 tc_fence_after();
                 const int n1 = g.ndx * g.n;                                      // output columns of one MMA
                 const uint32_t idesc = instr_desc_tf32(TILE_M, n1);
@@ -367,12 +371,13 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         }
     } else {
         // ===== epilogue warps: cell m = TMEM lane m =====
-        const int m = threadIdx.x;                                   // 0..127
+        const int m = (warp & 3) * 32 + lane;                        // cell 0..127 = TMEM lane
+        const int half = warp >> 2;                                  // which half of the channels this warp finishes
         const int slot = cell_slot(m);
         const int g8 = m >> 3, c = m & 7, r = g8 >> 1, b = g8 & 1;
         const int cell = r * 8 + c;
         const bool has_left = c > 0, has_right = c < 7;
-        const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
         float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
         float4* res = reinterpret_cast<float4*>(smem + OFF_RES);
@@ -382,7 +387,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = tile * 2 + b;
             // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split) ----
-            for (int cg = 0; cg < 2 * net.in_ksteps; ++cg) {
+            for (int cg = half; cg < 2 * net.in_ksteps; cg += EPI_WARPS / 4) {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -396,7 +401,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
             proxy_fence();
             for (int layer = 0; layer < n_layers; ++layer) {
                 tc_fence_before();
-                { long long a = clock64(); named_bar(1, 160); t_bar += clock64() - a; }
+                { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }
                 { long long a = clock64(); mbar_wait(bar_acc, acc_phase, net.error_flag, 3); t_acc += clock64() - a; }
                 const long long t_layer = clock64();
                 acc_phase ^= 1u;
@@ -408,7 +413,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     const bool add_res = layer > 0 && (layer & 1) == 0;      // second conv of a block
                     const bool save_res = (layer & 1) == 0;                  // block input of the next block
 #pragma unroll 1
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 2 * half; q < 2 * half + 2; ++q) {
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = hi half + lo half of accumulator dx
                         float o[16], v[16], w[16];
                         tmem_ld16x2(t_lane + CH + q * 16, t_lane + 4 * CH + q * 16, v, w);           // dx = 0: main, hi*lo
@@ -449,7 +454,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                     const int pc = net.policy_channels;
-                    if (board < batch) {
+                    if (board < batch && half == 0) {
                         float* dst = net.head_act + board * (long long)((pc + 1) * 64);
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
@@ -459,7 +464,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                 }
             }
         }
-        if (m == 0 && net.timing) {
+        if (threadIdx.x == 0 && net.timing) {
             net.timing[blockIdx.x * 12 + 4] = t_bar; net.timing[blockIdx.x * 12 + 5] = t_acc; net.timing[blockIdx.x * 12 + 6] = t_head;
             net.timing[blockIdx.x * 12 + 7] = clock64() - t0;
         }
@@ -470,7 +475,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                               // no CTA leaves while peers may still signal its barriers
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }

@@ -1,0 +1,64 @@
+"""Throughput of the other BASELINE.json configurations on one B200 (bench.py measures config 3/4):
+  config 2: Othello environment only -- perft(1..11) and random-rollout sweep (steps/s);
+  config 1/5 shapes: Connect Four, Go 7x7 and Go 9x9 self-play with the reference's network shapes
+  (traced module through LibTorch; the tcgen05 evaluator covers 8x8 boards).
+Prints one JSON object per line."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sprl_b200 import capi, selfplay as SP
+from sprl_b200.network import make_network, trace_network
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+dev = torch.device("cuda", 0)
+
+# ---- config 2: perft
+for d in (8, 9, 10, 11):
+    count, ms = SP.env_perft(capi.GAME_OTHELLO, d)
+    print(json.dumps({"config": "othello_perft", "depth": d, "leaves": count, "device_ms": round(ms, 3),
+                      "leaves_per_sec": round(count / (ms / 1e3), 1)}), flush=True)
+# ---- config 2: random rollouts, one thread per game
+for lg in (10, 14, 18, 20, 22, 24):
+    n = 1 << lg
+    SP.env_rollout(capi.GAME_OTHELLO, 0, 0, min(n, 1 << 14))
+    r = SP.env_rollout(capi.GAME_OTHELLO, 0, 0, n)
+    steps = r["total_positions"] - n
+    print(json.dumps({"config": "othello_rollout", "games": n, "steps": int(steps), "kernel_ms": round(r["elapsed_ms"], 3),
+                      "steps_per_sec": round(steps / (r["elapsed_ms"] / 1e3), 1)}), flush=True)
+for game, name in ((capi.GAME_C4, "c4"), (capi.GAME_GO7, "go7"), (capi.GAME_GO9, "go9")):
+    r = SP.env_rollout(game, 0, 0, 1 << 18)
+    steps = r["total_positions"] - (1 << 18)
+    print(json.dumps({"config": name + "_rollout", "games": 1 << 18, "steps": int(steps), "kernel_ms": round(r["elapsed_ms"], 3),
+                      "steps_per_sec": round(steps / (r["elapsed_ms"] / 1e3), 1)}), flush=True)
+
+# ---- self-play of the other games (network through LibTorch on device buffers)
+for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5, 4096), (capi.GAME_GO7, "go7", 400, 16, 8, 0.2, 2048),
+                                              (capi.GAME_GO9, "go9", 400, 16, 8, 0.2, 1024)):
+    module = trace_network(make_network(kind, 0), dev)
+    with SP.Engine(game, capi.EVAL_EXTERNAL, seed=0, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=alpha,
+                   num_slots=slots, max_games=slots * 8) as eng:
+        eng.attach_network(module, use_cuda_graph=True)
+        eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        eng.begin_iteration(0, slots * 8)
+        eng._capture()
+        g = eng._nn["graph"]
+        for _ in range(100):
+            g.replay()
+        torch.cuda.synchronize()
+        eng.reset_stats()
+        t0 = time.time()
+        for _ in range(300):
+            g.replay()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        st = eng.stats()
+        playing, failed = eng.poll()
+    print(json.dumps({"config": kind + "_selfplay", "sims_per_move": sims, "batch_queue": [b, q], "slots": slots,
+                      "sims_per_sec": round(st["sims"] / dt, 1), "moves_per_sec": round(st["moves"] / dt, 1),
+                      "evals_per_sec": round(st["evals"] / dt, 1), "failed_slots": failed,
+                      "evaluator": "traced module, LibTorch/cuDNN fp32"}), flush=True)
