@@ -66,7 +66,7 @@ constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA war
 #define SPRL_EVALNET_CLUSTER 2
 #endif
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
-constexpr int TMEM_COLS = 512;               // accumulators: [0, 3n) = Z_dx main (hi*hi + lo*hi), [3n, 6n) = Z_dx hi*lo; n = 64
+constexpr int TMEM_COLS = 256;               // accumulator columns [dx * 64 + channel] = Z_dx (all three split products)
 constexpr int MAX_SMEM = 232448;             // 227 KB
 
 // shared memory map (bytes); the ring, the biases and the barriers follow at run-time offsets
@@ -215,9 +215,9 @@ __device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
 // applied to the outputs, see the header), so their weights are stacked along N: one weight unit
 // holds, for one dy and up to UNIT_KS k-steps, [K chunk of 4][rows][4 floats] with rows =
 // W_hi(dx=-1) | W_hi(0) | W_hi(+1) | W_lo(-1) | W_lo(0) | W_lo(+1), n rows each.  Per k-step three
-// MMAs with N = 3n: A_hi*[W_hi x3] and A_lo*[W_hi x3] into accumulator columns [0,3n), A_hi*[W_lo x3]
-// into [3n,6n) -- each 4 KB read of A feeds 192 output columns.  The 1x1 head convolution is the
-// same with one dx.
+// MMAs with N = 3n accumulate into the same columns [dx*n + channel]: A_hi*[W_hi x3], A_hi*[W_lo x3]
+// and A_lo*[W_hi x3] -- each 4 KB read of A feeds 192 output columns.  The 1x1 head convolution is
+// the same with one dx.
 struct LayerGeom { int ndy, ndx, ksteps, n, units_per_dy; };
 __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
     LayerGeom g;
@@ -325,8 +325,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                 const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
                 const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
                 constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
-                const uint32_t d_main = tmem, d_lo = tmem + (uint32_t)n1;
-                uint32_t acc = 0;                        // 0 until the layer's first k-step has initialised both accumulators
+                const uint32_t d_main = tmem;
+                uint32_t acc = 0;                        // 0 for the layer's very first MMA only
                 for (int t = 0; t < g.ndy; ++t) {
                     const int dyi = (t + cluster_id) % g.ndy;                    // same rotation as the producer
                     const int dy = g.ndy == 3 ? dyi - 1 : 0;
@@ -343,14 +343,14 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
 #pragma unroll
                                 for (int ks = 0; ks < UNIT_KS; ++ks) {
                                     umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_tf32(d_lo, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, acc);
+                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
                                     if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
                             } else {
                                 for (int ks = 0; ks < nks; ++ks) {
                                     umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_tf32(d_lo, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, acc);
+                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
                                     if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
@@ -416,20 +416,12 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     for (int q = 2 * half; q < 2 * half + 2; ++q) {
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = hi half + lo half of accumulator dx
                         float o[16], v[16], w[16];
-                        tmem_ld16x2(t_lane + CH + q * 16, t_lane + 4 * CH + q * 16, v, w);           // dx = 0: main, hi*lo
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = v[i] + w[i];
-                        tmem_ld16x2(t_lane + q * 16, t_lane + 3 * CH + q * 16, v, w);                // dx = -1
+                        tmem_ld16(t_lane + CH + q * 16, o);                                          // dx = 0
+                        tmem_ld16x2(t_lane + q * 16, t_lane + 2 * CH + q * 16, v, w);                // dx = -1, dx = +1
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float z = __shfl_up_sync(0xffffffffu, v[i] + w[i], 1);
-                            o[i] += has_left ? z : 0.0f;
-                        }
-                        tmem_ld16x2(t_lane + 2 * CH + q * 16, t_lane + 5 * CH + q * 16, v, w);       // dx = +1
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float z = __shfl_down_sync(0xffffffffu, v[i] + w[i], 1);
-                            o[i] += has_right ? z : 0.0f;
+                            const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                            o[i] += (has_left ? zl : 0.0f) + (has_right ? zr : 0.0f);
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -449,10 +441,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     // ---- heads (1x1): columns 0..pc-1 = policy conv channels, column pc = value conv.
                     // The ReLU'd activations go to global memory; the fully connected layers run in k_heads
                     // (they need 49 KB of weights that this kernel's shared memory has no room for).
-                    float v[16], w[16];
-                    tmem_ld16x2(t_lane, t_lane + HEAD_N, v, w);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                    float v[16];
+                    tmem_ld16(t_lane, v);
                     const int pc = net.policy_channels;
                     if (board < batch && half == 0) {
                         float* dst = net.head_act + board * (long long)((pc + 1) * 64);
