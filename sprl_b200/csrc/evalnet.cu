@@ -49,12 +49,11 @@ constexpr int NCG = CH / 4;                  // channel groups of 4 floats (16 B
 constexpr int SLOTS = 160;                   // 20 storage rows x 8 cells
 constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the image
 constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 40,960
-constexpr int RES_BYTES = NCG * TILE_M * 16; // 32,768
 #ifndef SPRL_EVALNET_UNIT_KSTEPS
-#define SPRL_EVALNET_UNIT_KSTEPS 2
+#define SPRL_EVALNET_UNIT_KSTEPS 4
 #endif
 constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (8 input channels each) per weight unit
-constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 4][3 dx x (hi, lo) x 64 rows][4 floats]: 24 KB
+constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 4][3 dx x (hi, lo) x 64 rows][4 floats]: 48 KB
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
@@ -66,14 +65,14 @@ constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA war
 #define SPRL_EVALNET_CLUSTER 2
 #endif
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
-constexpr int TMEM_COLS = 256;               // accumulator columns [dx * 64 + channel] = Z_dx (all three split products)
+constexpr int TMEM_COLS = 256;               // [dx * 64 + channel] = Z_dx (all three split products); [192, 256) = residual
+constexpr int RES_COL = 3 * CH;              // the block input of the current residual block, fp32, one cell per lane
 constexpr int MAX_SMEM = 232448;             // 227 KB
 
 // shared memory map (bytes); the ring, the biases and the barriers follow at run-time offsets
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + IMG_BYTES;
-constexpr int OFF_RES = OFF_ALO + IMG_BYTES;
-constexpr int OFF_RING = OFF_RES + RES_BYTES;                    // 114,688
+constexpr int OFF_RING = OFF_ALO + IMG_BYTES;                    // 81,920
 
 struct NetDev {
     const float* wunits;     // packed weight units in consumption order, `replicas` copies back to back
@@ -182,6 +181,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* v, float* w) {
     uint32_t r[16], q[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -253,7 +261,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
     constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1u);
 
     // ---- one-time setup ----
-    for (int i = threadIdx.x; i < (2 * IMG_BYTES + RES_BYTES) / 16; i += THREADS)
+    for (int i = threadIdx.x; i < (2 * IMG_BYTES) / 16; i += THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < n_layers * CH; i += THREADS) s_bias[i] = net.bias[i];
     if (threadIdx.x == 0) {
@@ -380,7 +388,6 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
         float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
-        float4* res = reinterpret_cast<float4*>(smem + OFF_RES);
         const int cells = 64, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
@@ -423,17 +430,20 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                             const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
                             o[i] += (has_left ? zl : 0.0f) + (has_right ? zr : 0.0f);
                         }
+                        if (add_res) {                                                               // block input, kept in TMEM
+                            tmem_ld16(t_lane + RES_COL + q * 16, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] += v[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + bias[q * 16 + i], 0.0f);
+                        if (save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int cg = q * 4 + j;
-                            float4 x = make_float4(o[4 * j] + bias[4 * cg], o[4 * j + 1] + bias[4 * cg + 1],
-                                                   o[4 * j + 2] + bias[4 * cg + 2], o[4 * j + 3] + bias[4 * cg + 3]);
-                            if (add_res) { float4 rr = res[cg * TILE_M + m]; x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
-                            x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
-                            if (save_res) res[cg * TILE_M + m] = x;
-                            float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+                            const float4 h = make_float4(tf32_round(o[4 * j]), tf32_round(o[4 * j + 1]), tf32_round(o[4 * j + 2]), tf32_round(o[4 * j + 3]));
                             a_hi[cg * SLOTS + slot] = h;
-                            a_lo[cg * SLOTS + slot] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                            a_lo[cg * SLOTS + slot] = make_float4(o[4 * j] - h.x, o[4 * j + 1] - h.y, o[4 * j + 2] - h.z, o[4 * j + 3] - h.w);
                         }
                     }
                     proxy_fence();
