@@ -192,9 +192,9 @@ int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* sh
 /* ------------------------------------------------------------------ evaluator network
  * The forward pass of the controller's network (src/networks/grid_networks.py:30-80
  * BasicGridNetwork, loaded by networks/GridNetwork.hpp:37-51 and run at :99) as one persistent
- * tcgen05 kernel for 8x8 boards: conv tower on the tensor cores with the 3xTF32 split
- * (fp32-level accuracy, fp32 accumulate), BatchNorm folded, heads fused.  Other board sizes
- * keep using the traced module through sprl_forward_fn. */
+ * tcgen05 kernel for boards up to 8x8 (Othello, Go 7x7, Connect Four): conv tower on the tensor
+ * cores with the 3xTF32 split (fp32-level accuracy, fp32 accumulate), BatchNorm folded, head FCs in
+ * a second kernel.  Larger boards (Go 9x9) keep using the traced module through sprl_forward_fn. */
 typedef struct {
     const float *weight, *bias;                             /* conv: [out, in, 3, 3], [out] */
     const float *bn_weight, *bn_bias, *bn_mean, *bn_var;    /* BatchNorm2d affine + running stats, [out] */
@@ -220,7 +220,7 @@ int sprl_evalnet_create(int device, const sprl_network_params* h_params, sprl_ev
  * for captured CUDA graphs). */
 int sprl_evalnet_update(sprl_evalnet* net, const sprl_network_params* h_params);
 /* INetwork::evaluate's forward (networks/GridNetwork.hpp:99-102) on device buffers:
- * d_in [batch, in_planes, 8, 8] -> d_logits [batch, actions], d_value [batch].  Asynchronous on
+ * d_in [batch, in_planes, rows, cols] -> d_logits [batch, actions], d_value [batch].  Asynchronous on
  * `cuda_stream`; matches sprl_forward_fn so that it can serve as the engine's evaluator. */
 int sprl_evalnet_forward(sprl_evalnet* net, const float* d_in, int64_t batch, float* d_logits, float* d_value,
                          void* cuda_stream);

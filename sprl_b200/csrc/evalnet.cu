@@ -1,6 +1,6 @@
 // evalnet.cu -- the evaluator network's forward pass as one persistent tcgen05 kernel.
 //
-// Replaces, for 8x8 boards, the LibTorch forward of the reference's traced
+// Replaces, for boards up to 8x8 (Othello 8x8, Go 7x7, Connect Four 6x7), the LibTorch forward of the reference's traced
 // `BasicGridNetwork` (/root/reference/cpp/src/networks/GridNetwork.hpp:99 calling the module
 // of /root/reference/src/networks/grid_networks.py:30-80): conv3x3+BN+ReLU stem, `blocks`
 // residual blocks of two conv3x3+BN, policy head (conv1x1 -> ReLU -> FC) and value head
@@ -9,8 +9,8 @@
 // reads them.
 //
 // Design (B200, sm_100a):
-//   * One CTA per SM, persistent over tiles of TWO boards = 128 cells = the M of one
-//     tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole tower on chip:
+//   * One CTA per SM, persistent over tiles of TWO boards, each on an 8x8 lattice (smaller boards
+//     leave lattice positions zero) = 128 cells = the M of one tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole tower on chip:
 //     activations never leave shared memory, fp32 accumulators live in TMEM.
 //   * Every 3x3 convolution is an implicit GEMM with NO im2col copy.  The activation image is
 //     kept in shared memory as [channel group of 4][storage row][8 cells][4 floats], the rows of
@@ -85,6 +85,7 @@ struct NetDev {
     const float* vfc1_b;     // [64]
     const float* vfc2_w;     // [64] weights, then the bias
     int n_layers;            // 1 stem + 2*blocks + 1 heads
+    int rows, cols;          // board (<= 8 x 8): cell (r, c) lives at lattice position (r, c) of an 8 x 8 tile half
     int in_planes;
     int in_ksteps;           // ceil(in_planes / 8)
     int actions;
@@ -383,12 +384,13 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         const int half = warp >> 2;                                  // which half of the channels this warp finishes
         const int slot = cell_slot(m);
         const int g8 = m >> 3, c = m & 7, r = g8 >> 1, b = g8 & 1;
-        const int cell = r * 8 + c;
-        const bool has_left = c > 0, has_right = c < 7;
+        const bool valid = r < net.rows && c < net.cols;             // lattice positions outside the board stay zero
+        const int cell = r * net.cols + c;
+        const bool has_left = c > 0, has_right = c + 1 < net.cols;
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
         float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
-        const int cells = 64, planes = net.in_planes;
+        const int cells = net.rows * net.cols, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
@@ -399,7 +401,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int p = cg * 4 + j;
-                    v[j] = (p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
+                    v[j] = (valid && p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
                 }
                 const float4 h = make_float4(tf32_round(v[0]), tf32_round(v[1]), tf32_round(v[2]), tf32_round(v[3]));
                 a_hi[cg * SLOTS + slot] = h;
@@ -436,7 +438,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                             for (int i = 0; i < 16; ++i) o[i] += v[i];
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i] + bias[q * 16 + i], 0.0f);
+                        for (int i = 0; i < 16; ++i) o[i] = valid ? fmaxf(o[i] + bias[q * 16 + i], 0.0f) : 0.0f;
                         if (save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -454,11 +456,11 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                     float v[16];
                     tmem_ld16(t_lane, v);
                     const int pc = net.policy_channels;
-                    if (board < batch && half == 0) {
-                        float* dst = net.head_act + board * (long long)((pc + 1) * 64);
+                    if (board < batch && half == 0 && valid) {
+                        float* dst = net.head_act + board * (long long)((pc + 1) * cells);
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
-                            if (j <= pc) dst[j * 64 + cell] = fmaxf(v[j] + bias[j], 0.0f);
+                            if (j <= pc) dst[j * cells + cell] = fmaxf(v[j] + bias[j], 0.0f);
                     }
                     t_head += clock64() - t_layer;
                 }
@@ -489,14 +491,14 @@ constexpr int HP_STRIDE = 68;                 // policy weight row stride in flo
 __global__ void __launch_bounds__(256)
 k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restrict__ value) {
     extern __shared__ __align__(16) float hs[];
-    const int pc = net.policy_channels, K = pc * 64, A = net.actions, IN = (pc + 1) * 64;
+    const int pc = net.policy_channels, cells = net.rows * net.cols, K = pc * cells, A = net.actions, IN = (pc + 1) * cells;
     float* wp = hs;                           // [K][HP_STRIDE]
-    float* wv = wp + K * HP_STRIDE;           // [64][64]
-    float* x = wv + 64 * 64;                  // [HB][IN]
+    float* wv = wp + K * HP_STRIDE;           // [cells][64]
+    float* x = wv + cells * 64;               // [HB][IN]
     float* hid = x + HB * IN;                 // [HB][64]
     const int t = threadIdx.x;
     for (int i = t; i < K * HP_STRIDE; i += 256) { const int k = i / HP_STRIDE, a = i - k * HP_STRIDE; wp[i] = a < A ? net.pfc_wt[k * A + a] : 0.0f; }
-    for (int i = t; i < 64 * 64; i += 256) wv[i] = net.vfc1_wt[i];
+    for (int i = t; i < cells * 64; i += 256) wv[i] = net.vfc1_wt[i];
     const int ag = t & 15, bg = t >> 4;       // 16 output groups x 16 board groups
     for (long long b0 = (long long)blockIdx.x * HB; b0 < batch; b0 += (long long)gridDim.x * HB) {
         __syncthreads();
@@ -531,7 +533,7 @@ k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restri
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-            for (int k = 0; k < 64; ++k) {
+            for (int k = 0; k < cells; ++k) {
                 const float4 w = *reinterpret_cast<const float4*>(wv + k * 64 + 4 * ag);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -554,7 +556,7 @@ k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restri
     }
 }
 
-static inline size_t heads_smem_bytes(int pc) { return (size_t)(pc * 64 * HP_STRIDE + 64 * 64 + HB * (pc + 1) * 64 + HB * 64) * sizeof(float); }
+static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + HB * (pc + 1) * cells + HB * 64) * sizeof(float); }
 
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
 static inline float tf32_rna_host(float x) {
@@ -663,13 +665,14 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         bias[(size_t)(L - 1) * C + pc] = p->value_conv_b[0];
         append_units(units, bb, HEAD_N, C);
     }
-    const int A = p->actions, K = p->policy_channels * 64;
-    std::vector<float> pfc_wt((size_t)K * A), pfc_b(p->policy_fc_b, p->policy_fc_b + A), vfc1_wt(64 * 64),
+    const int cells = p->rows * p->cols;
+    const int A = p->actions, K = p->policy_channels * cells;
+    std::vector<float> pfc_wt((size_t)K * A), pfc_b(p->policy_fc_b, p->policy_fc_b + A), vfc1_wt((size_t)cells * 64),
         vfc1_b(p->value_fc1_b, p->value_fc1_b + 64), vfc2_w(p->value_fc2_w, p->value_fc2_w + 64);
     for (int a = 0; a < A; ++a)
         for (int k = 0; k < K; ++k) pfc_wt[(size_t)k * A + a] = p->policy_fc_w[(size_t)a * K + k];
     for (int j = 0; j < 64; ++j)
-        for (int k = 0; k < 64; ++k) vfc1_wt[(size_t)k * 64 + j] = p->value_fc1_w[(size_t)j * 64 + k];
+        for (int k = 0; k < cells; ++k) vfc1_wt[(size_t)k * 64 + j] = p->value_fc1_w[(size_t)j * cells + k];
     vfc2_w.push_back(p->value_fc2_b[0]);
     e->upload_bytes = 0;
     constexpr int REPLICAS = 2;
@@ -699,6 +702,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     if (rc) return rc;
     e->dev.error_flag = const_cast<unsigned long long*>(fp);
     e->dev.n_layers = L;
+    e->dev.rows = p->rows;
+    e->dev.cols = p->cols;
     e->dev.in_planes = P;
     e->dev.in_ksteps = in_k / 8;
     e->dev.actions = A;
@@ -708,8 +713,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
 
 static int validate(const sprl_network_params* p) {
     if (!p) return fail(SPRL_E_INVALID, "null network parameters");
-    if (p->rows != 8 || p->cols != 8)
-        return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles 8x8 boards (two per MMA); %dx%d boards run through the LibTorch module", p->rows, p->cols);
+    if (p->rows < 1 || p->cols < 1 || p->rows > 8 || p->cols > 8)
+        return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles boards up to 8x8 (two per MMA); %dx%d boards run through the LibTorch module", p->rows, p->cols);
     if (p->channels != CH) return fail(SPRL_E_INVALID, "tower width must be %d channels, got %d", CH, p->channels);
     if (p->blocks < 0 || 2 + 2 * p->blocks > MAX_LAYERS) return fail(SPRL_E_INVALID, "unsupported number of residual blocks %d", p->blocks);
     if (p->in_planes < 1 || p->in_planes > CH) return fail(SPRL_E_INVALID, "unsupported number of input planes %d", p->in_planes);
@@ -749,7 +754,7 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     e->sm_count = prop.multiProcessorCount;
     err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
-    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes(params->policy_channels));
+    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes(params->policy_channels, 64));
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     rc = pack_and_upload(e, params);
     if (rc) { e->release(); delete e; return rc; }
@@ -761,7 +766,7 @@ int sprl_evalnet_update(sprl_evalnet* e, const sprl_network_params* params) {
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     int rc = validate(params);
     if (rc) return rc;
-    if (params->in_planes != e->in_planes || params->blocks != e->blocks || params->actions != e->actions ||
+    if (params->rows != e->rows || params->cols != e->cols || params->in_planes != e->in_planes || params->blocks != e->blocks || params->actions != e->actions ||
         params->policy_channels != e->policy_channels)
         return fail(SPRL_E_INVALID, "sprl_evalnet_update: the network shape changed");
     rc = use_device(e->device);
@@ -784,7 +789,7 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
         cudaDeviceSynchronize();
         if (e->head_act) cudaFree(e->head_act);
         e->head_act = nullptr; e->head_cap = 0;
-        err = cudaMalloc((void**)&e->head_act, (size_t)batch * (e->policy_channels + 1) * 64 * sizeof(float));
+        err = cudaMalloc((void**)&e->head_act, (size_t)batch * (e->policy_channels + 1) * e->rows * e->cols * sizeof(float));
         if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of the head activations failed: %s", cudaGetErrorString(err));
         e->head_cap = batch;
     }
@@ -807,7 +812,7 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {
         const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, 2LL * e->sm_count);
-        k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, d_logits, d_value);
+        k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels, e->rows * e->cols), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, d_logits, d_value);
         e->launches += 1;
         err = cudaGetLastError();
     }

@@ -245,6 +245,30 @@ class Engine:
         assert got.value == n
         return states, dists, outcomes
 
+    def collect_samples_device(self):
+        """The iteration's samples left on the GPU (hand-off to an in-process trainer
+        without the filesystem): torch tensors that alias engine-owned device memory, valid until the
+        next begin_iteration / collect call.  Same order and layout as collect_samples()."""
+        import torch
+        gi = self.gi
+        ds, dd, do, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        capi.check(self.lib.sprl_collect_samples_device(self.handle, C.byref(ds), C.byref(dd), C.byref(do), C.byref(n)))
+        dev = torch.device("cuda", self.cfg.device)
+
+        class _View:            # __cuda_array_interface__ v3 over a raw device pointer
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = dict(shape=shape, typestr="<f4", data=(ptr, False), version=3, strides=None,
+                                                     stream=None)
+
+        def view(ptr, shape):
+            if n.value == 0:
+                return torch.empty(shape, dtype=torch.float32, device=dev)
+            return torch.as_tensor(_View(ptr.value, shape), device=dev)
+
+        torch.cuda.synchronize(dev)
+        return (view(ds, (n.value, 2 * gi.history + 1, gi.rows, gi.cols)), view(dd, (n.value, gi.actions)),
+                view(do, (n.value,)))
+
     def move_stats(self, num_games):
         """Per-move root statistics of the last iteration (engine created with record_stats=1)."""
         gi = self.gi

@@ -29,8 +29,8 @@ def randomized(net, seed):
 def test_evalnet_rejects_unsupported_shapes():
     lib = capi.load()
     h = C.c_void_p()
-    # Connect Four board (6x7): stays on the TorchScript path
-    p, keep = network_params(make_network("c4", 0).state_dict(), rows=6, cols=7)
+    # Go 9x9 does not fit the 8x8 lattice: stays on the TorchScript path
+    p, keep = network_params(make_network("go9", 0).state_dict(), rows=9, cols=9)
     assert lib.sprl_evalnet_create(0, C.byref(p), C.byref(h)) == capi.SPRL_E_INVALID and not h
     assert b"8x8" in lib.sprl_last_error()
     # wrong tower width
@@ -75,6 +75,23 @@ def test_evalnet_matches_fp64_forward(batch, blocks, planes):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,rows,cols,batch", [("c4", 6, 7, 131), ("go7", 7, 7, 77)])
+def test_evalnet_smaller_boards(kind, rows, cols, batch):
+    """Connect Four (6x7, 7 actions) and Go 7x7 (17 planes, 6 blocks, 50 actions) on the 8x8 lattice."""
+    net = randomized(make_network(kind, 3), 9)
+    planes = net.conv.in_channels
+    x = (torch.rand(batch, planes, rows, cols) > 0.5).float()
+    with torch.no_grad():
+        want_l, want_v = net.double()(x.double())
+        net.float()
+    ev = EvalNet(net, device=0, rows=rows, cols=cols)
+    got_l, got_v = ev(x.cuda())
+    ev.status()
+    assert (got_l.cpu().double() - want_l).abs().max().item() <= 2e-6
+    assert (got_v.cpu().double() - want_v).abs().max().item() <= 2e-6
+
+
+@pytest.mark.gpu
 def test_evalnet_real_valued_inputs():
     """The reference's planes are 0/1, but the kernel splits any fp32 input into hi + lo."""
     net = randomized(make_network("othello", 1), 2)
@@ -101,7 +118,7 @@ def test_evalnet_update_in_place_and_batches_in_a_row():
         assert torch.equal(ev(xg[:n])[0].cpu(), lb[:n])
     assert ev.status() >= 6
     with pytest.raises(capi.SprlError):
-        ev.update(make_network("c4", 0))           # shape change is refused
+        ev.update(make_network("go7", 0))          # shape change is refused
 
 
 @pytest.mark.gpu

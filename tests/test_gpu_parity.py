@@ -272,3 +272,16 @@ def test_sharded_generation_equals_unsharded():
     for g in range(n):
         assert np.array_equal(merged[g][0], whole["move_N"][bounds[g]:bounds[g + 1]]), g
         assert np.array_equal(merged[g][1], whole["move_action"][bounds[g]:bounds[g + 1]]), g
+
+
+def test_device_resident_samples_alias_the_host_copy():
+    """N1: samples handed over on the device are the arrays collect_samples() copies to the host."""
+    import torch
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, seed=2, sims=40, max_batch=8, max_queue=4, num_slots=6, max_games=6) as eng:
+        states, dists, outcomes = eng.run_iteration(6)
+        ds, dd, do = eng.collect_samples_device()
+        assert ds.is_cuda and ds.shape == states.shape and dd.shape == dists.shape and do.shape == outcomes.shape
+        assert np.array_equal(ds.cpu().numpy(), states) and np.array_equal(dd.cpu().numpy(), dists)
+        assert np.array_equal(do.cpu().numpy(), outcomes)
+        loss = (dd * torch.log(dd.clamp_min(1e-9))).sum()          # usable by torch without a copy
+        assert torch.isfinite(loss)

@@ -1,7 +1,7 @@
 """Throughput of the other BASELINE.json configurations on one B200 (bench.py measures config 3/4):
   config 2: Othello environment only -- perft(1..11) and random-rollout sweep (steps/s);
   config 1/5 shapes: Connect Four, Go 7x7 and Go 9x9 self-play with the reference's network shapes
-  (traced module through LibTorch; the tcgen05 evaluator covers 8x8 boards).
+  (tcgen05 evaluator for boards up to 8x8; Go 9x9 runs the traced module through LibTorch).
 Prints one JSON object per line."""
 import json
 import os
@@ -11,6 +11,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sprl_b200 import capi, selfplay as SP
+from sprl_b200.evalnet import EvalNet
 from sprl_b200.network import make_network, trace_network
 
 torch.backends.cudnn.allow_tf32 = False
@@ -39,10 +40,15 @@ for game, name in ((capi.GAME_C4, "c4"), (capi.GAME_GO7, "go7"), (capi.GAME_GO9,
 # ---- self-play of the other games (network through LibTorch on device buffers)
 for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5, 4096), (capi.GAME_GO7, "go7", 400, 16, 8, 0.2, 2048),
                                               (capi.GAME_GO9, "go9", 400, 16, 8, 0.2, 1024)):
-    module = trace_network(make_network(kind, 0), dev)
+    net = make_network(kind, 0)
+    gi = capi.game_info(game)
+    library = gi.rows <= 8 and gi.cols <= 8
     with SP.Engine(game, capi.EVAL_EXTERNAL, seed=0, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=alpha,
                    num_slots=slots, max_games=slots * 8) as eng:
-        eng.attach_network(module, use_cuda_graph=True)
+        if library:
+            eng.attach_evalnet(EvalNet(net, device=0, rows=gi.rows, cols=gi.cols), use_cuda_graph=True)
+        else:
+            eng.attach_network(trace_network(net, dev), use_cuda_graph=True)
         eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         eng.begin_iteration(0, slots * 8)
         eng._capture()
@@ -61,4 +67,4 @@ for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5
     print(json.dumps({"config": kind + "_selfplay", "sims_per_move": sims, "batch_queue": [b, q], "slots": slots,
                       "sims_per_sec": round(st["sims"] / dt, 1), "moves_per_sec": round(st["moves"] / dt, 1),
                       "evals_per_sec": round(st["evals"] / dt, 1), "failed_slots": failed,
-                      "evaluator": "traced module, LibTorch/cuDNN fp32"}), flush=True)
+                      "evaluator": "library (tcgen05, 3xTF32)" if library else "traced module, LibTorch/cuDNN fp32"}), flush=True)
