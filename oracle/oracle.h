@@ -23,8 +23,8 @@ extern "C" {
 #endif
 
 enum { OG_OTHELLO = 0, OG_C4 = 1, OG_GO7 = 2, OG_GO9 = 3 };
-enum { OE_UNIFORM = 0, OE_HASHNET = 1, OE_CALLBACK = 2 };
-enum { OQ_ZERO = 0, OQ_PARENT = 1 };
+enum { OE_UNIFORM = 0, OE_HASHNET = 1, OE_CALLBACK = 2, OE_HEURISTIC = 3 /* networks/OthelloHeuristic.cpp, Othello only */ };
+enum { OQ_ZERO = 0, OQ_PARENT = 1, OQ_DROP_PARENT = 2 };
 
 #define OG_MAXB 81
 #define OG_MAXA 82
@@ -71,6 +71,7 @@ typedef struct {
     float u_weight;     /* constants.hpp:6 U_WEIGHT = 1.1f */
     oracle_eval_cb eval_cb;
     void* eval_user;
+    uint64_t hash_salt; /* OE_HASHNET: 0 = the plain net, other values = independent nets (matches) */
 } oracle_selfplay_cfg;
 
 typedef struct {
@@ -109,6 +110,28 @@ typedef struct {
  * Any output pointer may be NULL.  Returns 0, or -1 on capacity overflow. */
 int oracle_selfplay(const oracle_selfplay_cfg* cfg, uint64_t first_game, int ngames,
                     oracle_selfplay_out* out);
+
+/* Match play between two evaluators (Evaluate.cpp:93-157: UCTNetworkAgent::act, agents/UCTNetworkAgent.hpp:42-108,
+ * inside playGame, evaluate/play.hpp:24-69).  Each side owns a tree (Dirichlet noise on, eps 0.25, alpha 0.1, default
+ * uWeight 1.0) and its own evaluator / symmetrizer / init-Q (`agents[k]`: evaluator, hash_salt, use_sym, init_q, eval_cb
+ * are read from it; game, seed, sims, max_batch, max_queue from agents[0]).  Game t = first_game + g: agents[t % 2]
+ * plays Player ZERO.  The mover searches `sims` descents, plays the FIRST action with the most visits, and both trees
+ * advance.  Per-move arrays describe the mover's root. */
+typedef struct {
+    int64_t cap_moves;
+    int32_t* game_moves;      /* [ngames] */
+    int32_t* game_winner;     /* [ngames] -1 none / 0 / 1 (Player) */
+    uint64_t* game_rng_draws; /* [ngames] */
+    float* move_N; float* move_W; float* move_P;   /* [cap_moves, A] */
+    float* move_root_N; float* move_root_W;        /* [cap_moves] */
+    int32_t* move_action; int32_t* move_traversals; int32_t* move_agent;
+    int8_t* move_player;
+    int64_t n_moves;
+    int64_t wins[2];          /* games won by agents[0] / agents[1] */
+    int64_t draws;
+} oracle_match_out;
+
+int oracle_match(const oracle_selfplay_cfg agents[2], uint64_t first_game, int ngames, oracle_match_out* out);
 
 /* .npy v1.0 writer restated from utils/npy.hpp:430-476,616-639 (float32, C order). */
 int oracle_write_npy_f32(const char* path, const float* data, const uint64_t* shape, int ndim);

@@ -57,6 +57,8 @@ static void oth_mask(const int8_t* b, int player, float* mask) {
     mask[64] = any ? 0.0f : 1.0f;
 }
 
+void og_othello_mask(const int8_t* b, int player, float* mask) { oth_mask(b, player, mask); }
+
 /* games/OthelloNode.cpp:179-191 */
 static int oth_terminal(const int8_t* b) {
     float m[65];

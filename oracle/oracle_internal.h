@@ -42,6 +42,9 @@ void og_rewards(const onode* n, float out[2]);
 /* GameNode::getGameState: hist[t][cell], returns valid length */
 int og_game_state(int game, const onode* n, int8_t hist[OG_MAXH][OG_MAXB]);
 
+/* OthelloNode::actionMask(board, player), games/OthelloNode.cpp:156-177 (65 entries) */
+void og_othello_mask(const int8_t* b, int player, float* mask);
+
 void osym_cells(int game, int sym, const int8_t* in, int8_t* out);
 void osym_dist(int game, int sym, const float* in, float* out);
 int osym_inverse(int game, int sym);

@@ -257,6 +257,10 @@ static inline uint64_t ohashnet_state_hash(const uint64_t* words, int size, int 
     for (int i = 0; i < 4 * size; ++i) h = ohash_mix(h ^ words[i]);
     return h;
 }
+/* A second, independent HashNet for two-network matches (Evaluate.cpp): salt 0 is the plain net. */
+static inline uint64_t ohashnet_salt(uint64_t h, uint64_t salt) {
+    return salt ? ohash_mix(h ^ (salt * 0xD6E8FEB86659FD93ULL)) : h;
+}
 /* Un-normalised prior of action index i: an integer in [1, 2^24], exact in fp32.
  * The caller then applies the reference's own mask -> sequential sum ->
  * x * (1/sum) pipeline (networks/GridNetwork.hpp:117-139). */

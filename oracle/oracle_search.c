@@ -105,7 +105,7 @@ static void mask_normalise(float* policy, const float* mask, int A) {
     }
 }
 
-static void hashnet_eval(const ogame_info* gi, const ostate* s, const float* mask, float* policy, float* value) {
+static void hashnet_eval(const ogame_info* gi, const ostate* s, const float* mask, uint64_t salt, float* policy, float* value) {
     uint64_t words[4 * OG_MAXH];
     memset(words, 0, sizeof(words));
     int own = s->player, opp = 1 - own;
@@ -114,7 +114,7 @@ static void hashnet_eval(const ogame_info* gi, const ostate* s, const float* mas
             if (s->hist[t][i] == own) words[4 * t + (i >> 6)] |= 1ULL << (i & 63);
             if (s->hist[t][i] == opp) words[4 * t + 2 + (i >> 6)] |= 1ULL << (i & 63);
         }
-    uint64_t h = ohashnet_state_hash(words, s->size, s->player);
+    uint64_t h = ohashnet_salt(ohashnet_state_hash(words, s->size, s->player), salt);
     for (int i = 0; i < gi->actions; ++i) policy[i] = ohashnet_prior_raw(h, i);
     mask_normalise(policy, mask, gi->actions);
     *value = ohashnet_value(h);
@@ -128,7 +128,7 @@ void oracle_hashnet(int game, const int8_t* hist_cells, int hist_size, int playe
     for (int t = 0; t < hist_size; ++t) memcpy(s.hist[t], hist_cells + t * gi->cells, (size_t)gi->cells);
     s.size = hist_size;
     s.player = player;
-    hashnet_eval(gi, &s, mask, policy, value);
+    hashnet_eval(gi, &s, mask, 0, policy, value);
 }
 
 /* INetwork::evaluate for a batch (networks/INetwork.hpp:25-27) */
@@ -144,7 +144,19 @@ static void evaluate_batch(const oracle_selfplay_cfg* cfg, const ogame_info* gi,
             value[b] = 0.0f;
         }
     } else if (cfg->evaluator == OE_HASHNET) {
-        for (int b = 0; b < n; ++b) hashnet_eval(gi, &states[b], masks[b], policy[b], &value[b]);
+        for (int b = 0; b < n; ++b) hashnet_eval(gi, &states[b], masks[b], cfg->hash_salt, policy[b], &value[b]);
+    } else if (cfg->evaluator == OE_HEURISTIC) { /* networks/OthelloHeuristic.cpp:5-53 */
+        for (int b = 0; b < n; ++b) {
+            int numLegal = 0, numEmpty = 0, numOppLegal = 0;
+            for (int i = 0; i < A; ++i) if (masks[b][i] > 0.0f) ++numLegal;      /* counts the pass slot too */
+            float uniform = 1.0f / numLegal;
+            for (int i = 0; i < A; ++i) policy[b][i] = (masks[b][i] > 0.0f) ? uniform : 0.0f;
+            for (int i = 0; i < gi->cells; ++i) if (states[b].hist[0][i] == O_NONE) ++numEmpty;
+            float oppMask[OG_MAXA];
+            og_othello_mask(states[b].hist[0], 1 - states[b].player, oppMask);
+            for (int i = 0; i < gi->cells; ++i) if (oppMask[i] > 0.0f) ++numOppLegal;   /* placements only */
+            value[b] = (float)(numLegal - numOppLegal) / numEmpty;
+        }
     } else {                                     /* networks/GridNetwork.hpp:62-145 */
         int plane = (2 * gi->history + 1) * gi->cells;
         float* planes = (float*)malloc(sizeof(float) * (size_t)plane * (size_t)n);
@@ -184,9 +196,19 @@ static onode* uct_get_add_child(otree* t, onode* n, int action) {
         onode* c = og_get_add_child(t->game, n, action);
         node_attach_stats(c);
         if (t->cfg->init_q == OQ_PARENT) n->W[action] = n->evaluated ? n->net_value : 0.0f;
-        else n->W[action] = 0.0f;
+        else n->W[action] = 0.0f;           /* ZERO, and DROP_PARENT ("never used", :273-278) */
     }
     return n->child[action];
+}
+
+/* UCTNode::Q, uct/UCTNode.hpp:152-163.  With DROP_PARENT an unvisited node answers with its parent's Q; the
+ * decision node keeps its predecessor as m_parent, so the walk never leaves the tree. */
+static float uct_node_q(otree* t, onode* n) {
+    if (t->cfg->init_q == OQ_DROP_PARENT) {
+        if (*n->own_N == 0) return n->parent ? uct_node_q(t, n->parent) : 0.0f;   /* root of a fresh tree: null deref in the reference */
+        return *n->own_W / *n->own_N;
+    }
+    return *n->own_W / (1 + *n->own_N);
 }
 
 /* uct/UCTNode.hpp:221-251 with child_Q / child_U of :191-211 */
@@ -197,7 +219,9 @@ static int uct_best_action(otree* t, onode* n) {
     float uWeight = t->cfg->u_weight;
     for (int a = 0; a < A; ++a) {
         if (n->mask[a] == 0.0f) continue;
-        float q = n->W[a] / (1 + n->N[a]);
+        float q;
+        if (t->cfg->init_q == OQ_DROP_PARENT) q = (n->N[a] == 0) ? uct_node_q(t, n) : n->W[a] / n->N[a];
+        else q = n->W[a] / (1 + n->N[a]);
         float u = n->P[a] * __builtin_sqrtf(*n->own_N) / (1 + n->N[a]);
         float value = q + uWeight * u;
         if (value > bestValue) { bestValue = value; nbest = 0; best[nbest++] = a; }
@@ -457,6 +481,84 @@ int oracle_selfplay(const oracle_selfplay_cfg* cfg, uint64_t first_game, int nga
         if (rc) return rc;
     }
     return 0;
+}
+
+/* ------------------------------------------------------------------ match play */
+static void match_tree_init(otree* t, const oracle_selfplay_cfg* cfg, orng_t* rng) {
+    memset(t, 0, sizeof(*t));
+    t->cfg = cfg; t->gi = og_info(cfg->game); t->game = cfg->game; t->rng = rng; t->stats = NULL;
+    t->game_root = og_new_root(cfg->game);
+    t->game_root->own_N = &t->root_N[0];
+    t->game_root->own_W = &t->root_W[0];
+    t->decision = t->game_root;
+}
+
+int oracle_match(const oracle_selfplay_cfg agents[2], uint64_t first_game, int ngames, oracle_match_out* out) {
+    const ogame_info* gi = og_info(agents[0].game);
+    if (!gi) return -2;
+    int A = gi->actions;
+    oracle_selfplay_cfg cfg[2] = { agents[0], agents[1] };
+    for (int k = 0; k < 2; ++k) {               /* Evaluate.cpp:95-111; agents search with the default uWeight */
+        if (cfg[k].evaluator == OE_CALLBACK && !cfg[k].eval_cb) return -2;
+        cfg[k].game = agents[0].game; cfg[k].seed = agents[0].seed; cfg[k].sims = agents[0].sims;
+        cfg[k].max_batch = agents[0].max_batch; cfg[k].max_queue = agents[0].max_queue;
+        cfg[k].dir_eps = 0.25f; cfg[k].dir_alpha = 0.1f; cfg[k].add_noise = 1; cfg[k].u_weight = 1.0f;
+    }
+    out->n_moves = 0; out->wins[0] = out->wins[1] = 0; out->draws = 0;
+    onode** leaves = (onode**)malloc(sizeof(onode*) * (size_t)(cfg[0].max_batch > 0 ? cfg[0].max_batch : 1));
+    int rc = 0;
+    for (int g = 0; g < ngames && rc == 0; ++g) {
+        uint64_t tg = first_game + (uint64_t)g;
+        orng_t rng = { cfg[0].seed, tg, 0 };
+        otree tree[2];
+        match_tree_init(&tree[0], &cfg[0], &rng);
+        match_tree_init(&tree[1], &cfg[1], &rng);
+        int moves = 0;
+        while (!tree[0].decision->terminal) {   /* evaluate/play.hpp:38-57 */
+            if (out->n_moves >= out->cap_moves) { rc = -1; break; }
+            int player = tree[0].decision->player;
+            int agent = (tg % 2 == 0) ? player : 1 - player;
+            otree* t = &tree[agent];
+            onode* root = t->decision;
+            int traversals = 0;
+            while (traversals < cfg[agent].sims) {      /* agents/UCTNetworkAgent.hpp:45-57 */
+                int nleaves = 0;
+                int trav = tree_search(t, leaves, &nleaves);
+                if (nleaves > 0) tree_evaluate_and_backprop(t, leaves, nleaves);
+                traversals += trav;
+            }
+            int64_t m = out->n_moves;
+            int action = 0;                     /* std::max_element: first of the largest, :92-93 */
+            for (int a = 0; a < A; ++a) {
+                PUT(out->move_N, m * A + a, root->N[a]);
+                PUT(out->move_W, m * A + a, root->W[a]);
+                PUT(out->move_P, m * A + a, root->P[a]);
+                if (root->N[a] > root->N[action]) action = a;
+            }
+            PUT(out->move_root_N, m, *root->own_N);
+            PUT(out->move_root_W, m, *root->own_W);
+            PUT(out->move_traversals, m, traversals);
+            PUT(out->move_agent, m, agent);
+            PUT(out->move_player, m, (int8_t)player);
+            PUT(out->move_action, m, action);
+            tree_advance(&tree[agent], action);         /* act(): own tree */
+            tree_advance(&tree[1 - agent], action);     /* opponentAct() */
+            out->n_moves += 1;
+            ++moves;
+        }
+        if (rc == 0) {
+            int winner = tree[0].decision->winner;      /* Player: -1 none */
+            PUT(out->game_moves, g, moves);
+            PUT(out->game_winner, g, winner);
+            PUT(out->game_rng_draws, g, rng.ctr);
+            if (winner == O_NONE) out->draws += 1;      /* Evaluate.cpp:141-153 */
+            else out->wins[(tg % 2 == 0) ? winner : 1 - winner] += 1;
+        }
+        og_free_subtree(tree[0].game_root);
+        og_free_subtree(tree[1].game_root);
+    }
+    free(leaves);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ npy I/O */

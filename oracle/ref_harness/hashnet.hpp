@@ -20,6 +20,8 @@ public:
     using State = SPRL::GridState<BOARD_SIZE, HISTORY_SIZE>;
     using ActionDist = SPRL::GameActionDist<ACTION_SIZE>;
 
+    explicit HashNet(uint64_t salt = 0) : m_salt(salt) {}
+
     std::vector<std::pair<ActionDist, SPRL::Value>> evaluate(
         const std::vector<State>& states, const std::vector<ActionDist>& masks) override {
         int n = (int)states.size();
@@ -38,7 +40,7 @@ public:
                     if (p == opp) words[4 * t + 2 + (i >> 6)] |= 1ULL << (i & 63);
                 }
             }
-            uint64_t h = ohashnet_state_hash(words, s.size(), (int)s.getPlayer());
+            uint64_t h = ohashnet_salt(ohashnet_state_hash(words, s.size(), (int)s.getPlayer()), m_salt);
             ActionDist policy;
             for (int i = 0; i < ACTION_SIZE; ++i) policy[i] = ohashnet_prior_raw(h, i);
             int numLegal = 0;
@@ -60,6 +62,7 @@ public:
 
 private:
     int m_numEvals { 0 };
+    uint64_t m_salt;
 };
 
 }  // namespace SPRLREF

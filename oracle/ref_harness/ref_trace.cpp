@@ -4,8 +4,13 @@
 //
 //   perft    <game> <maxdepth>
 //   rollout  <game> <seed> <first_game> <ngames> <out.trace>
-//   selfplay <game> <hash|uniform> <seed> <first_game> <ngames> <sims> <batch>
-//            <queue> <eps> <alpha> <noise 0|1> <sym 0|1> <parent|zero> <out.trace>
+//   selfplay <game> <evaluator> <seed> <first_game> <ngames> <sims> <batch>
+//            <queue> <eps> <alpha> <noise 0|1> <sym 0|1> <parent|zero|drop> <out.trace>
+//   match    <game> <evaluator0> <evaluator1> <seed> <first_game> <ngames> <sims> <batch> <queue>
+//            <sym0 0|1> <initq0> <sym1 0|1> <initq1> <out.trace>
+//
+// evaluator = hash | hash1 (a second, independent HashNet) | uniform (networks/RandomNetwork.hpp)
+//           | heuristic (networks/OthelloHeuristic.cpp, Othello only).
 //
 // game = othello | c4 | go.  Randomness comes from random_shim.cpp (the
 // contract stream of oracle/oracle_rng.h).  `selfplay` runs every game twice:
@@ -14,9 +19,16 @@
 // (uct/UCTTree.hpp:38-210) that records the root statistics after every search;
 // it aborts unless both produce identical samples and consume the same number
 // of draws, so the recorded statistics are those of the reference's selfPlay.
+// `match` does the same for the match-play path of Evaluate.cpp:93-157: the
+// reference's own UCTNetworkAgent (agents/UCTNetworkAgent.hpp:42-108) + playGame
+// (evaluate/play.hpp:24-69), then an instrumented loop that must reproduce its
+// actions, winner and draw count.
 #include "games/ConnectFourNode.hpp"
 #include "games/GoNode.hpp"
 #include "games/OthelloNode.hpp"
+#include "agents/UCTNetworkAgent.hpp"
+#include "evaluate/play.hpp"
+#include "networks/OthelloHeuristic.hpp"
 #include "networks/RandomNetwork.hpp"
 #include "selfplay/SelfPlay.hpp"
 #include "symmetry/ConnectFourSymmetrizer.hpp"
@@ -30,7 +42,9 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <string>
+#include <type_traits>
 
 extern "C" void sprl_shim_set_stream(uint64_t seed, uint64_t game);
 extern "C" uint64_t sprl_shim_get_counter();
@@ -169,6 +183,28 @@ void embedStates(const std::vector<StateOf<D>>& states, std::vector<float>& out)
     }
 }
 
+// ---- evaluators and options by name -----------------------------------------
+template <class D>
+std::unique_ptr<INetwork<StateOf<D>, D::A>> makeEvaluator(const std::string& kind) {
+    using State = StateOf<D>;
+    if (kind == "hash") return std::make_unique<SPRLREF::HashNet<D::R * D::C, D::H, D::A>>(0);
+    if (kind == "hash1") return std::make_unique<SPRLREF::HashNet<D::R * D::C, D::H, D::A>>(1);
+    if (kind == "uniform") return std::make_unique<RandomNetwork<State, D::A>>();
+    if constexpr (std::is_same_v<typename D::Node, OthelloNode>) {
+        if (kind == "heuristic") return std::make_unique<OthelloHeuristic>();
+    }
+    std::cerr << "unknown evaluator " << kind << "\n";
+    std::exit(2);
+}
+
+static InitQ parseInitQ(const std::string& s) {
+    if (s == "zero") return InitQ::ZERO;
+    if (s == "parent") return InitQ::PARENT;
+    if (s == "drop") return InitQ::DROP_PARENT;
+    std::cerr << "unknown init-Q " << s << "\n";
+    std::exit(2);
+}
+
 template <class D>
 int cmdSelfplay(const std::string& evalKind, uint64_t seed, uint64_t firstGame, int nGames,
                 int sims, int maxBatch, int maxQueue, float eps, float alpha,
@@ -178,12 +214,8 @@ int cmdSelfplay(const std::string& evalKind, uint64_t seed, uint64_t firstGame, 
     using State = StateOf<D>;
     using Dist = GameActionDist<A>;
 
-    SPRLREF::HashNet<B, D::H, A> hashNet;
-    RandomNetwork<State, A> uniformNet;
-    INetwork<State, A>* net = nullptr;
-    if (evalKind == "hash") net = &hashNet;
-    else if (evalKind == "uniform") net = &uniformNet;
-    else { std::cerr << "unknown evaluator " << evalKind << "\n"; return 2; }
+    auto netOwner = makeEvaluator<D>(evalKind);
+    INetwork<State, A>* net = netOwner.get();
 
     typename D::Sym symObj;
     ISymmetrizer<State, A>* sym = useSym ? &symObj : nullptr;
@@ -315,6 +347,132 @@ int cmdSelfplay(const std::string& evalKind, uint64_t seed, uint64_t firstGame, 
     return 0;
 }
 
+// ---- match play (Evaluate.cpp:93-157) ----------------------------------------
+template <class D>
+int cmdMatch(const std::string& evalKind0, const std::string& evalKind1, uint64_t seed, uint64_t firstGame, int nGames,
+             int sims, int maxBatch, int maxQueue, bool sym0, InitQ initQ0, bool sym1, InitQ initQ1,
+             const std::string& outPath) {
+    constexpr int B = D::R * D::C;
+    constexpr int A = D::A;
+    using State = StateOf<D>;
+    using Tree = UCTTree<typename D::Node, State, A>;
+    using Agent = UCTNetworkAgent<typename D::Node, State, A>;
+
+    auto net0 = makeEvaluator<D>(evalKind0);
+    auto net1 = makeEvaluator<D>(evalKind1);
+    typename D::Sym symObj;
+    const float eps = 0.25f, alpha = 0.1f;                 // Evaluate.cpp:97-98,106-107
+
+    std::vector<int32_t> gameMoves, gameWinner, gameFirst;
+    std::vector<uint64_t> gameCtr;
+    std::vector<float> mvN, mvW, mvP, mvRootN, mvRootW;
+    std::vector<int32_t> mvAction, mvTrav, mvAgent;
+    std::vector<int8_t> mvPlayer, mvBoard;
+
+    for (int g = 0; g < nGames; ++g) {
+        const uint64_t t = firstGame + g;                  // the loop index of Evaluate.cpp:93
+        // Pass 1: the reference's agents and playGame.
+        sprl_shim_set_stream(seed, t);
+        std::vector<int> refActions;
+        Player refWinner;
+        {
+            Tree tree0 { std::make_unique<typename D::Node>(), eps, alpha, initQ0, sym0 ? &symObj : nullptr, true };
+            Tree tree1 { std::make_unique<typename D::Node>(), eps, alpha, initQ1, sym1 ? &symObj : nullptr, true };
+            Agent agent0 { net0.get(), &tree0, sims, maxBatch, maxQueue };
+            Agent agent1 { net1.get(), &tree1, sims, maxBatch, maxQueue };
+            // forwards to the reference's agent and notes what it played
+            struct Recorder : IAgent<typename D::Node, State, A> {
+                const IAgent<typename D::Node, State, A>* inner;
+                std::vector<int>* log;
+                ActionIdx act(const GameNode<typename D::Node, State, A>* node, bool verbose = false) const override {
+                    ActionIdx a = inner->act(node, verbose);
+                    log->push_back((int)a);
+                    return a;
+                }
+                void opponentAct(const ActionIdx action) const override { inner->opponentAct(action); }
+            };
+            Recorder rec0, rec1;
+            rec0.inner = &agent0; rec0.log = &refActions;
+            rec1.inner = &agent1; rec1.log = &refActions;
+            std::array<IAgent<typename D::Node, State, A>*, 2> agents;
+            if (t % 2 == 0) agents = { &rec0, &rec1 }; else agents = { &rec1, &rec0 };
+            typename D::Node rootNode {};
+            refWinner = playGame<typename D::Node, State, A>(&rootNode, agents, false);
+        }
+        uint64_t refCtr = sprl_shim_get_counter();
+
+        // Pass 2: instrumented loop over the public UCTTree API.
+        sprl_shim_set_stream(seed, t);
+        Tree tree0 { std::make_unique<typename D::Node>(), eps, alpha, initQ0, sym0 ? &symObj : nullptr, true };
+        Tree tree1 { std::make_unique<typename D::Node>(), eps, alpha, initQ1, sym1 ? &symObj : nullptr, true };
+        Tree* trees[2] = { &tree0, &tree1 };
+        INetwork<State, A>* nets[2] = { net0.get(), net1.get() };
+        std::vector<int> actions;
+        typename D::Node gameRoot {};
+        GNode<D>* cur = &gameRoot;
+        while (!tree0.getDecisionNode()->isTerminal()) {
+            int player = (int)tree0.getDecisionNode()->getPlayer();
+            int agent = (t % 2 == 0) ? player : 1 - player;        // which network moves
+            Tree& tree = *trees[agent];
+            auto* root = const_cast<UCTNode<typename D::Node, State, A>*>(tree.getDecisionNode());
+            State rootState = root->getGameState();
+            int trav = 0;
+            while (trav < sims) {
+                auto [leaves, n] = tree.searchAndGetLeaves(maxBatch, maxQueue, nets[agent]);   // default uWeight, as the agent
+                if (!leaves.empty()) tree.evaluateAndBackpropLeaves(leaves, nets[agent]);
+                trav += n;
+            }
+            const auto* es = root->getEdgeStatistics();
+            for (int a = 0; a < A; ++a) {
+                mvN.push_back(es->m_numVisits[a]);
+                mvW.push_back(es->m_totalValues[a]);
+                mvP.push_back(es->m_childPriors[a]);
+            }
+            mvRootN.push_back(root->N());
+            mvRootW.push_back(root->W());
+            mvTrav.push_back(trav);
+            mvAgent.push_back(agent);
+            mvPlayer.push_back((int8_t)player);
+            for (int i = 0; i < B; ++i) mvBoard.push_back((int8_t)rootState.getHistory()[0][i]);
+            auto visits = es->m_numVisits;
+            int action = (int)std::distance(visits.begin(), std::max_element(visits.begin(), visits.end()));
+            mvAction.push_back(action);
+            actions.push_back(action);
+            tree.advanceDecision((ActionIdx)action);
+            trees[1 - agent]->advanceDecision((ActionIdx)action);
+            cur = cur->getAddChild((ActionIdx)action);
+        }
+        Player winner = cur->getWinner();
+        uint64_t myCtr = sprl_shim_get_counter();
+        if (myCtr != refCtr || winner != refWinner || actions != refActions) {
+            std::cerr << "instrumented match loop diverged from reference playGame in game " << g << "\n";
+            return 3;
+        }
+        gameMoves.push_back((int32_t)actions.size());
+        gameWinner.push_back((int32_t)winner);
+        gameFirst.push_back((int32_t)(t % 2));               // network that plays Player::ZERO
+        gameCtr.push_back(myCtr);
+    }
+    uint64_t M = mvAction.size();
+    TraceWriter w(outPath);
+    w.put("game_moves", 'i', gameMoves, { (uint64_t)nGames });
+    w.put("game_winner", 'i', gameWinner, { (uint64_t)nGames });
+    w.put("game_first", 'i', gameFirst, { (uint64_t)nGames });
+    w.put("game_rng_draws", 'Q', gameCtr, { (uint64_t)nGames });
+    w.put("move_N", 'f', mvN, { M, (uint64_t)A });
+    w.put("move_W", 'f', mvW, { M, (uint64_t)A });
+    w.put("move_P", 'f', mvP, { M, (uint64_t)A });
+    w.put("move_root_N", 'f', mvRootN, { M });
+    w.put("move_root_W", 'f', mvRootW, { M });
+    w.put("move_action", 'i', mvAction, { M });
+    w.put("move_traversals", 'i', mvTrav, { M });
+    w.put("move_agent", 'i', mvAgent, { M });
+    w.put("move_player", 'b', mvPlayer, { M });
+    w.put("move_board", 'b', mvBoard, { M, (uint64_t)B });
+    std::cout << "{\"moves\": " << M << "}" << std::endl;
+    return 0;
+}
+
 template <class D>
 int dispatch(int argc, char** argv) {
     std::string cmd = argv[1];
@@ -322,12 +480,16 @@ int dispatch(int argc, char** argv) {
     if (cmd == "rollout" && argc == 7)
         return cmdRollout<D>(std::strtoull(argv[3], 0, 10), std::strtoull(argv[4], 0, 10), std::atoi(argv[5]), argv[6]);
     if (cmd == "selfplay" && argc == 16) {
-        InitQ q = std::string(argv[14]) == "zero" ? InitQ::ZERO : InitQ::PARENT;
+        InitQ q = parseInitQ(argv[14]);
         return cmdSelfplay<D>(argv[3], std::strtoull(argv[4], 0, 10), std::strtoull(argv[5], 0, 10),
                               std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]), std::atoi(argv[9]),
                               (float)std::atof(argv[10]), (float)std::atof(argv[11]),
                               std::atoi(argv[12]) != 0, std::atoi(argv[13]) != 0, q, argv[15]);
     }
+    if (cmd == "match" && argc == 16)
+        return cmdMatch<D>(argv[3], argv[4], std::strtoull(argv[5], 0, 10), std::strtoull(argv[6], 0, 10), std::atoi(argv[7]),
+                           std::atoi(argv[8]), std::atoi(argv[9]), std::atoi(argv[10]), std::atoi(argv[11]) != 0,
+                           parseInitQ(argv[12]), std::atoi(argv[13]) != 0, parseInitQ(argv[14]), argv[15]);
     std::cerr << "bad arguments; see the header of ref_trace.cpp\n";
     return 2;
 }

@@ -200,6 +200,9 @@ __host__ __device__ __forceinline__ uint64_t hash_mix(uint64_t z) {
 __host__ __device__ __forceinline__ uint64_t hashnet_seed(int player) {
     return hash_mix(0x5350524C42323030ULL ^ (uint64_t)player);
 }
+__host__ __device__ __forceinline__ uint64_t hashnet_salt(uint64_t h, uint64_t salt) {   // second net of a match; 0 = plain
+    return salt ? hash_mix(h ^ (salt * 0xD6E8FEB86659FD93ULL)) : h;
+}
 __host__ __device__ __forceinline__ float hashnet_prior_raw(uint64_t h, int i) {
     return (float)((hash_mix(h ^ ((uint64_t)(i + 1) << 32)) >> 40) + 1);
 }

@@ -26,6 +26,18 @@ SELFPLAY = [
     ("c4_hash_512_8_4", "c4", "hash", 0, 0, 3, 512, 8, 4, 0.25, 0.5, 1, 1, "parent"),
     ("c4_uniform_2048_1_1", "c4", "uniform", 1, 0, 1, 2048, 1, 1, 0.25, 0.5, 1, 1, "parent"),
     ("go_hash_100_16_8", "go", "hash", 0, 0, 1, 100, 16, 8, 0.25, 0.2, 1, 1, "parent"),
+    # networks/OthelloHeuristic.cpp as the evaluator, InitQ::DROP_PARENT
+    ("othello_heuristic_100_8_4", "othello", "heuristic", 3, 0, 1, 100, 8, 4, 0.25, 0.3, 1, 1, "parent"),
+    ("othello_hash_drop_120_8_4", "othello", "hash", 4, 0, 1, 120, 8, 4, 0.25, 0.3, 1, 1, "drop"),
+    ("c4_hash_drop_200_8_4", "c4", "hash", 2, 5, 2, 200, 8, 4, 0.25, 0.5, 1, 1, "drop"),
+]
+# match play (Evaluate.cpp).  name, game, evaluator0, evaluator1, seed, first_game, ngames, sims, batch,
+# queue, sym0, initq0, sym1, initq1
+MATCH = [
+    ("othello_hash_hash1_100_8_4", "othello", "hash", "hash1", 0, 0, 2, 100, 8, 4, 1, "parent", 1, "parent"),
+    ("othello_heuristic_uniform_60_8_4", "othello", "heuristic", "uniform", 1, 3, 2, 60, 8, 4, 0, "zero", 1, "parent"),
+    ("c4_hash_hash1_128_8_4", "c4", "hash", "hash1", 0, 0, 4, 128, 8, 4, 1, "parent", 0, "zero"),
+    ("go_hash_hash1_50_16_8", "go", "hash", "hash1", 0, 0, 1, 50, 16, 8, 1, "parent", 1, "drop"),
 ]
 PERFT = {"othello": 9, "c4": 8, "go": 3}
 
@@ -54,6 +66,12 @@ def main():
                                 cmd=json.dumps(dict(game=game, evaluator=ev, seed=seed, first_game=first, ngames=n,
                                                     sims=sims, max_batch=b, max_queue=q, eps=eps, alpha=alpha,
                                                     noise=noise, sym=sym, initq=initq)), **t)
+        for name, game, ev0, ev1, seed, first, n, sims, b, q, sym0, q0, sym1, q1 in MATCH:
+            O.run_ref("match", game, ev0, ev1, seed, first, n, sims, b, q, sym0, q0, sym1, q1, path)
+            t = O.read_trace(path)
+            np.savez_compressed(os.path.join(HERE, f"match_{name}.npz"),
+                                cmd=json.dumps(dict(game=game, evaluators=[ev0, ev1], seed=seed, first_game=first, ngames=n,
+                                                    sims=sims, max_batch=b, max_queue=q, sym=[sym0, sym1], initq=[q0, q1])), **t)
     print("golden fixtures written to", HERE)
 
 

@@ -8,10 +8,12 @@ import oracle_py as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GAME_ID = {"othello": O.OG_OTHELLO, "c4": O.OG_C4, "go": O.OG_GO7}
-EVAL_ID = {"hash": O.OE_HASHNET, "uniform": O.OE_UNIFORM}
-INITQ_ID = {"parent": O.OQ_PARENT, "zero": O.OQ_ZERO}
+EVAL_ID = {"hash": O.OE_HASHNET, "hash1": O.OE_HASHNET, "uniform": O.OE_UNIFORM, "heuristic": O.OE_HEURISTIC}
+HASH_SALT = {"hash1": 1}
+INITQ_ID = {"parent": O.OQ_PARENT, "zero": O.OQ_ZERO, "drop": O.OQ_DROP_PARENT}
 
 SELFPLAY_FIXTURES = sorted(f[len("selfplay_"):-4] for f in os.listdir(GOLDEN) if f.startswith("selfplay_"))
+MATCH_FIXTURES = sorted(f[len("match_"):-4] for f in os.listdir(GOLDEN) if f.startswith("match_"))
 ROLLOUT_FIXTURES = sorted(f[len("rollout_"):-4] for f in os.listdir(GOLDEN) if f.startswith("rollout_"))
 
 
@@ -22,6 +24,12 @@ def load(name):
     if "states" in d:
         d["states"] = d["states"].astype(np.float32)
     return cmd, d
+
+
+def match_agents(cmd):
+    """The two agent descriptions of a match fixture, as oracle_py.match() takes them."""
+    return [dict(evaluator=EVAL_ID[cmd["evaluators"][k]], hash_salt=HASH_SALT.get(cmd["evaluators"][k], 0),
+                 use_sym=cmd["sym"][k], init_q=INITQ_ID[cmd["initq"][k]]) for k in range(2)]
 
 
 def perft_table():

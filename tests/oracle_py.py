@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_TRACE = os.path.join(ORACLE_DIR, "_ref", "ref_trace")
 
 OG_OTHELLO, OG_C4, OG_GO7, OG_GO9 = 0, 1, 2, 3
-OE_UNIFORM, OE_HASHNET, OE_CALLBACK = 0, 1, 2
-OQ_ZERO, OQ_PARENT = 0, 1
+OE_UNIFORM, OE_HASHNET, OE_CALLBACK, OE_HEURISTIC = 0, 1, 2, 3
+OQ_ZERO, OQ_PARENT, OQ_DROP_PARENT = 0, 1, 2
 GAME_NAMES = {OG_OTHELLO: "othello", OG_C4: "c4", OG_GO7: "go"}
 
 _DT = {"b": np.int8, "i": np.int32, "f": np.float32, "Q": np.uint64}
@@ -60,7 +60,15 @@ class SelfplayCfg(C.Structure):
     _fields_ = [("game", C.c_int), ("evaluator", C.c_int), ("seed", C.c_uint64), ("sims", C.c_int),
                 ("max_batch", C.c_int), ("max_queue", C.c_int), ("dir_eps", C.c_float), ("dir_alpha", C.c_float),
                 ("add_noise", C.c_int), ("use_sym", C.c_int), ("init_q", C.c_int), ("u_weight", C.c_float),
-                ("eval_cb", EVAL_CB), ("eval_user", C.c_void_p)]
+                ("eval_cb", EVAL_CB), ("eval_user", C.c_void_p), ("hash_salt", C.c_uint64)]
+
+
+class MatchOut(C.Structure):
+    _fields_ = [("cap_moves", C.c_int64), ("game_moves", C.c_void_p), ("game_winner", C.c_void_p),
+                ("game_rng_draws", C.c_void_p), ("move_N", C.c_void_p), ("move_W", C.c_void_p), ("move_P", C.c_void_p),
+                ("move_root_N", C.c_void_p), ("move_root_W", C.c_void_p), ("move_action", C.c_void_p),
+                ("move_traversals", C.c_void_p), ("move_agent", C.c_void_p), ("move_player", C.c_void_p),
+                ("n_moves", C.c_int64), ("wins", C.c_int64 * 2), ("draws", C.c_int64)]
 
 
 class SelfplayOut(C.Structure):
@@ -190,6 +198,50 @@ def selfplay(game, evaluator, seed, first_game, ngames, sims, max_batch, max_que
                         select_depth_sum=out.select_depth_sum, select_legal_sum=out.select_legal_sum,
                         select_nodes=out.select_nodes, leaves_terminal=out.leaves_terminal,
                         leaves_gray=out.leaves_gray, leaves_empty=out.leaves_empty)
+    return res
+
+
+def _make_eval_cb(gi, eval_fn):
+    A = gi.actions
+
+    def _cb(_user, planes, n, logits, values):
+        x = np.ctypeslib.as_array(planes, shape=(n, 2 * gi.history + 1, gi.rows, gi.cols))
+        lg, v = eval_fn(x)
+        np.ctypeslib.as_array(logits, shape=(n, A))[:] = np.asarray(lg, np.float32).reshape(n, A)
+        np.ctypeslib.as_array(values, shape=(n,))[:] = np.asarray(v, np.float32).reshape(n)
+    return EVAL_CB(_cb)
+
+
+def match(game, agents, seed, first_game, ngames, sims, max_batch, max_queue, max_moves_per_game=200):
+    """Run the oracle's match play.  agents = two dicts with keys evaluator, use_sym, init_q and optionally
+    hash_salt / eval_fn.  Returns a dict shaped like a ref_trace match trace (+ wins, draws)."""
+    gi = game_info(game)
+    A = gi.actions
+    cap_m = ngames * max_moves_per_game
+    arr = dict(game_moves=np.zeros(ngames, np.int32), game_winner=np.zeros(ngames, np.int32),
+               game_rng_draws=np.zeros(ngames, np.uint64),
+               move_N=np.zeros((cap_m, A), np.float32), move_W=np.zeros((cap_m, A), np.float32),
+               move_P=np.zeros((cap_m, A), np.float32), move_root_N=np.zeros(cap_m, np.float32),
+               move_root_W=np.zeros(cap_m, np.float32), move_action=np.zeros(cap_m, np.int32),
+               move_traversals=np.zeros(cap_m, np.int32), move_agent=np.zeros(cap_m, np.int32),
+               move_player=np.zeros(cap_m, np.int8))
+    cfgs = (SelfplayCfg * 2)()
+    keep = []
+    for k, ag in enumerate(agents):
+        cfgs[k] = SelfplayCfg(game=game, evaluator=ag["evaluator"], seed=seed, sims=sims, max_batch=max_batch,
+                              max_queue=max_queue, use_sym=int(ag.get("use_sym", 1)), init_q=ag.get("init_q", OQ_PARENT),
+                              hash_salt=ag.get("hash_salt", 0))
+        if ag["evaluator"] == OE_CALLBACK:
+            keep.append(_make_eval_cb(gi, ag["eval_fn"]))
+            cfgs[k].eval_cb = keep[-1]
+    out = MatchOut(cap_moves=cap_m)
+    for k, v in arr.items():
+        setattr(out, k, v.ctypes.data)
+    rc = lib().oracle_match(cfgs, C.c_uint64(first_game), C.c_int(ngames), C.byref(out))
+    assert rc == 0, rc
+    res = {k: (v[:out.n_moves] if k.startswith("move_") else v) for k, v in arr.items()}
+    res["wins"] = (out.wins[0], out.wins[1])
+    res["draws"] = out.draws
     return res
 
 

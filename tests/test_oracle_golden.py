@@ -53,6 +53,20 @@ def test_selfplay_matches_reference(name):
     G.assert_trace_equal(ref, got, ["distributions"], exact=False)
 
 
+@pytest.mark.parametrize("name", G.MATCH_FIXTURES)
+def test_match_play_matches_reference(name):
+    """Evaluate.cpp's match path (UCTNetworkAgent + playGame), two trees per game: bit-exact."""
+    cmd, ref = G.load("match_" + name)
+    got = O.match(G.GAME_ID[cmd["game"]], G.match_agents(cmd), cmd["seed"], cmd["first_game"], cmd["ngames"],
+                  cmd["sims"], cmd["max_batch"], cmd["max_queue"])
+    G.assert_trace_equal(ref, got, ["game_moves", "game_winner", "game_rng_draws", "move_N", "move_W", "move_P",
+                                    "move_root_N", "move_root_W", "move_action", "move_traversals", "move_agent",
+                                    "move_player"])
+    first = ref["game_first"]
+    wins = [int(((ref["game_winner"] >= 0) & ((ref["game_winner"] ^ first) == k)).sum()) for k in (0, 1)]
+    assert got["wins"] == tuple(wins) and got["draws"] == int((ref["game_winner"] < 0).sum())
+
+
 def test_othello_quirks():
     """Quirks the survey lists are visible in the traces."""
     cmd, ref = G.load("selfplay_othello_hash_400_8_4")
