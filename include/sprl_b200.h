@@ -40,10 +40,12 @@ extern "C" {
 #define SPRL_EVAL_UNIFORM 0    /* networks/RandomNetwork.hpp:21-49, evaluated on device */
 #define SPRL_EVAL_HASHNET 1    /* deterministic test evaluator, evaluated on device */
 #define SPRL_EVAL_EXTERNAL 2   /* networks/GridNetwork.hpp:62-145: caller runs the traced network on device buffers */
+#define SPRL_EVAL_OTHELLO_HEURISTIC 3 /* networks/OthelloHeuristic.cpp:5-53 (Othello only), evaluated on device */
 
 /* uct/UCTNode.hpp:24-28 */
 #define SPRL_INITQ_ZERO 0
 #define SPRL_INITQ_PARENT 1
+#define SPRL_INITQ_DROP_PARENT 2 /* :152-163,196-206: unvisited children answer with the node's own Q = W/N */
 
 const char* sprl_last_error(void);
 int sprl_device_count(void);
@@ -171,6 +173,30 @@ int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_dist
 int sprl_move_stats(sprl_engine* e, int64_t cap_moves, float* h_N, float* h_W, float* h_P, float* h_root_N,
                     float* h_root_W, int32_t* h_action, int32_t* h_traversals, int8_t* h_player,
                     int32_t* h_game_moves, uint64_t* h_game_draws, int64_t* n_moves);
+
+/* ------------------------------------------------------------------ match play
+ * Replaces Evaluate.cpp:93-157: UCTNetworkAgent::act / opponentAct (agents/UCTNetworkAgent.hpp:42-108) inside
+ * playGame (evaluate/play.hpp:24-69), for num_slots / 2 concurrent games.  Each game is served by two trees, one
+ * per side, with its own evaluator, symmetrizer and init-Q; the side to move spends `sims` descents in its tree,
+ * plays the first action with the most visits, and both trees advance.  Game t (stream id, as in self-play) gives
+ * Player ZERO to agent t % 2.  Search constants come from the engine's config (Evaluate.cpp uses Dirichlet noise
+ * on, eps 0.25, alpha 0.1 and the default uWeight 1.0).  Trees [0, num_slots/2) belong to agent 0 and
+ * [num_slots/2, 2 * (num_slots/2)) to agent 1, so with SPRL_EVAL_EXTERNAL the first half of the evaluator batch
+ * (row tree * max_queue + q) is agent 0's network input and the second half agent 1's. */
+typedef struct {
+    int evaluator;          /* SPRL_EVAL_* of this side */
+    int use_sym;            /* Evaluate.cpp model<k>UseSymmetrize */
+    int init_q;             /* Evaluate.cpp model<k>UseParentQ ? PARENT : ZERO */
+    uint64_t hash_salt;     /* SPRL_EVAL_HASHNET: 0 = the plain test net, other values = independent nets */
+} sprl_agent_config;
+
+/* Starts a match of games first_game .. (stride as in self-play); then sprl_round / sprl_poll as usual. */
+int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents /* [2] */, uint64_t first_game, int64_t num_games);
+
+/* Results of the finished match: per game the winner (-1 none / 0 / 1 = Player), moves played and RNG draws used
+ * (any of them may be NULL); wins[2] = games won by agent 0 / agent 1, draws (Evaluate.cpp:139-155). */
+int sprl_match_results(sprl_engine* e, int64_t cap_games, int8_t* h_winner, int32_t* h_moves, uint64_t* h_draws,
+                       int64_t* wins /* [2] */, int64_t* draws);
 
 typedef struct {
     uint64_t sims, evals, moves, games;

@@ -13,15 +13,15 @@ from . import build as _build
 SPRL_OK = 0
 SPRL_E_INVALID, SPRL_E_CUDA, SPRL_E_CAPACITY, SPRL_E_STATE, SPRL_E_IO, SPRL_E_NOGPU = -1, -2, -3, -4, -5, -6
 GAME_OTHELLO, GAME_C4, GAME_GO7, GAME_GO9 = 0, 1, 2, 3
-EVAL_UNIFORM, EVAL_HASHNET, EVAL_EXTERNAL = 0, 1, 2
-INITQ_ZERO, INITQ_PARENT = 0, 1
+EVAL_UNIFORM, EVAL_HASHNET, EVAL_EXTERNAL, EVAL_OTHELLO_HEURISTIC = 0, 1, 2, 3
+INITQ_ZERO, INITQ_PARENT, INITQ_DROP_PARENT = 0, 1, 2
 
 EXPORTS = [
     "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
     "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
     "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
-    "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
+    "sprl_match_begin", "sprl_match_results", "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
     "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_destroy",
 ]
 
@@ -52,6 +52,10 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class AgentConfig(C.Structure):
+    _fields_ = [("evaluator", C.c_int), ("use_sym", C.c_int), ("init_q", C.c_int), ("hash_salt", C.c_uint64)]
 
 
 class ConvBnParams(C.Structure):
@@ -101,6 +105,9 @@ def load():
     lib.sprl_collect_samples.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     lib.sprl_collect_samples_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.sprl_match_begin.argtypes = [C.c_void_p, C.POINTER(AgentConfig), C.c_uint64, C.c_int64]
+    lib.sprl_match_results.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]
     lib.sprl_move_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.POINTER(C.c_int64)]
     lib.sprl_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.sprl_reset_stats.argtypes = [C.c_void_p]

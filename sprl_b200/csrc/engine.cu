@@ -14,6 +14,8 @@ void search_launch_begin(int game, const EngineParams& p, cudaStream_t s);
 void search_launch_round(int game, const EngineParams& p, cudaStream_t s);
 void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
                         cudaStream_t s);
+void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
+void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 int search_header_units(int game);
 }  // namespace sprl
 
@@ -28,6 +30,8 @@ struct sprl_engine {
     int64_t num_games = 0;          // of the running / last iteration
     int64_t active_slots = 0;
     bool iteration_open = false;
+    bool match_open = false;        // the open iteration is a match (pairs of trees)
+    MatchParams match;
     bool failed = false;            // sticky CUDA error
     uint64_t launches = 0;
     uint64_t device_bytes = 0;
@@ -99,6 +103,14 @@ static int sum_tree_stats(sprl_engine* e, sprl_stats* out) {
     return SPRL_OK;
 }
 
+static int check_tree_options(int game, int evaluator, int init_q) {
+    if (evaluator < SPRL_EVAL_UNIFORM || evaluator > SPRL_EVAL_OTHELLO_HEURISTIC) return fail(SPRL_E_INVALID, "unknown evaluator %d", evaluator);
+    if (evaluator == SPRL_EVAL_OTHELLO_HEURISTIC && game != SPRL_GAME_OTHELLO)
+        return fail(SPRL_E_INVALID, "SPRL_EVAL_OTHELLO_HEURISTIC evaluates Othello positions only");
+    if (init_q < SPRL_INITQ_ZERO || init_q > SPRL_INITQ_DROP_PARENT) return fail(SPRL_E_INVALID, "unknown init_q %d", init_q);
+    return SPRL_OK;
+}
+
 extern "C" {
 
 int sprl_default_config(int game, sprl_config* cfg) {
@@ -128,8 +140,8 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (rc) return rc;
     if (cfg->num_slots <= 0 || cfg->sims <= 0 || cfg->max_batch <= 0 || cfg->max_queue <= 0)
         return fail(SPRL_E_INVALID, "num_slots, sims, max_batch and max_queue must be positive");
-    if (cfg->evaluator < SPRL_EVAL_UNIFORM || cfg->evaluator > SPRL_EVAL_EXTERNAL) return fail(SPRL_E_INVALID, "unknown evaluator %d", cfg->evaluator);
-    if (cfg->init_q != SPRL_INITQ_ZERO && cfg->init_q != SPRL_INITQ_PARENT) return fail(SPRL_E_INVALID, "unknown init_q %d", cfg->init_q);
+    rc = check_tree_options(cfg->game, cfg->evaluator, cfg->init_q);
+    if (rc) return rc;
     if (!(cfg->dir_alpha > 0.0f) && cfg->add_noise) return fail(SPRL_E_INVALID, "dir_alpha must be positive");
     rc = use_device(cfg->device);
     if (rc) return rc;
@@ -251,6 +263,78 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
     e->launches += 1;
     ENGINE_CUDA(e, cudaGetLastError());
     e->iteration_open = true;
+    e->match_open = false;
+    return SPRL_OK;
+}
+
+static int load_game_moves(sprl_engine* e, int64_t* n_moves);
+
+int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t first_game, int64_t num_games) {
+    ENGINE_CHECK(e);
+    if (!h_agents) return fail(SPRL_E_INVALID, "null agents");
+    if (num_games <= 0) return fail(SPRL_E_INVALID, "num_games must be positive");
+    if (num_games > e->cfg.max_games) return fail(SPRL_E_CAPACITY, "num_games %lld exceeds max_games %lld", (long long)num_games, (long long)e->cfg.max_games);
+    if (e->cfg.num_slots < 2) return fail(SPRL_E_INVALID, "a match needs two tree slots per game");
+    bool external = false;
+    for (int k = 0; k < 2; ++k) {
+        int rc = check_tree_options(e->cfg.game, h_agents[k].evaluator, h_agents[k].init_q);
+        if (rc) return rc;
+        external = external || h_agents[k].evaluator == SPRL_EVAL_EXTERNAL;
+        e->match.agent[k].evaluator = h_agents[k].evaluator;
+        e->match.agent[k].use_sym = h_agents[k].use_sym;
+        e->match.agent[k].init_q = h_agents[k].init_q;
+        e->match.agent[k].pad = 0;
+        e->match.agent[k].hash_salt = h_agents[k].hash_salt;
+    }
+    if (external && e->cfg.evaluator != SPRL_EVAL_EXTERNAL)
+        return fail(SPRL_E_STATE, "an agent with SPRL_EVAL_EXTERNAL needs an engine created with SPRL_EVAL_EXTERNAL");
+    if (external && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
+    e->match.n_pairs = e->cfg.num_slots / 2;
+    e->p.first_game = first_game;
+    e->p.num_games = num_games;
+    e->num_games = num_games;
+    e->active_slots = std::min<int64_t>(num_games, e->match.n_pairs);
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_moves, 0, (size_t)e->cfg.max_games * sizeof(int), e->stream));
+    if (e->cfg.record_stats) {
+        const size_t bytes = (size_t)e->cfg.max_games * e->p.max_moves * e->gi.actions * sizeof(float);
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_N, 0, bytes, e->stream));
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_W, 0, bytes, e->stream));
+        ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_P, 0, bytes, e->stream));
+    }
+    search_launch_match_begin(e->cfg.game, e->p, e->match, e->stream);
+    e->launches += 1;
+    ENGINE_CUDA(e, cudaGetLastError());
+    e->iteration_open = true;
+    e->match_open = true;
+    return SPRL_OK;
+}
+
+int sprl_match_results(sprl_engine* e, int64_t cap_games, int8_t* h_winner, int32_t* h_moves, uint64_t* h_draws,
+                       int64_t* wins, int64_t* draws) {
+    ENGINE_CHECK(e);
+    if (!e->iteration_open || !e->match_open) return fail(SPRL_E_STATE, "no match has been run");
+    if (cap_games < e->num_games && (h_winner || h_moves || h_draws))
+        return fail(SPRL_E_CAPACITY, "%lld games do not fit the caller's capacity %lld", (long long)e->num_games, (long long)cap_games);
+    int64_t total = 0;
+    int rc = load_game_moves(e, &total);
+    if (rc) return rc;
+    std::vector<unsigned char> w((size_t)e->num_games);
+    ENGINE_CUDA(e, cudaMemcpyAsync(w.data(), e->p.rec_winner, w.size(), cudaMemcpyDeviceToHost, e->stream));
+    if (h_draws) ENGINE_CUDA(e, cudaMemcpyAsync(h_draws, e->p.rec_draws, (size_t)e->num_games * 8, cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    int64_t tally[2] = { 0, 0 }, none = 0;
+    for (int64_t g = 0; g < e->num_games; ++g) {
+        const int winner = (int)w[g] - 1;                       // device encoding: 0 none, 1 ZERO, 2 ONE
+        if (h_winner) h_winner[g] = (int8_t)winner;
+        if (h_moves) h_moves[g] = e->h_moves[g];
+        if (e->h_moves[g] == 0) continue;                        // not played
+        const uint64_t id = e->p.first_game + (uint64_t)g * e->p.game_stride;
+        if (winner < 0) none += 1;
+        else tally[(id & 1ULL) ? 1 - winner : winner] += 1;     // Evaluate.cpp:139-153
+    }
+    if (wins) { wins[0] = tally[0]; wins[1] = tally[1]; }
+    if (draws) *draws = none;
     return SPRL_OK;
 }
 
@@ -258,6 +342,12 @@ int sprl_round(sprl_engine* e) {
     ENGINE_CHECK(e);
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration in progress");
     if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
+    if (e->match_open) {
+        search_launch_match_round(e->cfg.game, e->p, e->match, e->stream);
+        e->launches += 1;
+        ENGINE_CUDA(e, cudaGetLastError());
+        return SPRL_OK;
+    }
     search_launch_round(e->cfg.game, e->p, e->stream);
     e->launches += 2;               // the search kernel and the order flip
     ENGINE_CUDA(e, cudaGetLastError());

@@ -132,7 +132,7 @@ struct WarpScratch {
 };
 
 // ---- the warp that owns a tree -----------------------------------------------------------------
-template <class G>
+template <class G, bool MATCH = false>
 struct TreeWarp {
     static constexpr int W = G::W;
     static constexpr int HDR = HL<W>::HDR;
@@ -157,9 +157,18 @@ struct TreeWarp {
     Rng rng;
     uint4* slab;            // current slab
     WarpScratch& sm;
+    AgentCfg agent;         // match play: this side's evaluator / symmetrizer / init-Q (unused in self-play)
+    int game_step;          // game_index stride: slots (self-play) or pairs (match play)
 
-    __device__ TreeWarp(const EngineParams& p_, int tree_, int lane_, WarpScratch& sm_)
+    // per-tree options: the engine's in self-play, the side's in match play
+    __device__ __forceinline__ int cfg_evaluator() const { if constexpr (MATCH) return agent.evaluator; else return p.evaluator; }
+    __device__ __forceinline__ int cfg_use_sym() const { if constexpr (MATCH) return agent.use_sym; else return p.use_sym; }
+    __device__ __forceinline__ int cfg_init_q() const { if constexpr (MATCH) return agent.init_q; else return p.init_q; }
+    __device__ __forceinline__ unsigned long long cfg_salt() const { if constexpr (MATCH) return agent.hash_salt; else return 0ULL; }
+
+    __device__ TreeWarp(const EngineParams& p_, int tree_, int lane_, WarpScratch& sm_, const AgentCfg* agent_ = nullptr, int game_step_ = 0)
         : p(p_), tree(tree_), lane(lane_), sm(sm_) {
+        if constexpr (MATCH) { agent = *agent_; game_step = game_step_; } else { game_step = p_.n_slots; }
         const TreeState& g = p.trees[tree];
         st.game_id = g.game_id; st.n_units = g.n_units; st.slab = g.slab; st.high_water = g.high_water;
         st.traversals = g.traversals; st.move_count = g.move_count; st.status = g.status; st.n_queued = g.n_queued;
@@ -343,6 +352,11 @@ struct TreeWarp {
         u32 cur = ROOT_UNIT;
         uint4 d = slab[0];
         float n_own = __uint_as_float(d.z);
+        // InitQ::DROP_PARENT (uct/UCTNode.hpp:152-163,196-206): W, N of the current node before this descent's
+        // virtual loss, and the Q of its parent after it (the answer of an unvisited node; never needed in
+        // practice, a node is visited before it is expanded)
+        const bool drop = cfg_init_q() == SPRL_INITQ_DROP_PARENT;
+        float w_own = __uint_as_float(d.y), q_par = 0.0f;
         if (lane == 0) slab[0] = make_uint4(d.x, __float_as_uint(__uint_as_float(d.y) - 1.0f), __float_as_uint(n_own + 1.0f), d.w);
         int depth = 0;
         bool have = false;
@@ -355,6 +369,8 @@ struct TreeWarp {
             acc.nodes_visited += 1; acc.legal_sum += n;
             // UCTNode::bestAction (uct/UCTNode.hpp:221-251)
             const float sq = sqrtf(n_own);
+            float q_own = 0.0f;
+            if (drop) q_own = (n_own == 0.0f) ? q_par : w_own / n_own;
             uint4 e[NCH];
             float val[NCH];
             float best = -__int_as_float(0x7f800000);
@@ -367,6 +383,7 @@ struct TreeWarp {
                     float prior = (cur == ROOT_UNIT && p.add_noise) ? p.root_p[(size_t)tree * G::ACTIONS + k] : __uint_as_float(e[ch].x);
                     float w = __uint_as_float(e[ch].y), nv = __uint_as_float(e[ch].z);
                     float q = w / (1.0f + nv);
+                    if (drop) q = (nv == 0.0f) ? q_own : w / nv;
                     float u = prior * sq / (1.0f + nv);
                     val[ch] = q + p.u_weight * u;
                 }
@@ -411,9 +428,10 @@ struct TreeWarp {
                 H ch;
                 write_node(slab, child, cp, cur, edge_unit, ch);
                 ew |= child;
-                w_sel = (p.init_q == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
+                w_sel = (cfg_init_q() == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
                 h = ch; have = true;
             }
+            if (drop) { q_par = (w_own - 1.0f) / (n_own + 1.0f); w_own = __shfl_sync(FULL, w_sel, src_lane); }
             if (lane == src_lane)
                 slab[edge_unit] = make_uint4(es.x, __float_as_uint(w_sel - 1.0f), __float_as_uint(child_n + 1.0f), ew);
             n_own = child_n;
@@ -458,9 +476,9 @@ struct TreeWarp {
         st.n_queued = nq;
         __syncwarp();
         for (int q = 0; q < nq; ++q) {
-            int s = p.use_sym ? rng_uniform_int(rng, 0, G::NSYM - 1) : 0;
+            int s = cfg_use_sym() ? rng_uniform_int(rng, 0, G::NSYM - 1) : 0;
             if (lane == 0) p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s;
-            if (p.evaluator == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)tree * p.max_queue + q);
+            if (cfg_evaluator() == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)tree * p.max_queue + q);
         }
         acc.evals += nq;
         __syncwarp();
@@ -527,22 +545,33 @@ struct TreeWarp {
         float value = 0.0f;
         for (int i = lane; i < G::ACTIONS; i += 32) sm.pol[i] = 0.0f;
         __syncwarp();
-        if (p.evaluator == SPRL_EVAL_UNIFORM) {             // networks/RandomNetwork.hpp:21-49
+        const int ev = cfg_evaluator();
+        if (ev == SPRL_EVAL_UNIFORM || ev == SPRL_EVAL_OTHELLO_HEURISTIC) {   // networks/RandomNetwork.hpp:21-49
             float uniform = 1.0f / (float)n;
             for (int base = 0; base < n; base += 32) {
                 int k = base + lane;
                 if (k < n) sm.pol[legal_action<G>(pos, k)] = uniform;
             }
             __syncwarp();
+            if constexpr (G::KIND == GAME_OTHELLO) {
+                if (ev == SPRL_EVAL_OTHELLO_HEURISTIC) {
+                    // networks/OthelloHeuristic.cpp:18-50: (own legal actions, the pass slot included, minus the
+                    // opponent's placements) / empty squares; all three counts are symmetry-invariant
+                    const u64 own = player == 0 ? h.b0.w0 : h.b1.w0, opp = player == 0 ? h.b1.w0 : h.b0.w0;
+                    const int num_opp = __popcll(Othello::mobility(opp, own));
+                    const int num_empty = 64 - __popcll(own | opp);
+                    value = (float)(n - num_opp) / (float)num_empty;
+                }
+            }
         } else {
             unsigned long long hh = 0;
-            if (p.evaluator == SPRL_EVAL_HASHNET) { hh = state_hash(unit, player, s); value = hashnet_value(hh); }
+            if (ev == SPRL_EVAL_HASHNET) { hh = hashnet_salt(state_hash(unit, player, s), cfg_salt()); value = hashnet_value(hh); }
             else value = p.nn_value[slot];
             for (int base = 0; base < n; base += 32) {
                 int k = base + lane;
                 if (k < n) {
                     int i = legal_action<G>(pos, k);        // mask index == policy index (symmetrised frame)
-                    sm.pol[i] = (p.evaluator == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
+                    sm.pol[i] = (ev == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
                                                                     : det_expf(p.nn_logits[slot * G::ACTIONS + i]);
                 }
             }
@@ -567,7 +596,7 @@ struct TreeWarp {
             int k = base + lane;
             if (k < n) {
                 int a = legal_action<G>(pos, k);
-                float prior = sm.pol[p.use_sym ? sym_action<G>(s, a) : a];
+                float prior = sm.pol[cfg_use_sym() ? sym_action<G>(s, a) : a];
                 reinterpret_cast<float*>(slab + unit + HDR + k)[0] = prior;
             }
         }
@@ -684,17 +713,9 @@ struct TreeWarp {
         return true;
     }
 
-    // ---- per-move finalisation of selfPlay (selfplay/SelfPlay.hpp:111-146) ----
-    __device__ void finalize_move() {
-        H h;
-        HL<W>::load(slab + ROOT_UNIT, h);
-        P pos;
-        hdr_to_pos<G>(h, pos);
-        const int n = META_NLEGAL(h.meta);
-        if (st.move_count >= p.max_moves) { st.status = ST_ERR_MOVES; return; }
-        const size_t ri = rec_index();
+    // ---- the decision node's statistics and position, recorded when a move is made ----
+    __device__ void record_root(const H& h, const P& pos, int n, size_t ri) {
         uint4 dummy = slab[0];
-        // visits into a dense action vector
         for (int i = lane; i < G::ACTIONS; i += 32) sm.pol[i] = 0.0f;
         __syncwarp();
         for (int base = 0; base < n; base += 32) {
@@ -711,11 +732,79 @@ struct TreeWarp {
             }
         }
         __syncwarp();
-        if (p.record_stats && lane == 0) {
-            p.rec_root_W[ri] = __uint_as_float(dummy.y);
-            p.rec_root_N[ri] = __uint_as_float(dummy.z);
-            p.rec_trav[ri] = st.traversals;
+        if (lane == 0) {
+            if (p.record_stats) {
+                p.rec_root_W[ri] = __uint_as_float(dummy.y);
+                p.rec_root_N[ri] = __uint_as_float(dummy.z);
+                p.rec_trav[ri] = st.traversals;
+            }
+            for (int w = 0; w < W; ++w) {
+                p.rec_board[ri * 2 * W + w] = h.b0.word(w);
+                p.rec_board[ri * 2 * W + W + w] = h.b1.word(w);
+            }
+            p.rec_player[ri] = (unsigned char)pos.player;
         }
+    }
+
+    // ---- UCTTree::advanceDecision (uct/UCTTree.hpp:197-210) to edge slot ksel of the decision node ----
+    __device__ bool advance_root(const H& h, const P& pos, int ksel, int action) {
+        const u32 edge_unit = ROOT_UNIT + HDR + ksel;
+        uint4 es = slab[edge_unit];
+        u32 child = EDGE_CHILD(es.w);
+        float own_w = __uint_as_float(es.y), own_n = __uint_as_float(es.z);
+        if (child == 0) {
+            P cp;
+            make_child_pos(pos, ROOT_UNIT, action, cp);
+            u32 need = HDR + (cp.terminal ? 0u : (u32)cp.n_legal());
+            if (st.n_units + need + SLAB_SLACK > p.cap_units) { st.status = ST_ERR_CAPACITY; return false; }
+            child = st.n_units;
+            st.n_units += need;
+            H ch;
+            write_node(slab, child, cp, ROOT_UNIT, edge_unit, ch);
+            own_w = (cfg_init_q() == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
+            __syncwarp();
+        }
+        if (st.n_units > st.high_water) st.high_water = st.n_units;
+        uint4* dst = slab_ptr(st.slab ^ 1u);
+        u32 units = 0;
+        if (!compact_into(dst, child, own_w, own_n, units)) { st.status = ST_ERR_CAPACITY; return false; }
+        st.slab ^= 1u;
+        slab = dst;
+        st.n_units = units;
+        st.traversals = 0;
+        st.move_count += 1;
+        st.n_queued = 0;
+        __syncwarp();
+        return true;
+    }
+
+    // ---- after a move: a finished game is recorded (`record`: once per game) and the slot starts its next one ----
+    __device__ void after_move(bool record) {
+        u32 rmeta = *HL<W>::meta_ptr(slab + ROOT_UNIT);
+        if (META_TERMINAL(rmeta)) {
+            // game over: the outcome of every recorded move is filled in by the sample writer
+            if (lane == 0 && record) {
+                p.rec_moves[st.game_index] = st.move_count;
+                p.rec_winner[st.game_index] = (unsigned char)META_WINNER(rmeta);
+                p.rec_draws[st.game_index] = rng.ctr;
+            }
+            if (record) acc.games += 1;
+            st.game_index += game_step;                  // static striding: game -> slot is deterministic
+            if (st.game_index < p.num_games) init_game();
+            else { st.status = ST_DONE; }
+        }
+    }
+
+    // ---- per-move finalisation of selfPlay (selfplay/SelfPlay.hpp:111-146) ----
+    __device__ void finalize_move() {
+        H h;
+        HL<W>::load(slab + ROOT_UNIT, h);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        const int n = META_NLEGAL(h.meta);
+        if (st.move_count >= p.max_moves) { st.status = ST_ERR_MOVES; return; }
+        const size_t ri = rec_index();
+        record_root(h, pos, n, ri);             // leaves the visit counts in sm.pol
         // pdf = visits / sum; pdf = pow(pdf, e); pdf = pdf / sum; cdf = cumsum(pdf) / last
         float sum = 0.0f;
         for (int k = 0; k < n; ++k) sum += sm.pol[legal_action<G>(pos, k)];
@@ -743,15 +832,7 @@ struct TreeWarp {
         }
         const float inv_last = 1.0f / run;
         __syncwarp();
-        // record the sample source: position, mover, pdf
         for (int i = lane; i < G::ACTIONS; i += 32) p.rec_pdf[ri * G::ACTIONS + i] = sm.pol[i];
-        if (lane == 0) {
-            for (int w = 0; w < W; ++w) {
-                p.rec_board[ri * 2 * W + w] = h.b0.word(w);
-                p.rec_board[ri * 2 * W + W + w] = h.b1.word(w);
-            }
-            p.rec_player[ri] = (unsigned char)pos.player;
-        }
         // Random::SampleCDF (utils/random.cpp:86-98)
         float e;
         do { e = rng_unit_f32(rng); } while (e == 0.0f);
@@ -761,50 +842,47 @@ struct TreeWarp {
         const int action = legal_action<G>(pos, ksel);
         if (p.record_stats && lane == 0) p.rec_action[ri] = action;
         __syncwarp();
-
-        // UCTTree::advanceDecision
-        const u32 edge_unit = ROOT_UNIT + HDR + ksel;
-        uint4 es = slab[edge_unit];
-        u32 child = EDGE_CHILD(es.w);
-        float own_w = __uint_as_float(es.y), own_n = __uint_as_float(es.z);
-        if (child == 0) {
-            P cp;
-            make_child_pos(pos, ROOT_UNIT, action, cp);
-            u32 need = HDR + (cp.terminal ? 0u : (u32)cp.n_legal());
-            if (st.n_units + need + SLAB_SLACK > p.cap_units) { st.status = ST_ERR_CAPACITY; return; }
-            child = st.n_units;
-            st.n_units += need;
-            H ch;
-            write_node(slab, child, cp, ROOT_UNIT, edge_unit, ch);
-            own_w = (p.init_q == SPRL_INITQ_PARENT && (h.meta & META_EVALUATED)) ? h.net_value : 0.0f;
-            __syncwarp();
-        }
-        if (st.n_units > st.high_water) st.high_water = st.n_units;
-        uint4* dst = slab_ptr(st.slab ^ 1u);
-        u32 units = 0;
-        if (!compact_into(dst, child, own_w, own_n, units)) { st.status = ST_ERR_CAPACITY; return; }
-        st.slab ^= 1u;
-        slab = dst;
-        st.n_units = units;
-        st.traversals = 0;
-        st.move_count += 1;
+        if (!advance_root(h, pos, ksel, action)) return;
         acc.moves += 1;
-        st.n_queued = 0;
-        __syncwarp();
+        after_move(true);
+    }
 
-        u32 rmeta = *HL<W>::meta_ptr(slab + ROOT_UNIT);
-        if (META_TERMINAL(rmeta)) {
-            // game over: the outcome of every recorded move is filled in by the sample writer
-            if (lane == 0) {
-                p.rec_moves[st.game_index] = st.move_count;
-                p.rec_winner[st.game_index] = (unsigned char)META_WINNER(rmeta);
-                p.rec_draws[st.game_index] = rng.ctr;
-            }
-            acc.games += 1;
-            st.game_index += p.n_slots;                  // static striding: game -> slot is deterministic
-            if (st.game_index < p.num_games) init_game();
-            else { st.status = ST_DONE; }
+    // ---- UCTNetworkAgent::act after its search (agents/UCTNetworkAgent.hpp:59-105): the FIRST action with the
+    //      most visits, then advanceDecision on the mover's own tree.  Returns the action (-1 on failure). ----
+    __device__ int finalize_match_move() {
+        H h;
+        HL<W>::load(slab + ROOT_UNIT, h);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        const int n = META_NLEGAL(h.meta);
+        if (st.move_count >= p.max_moves) { st.status = ST_ERR_MOVES; return -1; }
+        const size_t ri = rec_index();
+        record_root(h, pos, n, ri);
+        // std::max_element over all actions; illegal ones hold 0 visits.  (All-zero visit counts, possible only
+        // when sims <= max_queue, make the reference play action 0 even when it is illegal; here the first legal one.)
+        int ksel = 0;
+        float best = -1.0f;
+        for (int k = 0; k < n; ++k) {
+            float v = sm.pol[legal_action<G>(pos, k)];
+            if (v > best) { best = v; ksel = k; }
         }
+        const int action = legal_action<G>(pos, ksel);
+        if (p.record_stats && lane == 0) p.rec_action[ri] = action;
+        __syncwarp();
+        if (!advance_root(h, pos, ksel, action)) return -1;
+        acc.moves += 1;
+        after_move(true);
+        return action;
+    }
+
+    // ---- IAgent::opponentAct (agents/UCTNetworkAgent.hpp:107-109): the other side's tree follows the move ----
+    __device__ void follow_move(int action) {
+        H h;
+        HL<W>::load(slab + ROOT_UNIT, h);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        if (!advance_root(h, pos, action_slot<G>(pos, action), action)) return;
+        after_move(false);
     }
 };
 
@@ -871,6 +949,72 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_rou
     if (lane == 0) order_next(p, parity, warp, t.st.status == ST_PLAYING && t.st.traversals >= p.sims);
 }
 
+// ---- match play (Evaluate.cpp:93-157, evaluate/play.hpp:24-69): one warp per PAIR of trees ----
+// The side to move searches in its own tree with its own evaluator; when its budget is spent it plays the
+// most-visited action and both trees advance.  Game-level state (stream id and draw counter, move count, game
+// index, status) is handed from one tree's record to the other's at every move; pair g's "side to move" lives in
+// trees[g].pad.  Network k of game t plays Player (k ^ (t & 1)) (Evaluate.cpp:129-133).
+template <class G>
+__global__ void __launch_bounds__(32) k_match_begin(EngineParams p, MatchParams m) {
+    __shared__ WarpScratch scratch;
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    if (pair >= m.n_pairs) return;
+    unsigned long long game_id = 0;
+    for (int k = 0; k < 2; ++k) {
+        TreeWarp<G, true> t(p, k * m.n_pairs + pair, lane, scratch, &m.agent[k], m.n_pairs);
+        t.st.game_index = pair;
+        t.st.n_queued = 0;
+        if (t.st.game_index < p.num_games) { t.st.status = ST_PLAYING; t.init_game(); }
+        else t.st.status = ST_DONE;
+        game_id = t.st.game_id;
+        t.save();
+    }
+    __syncwarp();
+    if (lane == 0) p.trees[pair].pad = (u32)(game_id & 1ULL);     // Player ZERO moves first
+}
+
+template <class G>
+__global__ void __launch_bounds__(32) k_match_round(EngineParams p, MatchParams m) {
+    __shared__ WarpScratch scratch;
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    if (pair >= m.n_pairs) return;
+    if (p.trees[pair].status != ST_PLAYING) return;
+    const int active = (int)p.trees[pair].pad;
+    int action = -1, status, move_count;
+    unsigned long long game_id, rng_ctr;
+    long long game_index;
+    {
+        TreeWarp<G, true> t(p, active * m.n_pairs + pair, lane, scratch, &m.agent[active], m.n_pairs);
+        for (int iter = 0; iter < p.rounds_per_launch; ++iter) {
+            if (t.st.n_queued > 0) t.apply_leaves();
+            if (t.st.traversals >= p.sims) { action = t.finalize_match_move(); break; }
+            t.search_batch();
+            if (t.st.status != ST_PLAYING) break;
+            if (t.cfg_evaluator() == SPRL_EVAL_EXTERNAL) break;
+        }
+        status = t.st.status; move_count = t.st.move_count; game_id = t.st.game_id; rng_ctr = t.rng.ctr;
+        game_index = t.st.game_index;
+        t.save();
+    }
+    if (action >= 0) {
+        TreeWarp<G, true> o(p, (active ^ 1) * m.n_pairs + pair, lane, scratch, &m.agent[active ^ 1], m.n_pairs);
+        o.follow_move(action);                      // same position: same terminal test, same next game
+        if (o.st.status == ST_ERR_CAPACITY) status = ST_ERR_CAPACITY;
+        else { o.st.status = status; o.st.move_count = move_count; o.st.game_id = game_id; o.rng.game = game_id; o.rng.ctr = rng_ctr; o.st.game_index = game_index; }
+        o.save();
+        __syncwarp();
+        if (status == ST_PLAYING && lane == 0) {
+            const u32 player = META_PLAYER(*HL<G::W>::meta_ptr(o.slab + ROOT_UNIT));
+            p.trees[pair].pad = player ^ (u32)(game_id & 1ULL);
+        }
+    }
+    if (status != ST_PLAYING && lane == 0) {
+        p.trees[pair].status = status;
+        p.trees[m.n_pairs + pair].status = status;
+        atomicAdd(&p.counters[status == ST_DONE ? 0 : 1], 1ULL);
+    }
+}
+
 // ---- sample writer: selfPlay's symmetrised samples (selfplay/SelfPlay.hpp:86-96,127-136,
 //      148-189) embedded as in runWorker (selfplay/GridWorker.hpp:146-196) ----
 // One block per recorded move; writes S consecutive rows of states / distributions / outcomes.
@@ -923,6 +1067,13 @@ template <class G> static void launch_emit(const EngineParams& p, const long lon
     k_emit<G><<<(unsigned)(p.num_games * p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
 }
 
+template <class G> static void launch_match_begin(const EngineParams& p, const MatchParams& m, cudaStream_t s) {
+    k_match_begin<G><<<m.n_pairs, 32, 0, s>>>(p, m);
+}
+template <class G> static void launch_match_round(const EngineParams& p, const MatchParams& m, cudaStream_t s) {
+    k_match_round<G><<<m.n_pairs, 32, 0, s>>>(p, m);
+}
+
 #define GAME_SWITCH(game, STMT)                                   \
     switch (game) {                                               \
     case SPRL_GAME_OTHELLO: { typedef Othello G; STMT; break; }   \
@@ -936,6 +1087,8 @@ void search_launch_begin(int game, const EngineParams& p, cudaStream_t s) { GAME
 void search_launch_round(int game, const EngineParams& p, cudaStream_t s) { GAME_SWITCH(game, launch_round<G>(p, s)); }
 void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
                         cudaStream_t s) { GAME_SWITCH(game, launch_emit<G>(p, row0, S, st, di, ou, s)); }
+void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_begin<G>(p, m, s)); }
+void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_round<G>(p, m, s)); }
 int search_header_units(int game) { return (game == SPRL_GAME_GO9) ? 5 : 3; }
 
 }  // namespace sprl

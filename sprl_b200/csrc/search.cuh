@@ -114,4 +114,15 @@ struct EngineParams {
     u32 cq_cap;
 };
 
+// Match play (Evaluate.cpp:93-157): a game is served by a PAIR of trees, one per side; tree
+// k * n_pairs + g belongs to agent k of pair g, so that the evaluator rows of one network are contiguous.
+struct AgentCfg {
+    int evaluator, use_sym, init_q, pad;
+    unsigned long long hash_salt;
+};
+struct MatchParams {
+    AgentCfg agent[2];
+    int n_pairs;
+};
+
 }  // namespace sprl

@@ -89,6 +89,7 @@ class Engine:
         capi.check(self.lib.sprl_create(C.byref(self.cfg), C.byref(self.handle)))
         self.samples_per_move = self.gi.nsym if self.cfg.use_sym else 1
         self._nn = None
+        self._match_running = False
 
     def close(self):
         if self.handle:
@@ -160,9 +161,34 @@ class Engine:
         self.attach_network(None, use_cuda_graph)
         self._nn["evalnet"] = evalnet
 
+    def attach_match_evaluators(self, evaluators, use_cuda_graph=True):
+        """Match play with networks: evaluators[k] serves agent k's trees = rows [k*half, (k+1)*half) of the
+        evaluator batch, half = (num_slots // 2) * max_queue.  An entry is an EvalNet, a traced module, or None
+        (that agent uses a device evaluator)."""
+        self.attach_network(None, use_cuda_graph)
+        self._nn["match_evaluators"] = list(evaluators)
+
+    def _forward_rows(self, ev, lo, n):
+        nn = self._nn
+        torch = nn["torch"]
+        if hasattr(ev, "forward_ptr"):
+            ev.forward_ptr(nn["inp"][lo:].data_ptr(), n, nn["logits"][lo:].data_ptr(), nn["value"][lo:].data_ptr(),
+                           torch.cuda.current_stream(nn["dev"]).cuda_stream)
+        else:
+            with torch.no_grad():
+                logits, value = ev(nn["inp"][lo:lo + n])
+                nn["logits"][lo:lo + n].copy_(logits)
+                nn["value"][lo:lo + n].copy_(value.reshape(-1))
+
     def _forward(self):
         nn = self._nn
         torch = nn["torch"]
+        if self._match_running and nn.get("match_evaluators") is not None:
+            half = (self.cfg.num_slots // 2) * self.cfg.max_queue
+            for k, ev in enumerate(nn["match_evaluators"]):
+                if ev is not None:
+                    self._forward_rows(ev, k * half, half)
+            return
         if nn.get("evalnet") is not None:
             nn["evalnet"].forward_ptr(nn["inp"].data_ptr(), nn["inp"].shape[0], nn["logits"].data_ptr(),
                                       nn["value"].data_ptr(), torch.cuda.current_stream(nn["dev"]).cuda_stream)
@@ -176,7 +202,7 @@ class Engine:
         self.round()
         self._forward()
 
-    def _capture(self):
+    def _capture(self, key="graph"):
         """Captures [search launch -> network forward -> output copy] as one CUDA graph."""
         nn = self._nn
         torch = nn["torch"]
@@ -192,7 +218,7 @@ class Engine:
             self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
             self._round_with_network()
         self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
-        nn["graph"] = graph
+        nn[key] = graph
 
     # -- runIteration -------------------------------------------------------------------
     def run_iteration(self, num_games, first_game=0, collect=True, poll_every=None):
@@ -224,6 +250,58 @@ class Engine:
         else:
             capi.check(self.lib.sprl_run_iteration(self.handle, first_game, num_games, None, None))
         return self.collect_samples() if collect else None
+
+    # -- match play (Evaluate.cpp) ----------------------------------------------------------
+    def run_match(self, agents, num_games, first_game=0, poll_every=None):
+        """Plays a match of `num_games` games between two agents on num_slots // 2 concurrent pairs of trees.
+        agents: two dicts with evaluator (capi.EVAL_*), use_sym, init_q and, for HashNet, hash_salt; agents with
+        EVAL_EXTERNAL take their network from attach_match_evaluators().  Returns winner / moves / rng draws per
+        game and the tally (wins of agent 0, wins of agent 1, draws) as Evaluate.cpp counts it."""
+        cfgs = (capi.AgentConfig * 2)()
+        for k, ag in enumerate(agents):
+            cfgs[k] = capi.AgentConfig(evaluator=ag["evaluator"], use_sym=int(ag.get("use_sym", 1)),
+                                       init_q=ag.get("init_q", capi.INITQ_PARENT), hash_salt=ag.get("hash_salt", 0))
+        external = any(ag["evaluator"] == capi.EVAL_EXTERNAL for ag in agents)
+        self._match_running = True
+        try:
+            if external:
+                nn = self._nn
+                if nn is None or nn.get("match_evaluators") is None:
+                    raise capi.SprlError(capi.SPRL_E_STATE, "attach_match_evaluators() first")
+                torch = nn["torch"]
+                with torch.cuda.device(nn["dev"]):
+                    self.set_stream(torch.cuda.current_stream(nn["dev"]).cuda_stream)
+                    capi.check(self.lib.sprl_match_begin(self.handle, cfgs, first_game, num_games))
+                    if nn["use_graph"] and nn.get("graph_match") is None:
+                        self._capture("graph_match")
+                    self._poll_loop(nn.get("graph_match"), poll_every or 64, True)
+            else:
+                capi.check(self.lib.sprl_match_begin(self.handle, cfgs, first_game, num_games))
+                self._poll_loop(None, poll_every or 8, False)
+        finally:
+            self._match_running = False
+        winner = np.zeros(num_games, np.int8)
+        moves = np.zeros(num_games, np.int32)
+        draws = np.zeros(num_games, np.uint64)
+        wins = (C.c_int64 * 2)()
+        ties = C.c_int64()
+        capi.check(self.lib.sprl_match_results(self.handle, num_games, _ptr(winner), _ptr(moves), _ptr(draws), wins, C.byref(ties)))
+        return dict(game_winner=winner, game_moves=moves, game_rng_draws=draws, wins=(wins[0], wins[1]), draws=ties.value)
+
+    def _poll_loop(self, graph, every, forward):
+        while True:
+            for _ in range(every):
+                if graph is not None:
+                    graph.replay()
+                elif forward:
+                    self._round_with_network()
+                else:
+                    self.round()
+            playing, failed = self.poll()
+            if failed:
+                self._raise_slot_failure()
+            if playing == 0:
+                return
 
     def _raise_slot_failure(self):
         # run_iteration's C path formats the message; reuse it through a zero-round call

@@ -14,8 +14,12 @@ from sprl_b200 import selfplay as SP
 pytestmark = pytest.mark.gpu
 
 GAMES = {"othello": capi.GAME_OTHELLO, "c4": capi.GAME_C4, "go": capi.GAME_GO7}
-EVALS = {"hash": capi.EVAL_HASHNET, "uniform": capi.EVAL_UNIFORM}
-INITQ = {"parent": capi.INITQ_PARENT, "zero": capi.INITQ_ZERO}
+EVALS = {"hash": capi.EVAL_HASHNET, "hash1": capi.EVAL_HASHNET, "uniform": capi.EVAL_UNIFORM,
+         "heuristic": capi.EVAL_OTHELLO_HEURISTIC}
+INITQ = {"parent": capi.INITQ_PARENT, "zero": capi.INITQ_ZERO, "drop": capi.INITQ_DROP_PARENT}
+O_EVALS = {capi.EVAL_HASHNET: O.OE_HASHNET, capi.EVAL_UNIFORM: O.OE_UNIFORM, capi.EVAL_OTHELLO_HEURISTIC: O.OE_HEURISTIC}
+MATCH_KEYS = ["game_moves", "game_winner", "game_rng_draws", "move_N", "move_W", "move_P", "move_root_N", "move_root_W",
+              "move_action", "move_traversals", "move_player"]
 
 EXACT_KEYS = ["game_moves", "game_rng_draws", "move_N", "move_W", "move_P", "move_root_N", "move_root_W",
               "move_action", "move_traversals", "move_player", "states", "outcomes"]
@@ -285,3 +289,72 @@ def test_device_resident_samples_alias_the_host_copy():
         assert np.array_equal(do.cpu().numpy(), outcomes)
         loss = (dd * torch.log(dd.clamp_min(1e-9))).sum()          # usable by torch without a copy
         assert torch.isfinite(loss)
+
+
+# ------------------------------------------------------- next rows: DROP_PARENT, OthelloHeuristic, match play
+@pytest.mark.parametrize("game,ev,initq,sims,b,q,alpha,ngames,slots", [
+    (capi.GAME_OTHELLO, capi.EVAL_HASHNET, "drop", 200, 8, 4, 0.3, 12, 5),
+    (capi.GAME_OTHELLO, capi.EVAL_OTHELLO_HEURISTIC, "parent", 120, 8, 4, 0.3, 10, 10),
+    (capi.GAME_OTHELLO, capi.EVAL_OTHELLO_HEURISTIC, "drop", 64, 4, 2, 0.3, 6, 3),
+    (capi.GAME_C4, capi.EVAL_HASHNET, "drop", 256, 8, 4, 0.5, 12, 12),
+    (capi.GAME_GO7, capi.EVAL_HASHNET, "drop", 80, 16, 8, 0.2, 4, 4),
+])
+def test_drop_parent_and_heuristic_vs_oracle(game, ev, initq, sims, b, q, alpha, ngames, slots):
+    """InitQ::DROP_PARENT (uct/UCTNode.hpp:152-163,196-206) and networks/OthelloHeuristic.cpp on the device."""
+    seed, first = 99, 20
+    oq = {"drop": O.OQ_DROP_PARENT, "parent": O.OQ_PARENT}[initq]
+    ref = O.selfplay(game, O_EVALS[ev], seed, first, ngames, sims, b, q, 0.25, alpha, init_q=oq, max_moves_per_game=170)
+    got = run_engine(game, ev, seed, first, ngames, sims, b, q, 0.25, alpha, 1, 1, INITQ[initq], num_slots=slots)
+    compare_selfplay(ref, got)
+
+
+def test_heuristic_is_othello_only():
+    with pytest.raises(capi.SprlError):
+        SP.Engine(capi.GAME_C4, capi.EVAL_OTHELLO_HEURISTIC, num_slots=2)
+
+
+def run_match(game, agents, seed, first_game, ngames, sims, b, q, pairs=None):
+    """Match play through the C ABI with Evaluate.cpp's constants (noise on, eps 0.25, alpha 0.1, uWeight 1.0)."""
+    pairs = pairs or ngames
+    with SP.Engine(game, capi.EVAL_UNIFORM, seed=seed, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.1,
+                   u_weight=1.0, add_noise=1, num_slots=2 * pairs, max_games=ngames, record_stats=1) as eng:
+        got = eng.run_match(agents, ngames, first_game=first_game)
+        got.update(eng.move_stats(ngames))
+    return got
+
+
+def gpu_agents(cmd):
+    return [dict(evaluator=EVALS[cmd["evaluators"][k]], hash_salt=G.HASH_SALT.get(cmd["evaluators"][k], 0),
+                 use_sym=cmd["sym"][k], init_q=INITQ[cmd["initq"][k]]) for k in range(2)]
+
+
+@pytest.mark.parametrize("name", G.MATCH_FIXTURES)
+def test_match_golden(name):
+    """Evaluate.cpp's match path against the verbatim reference: every root statistic, action and winner."""
+    cmd, ref = G.load("match_" + name)
+    got = run_match(GAMES[cmd["game"]], gpu_agents(cmd), cmd["seed"], cmd["first_game"], cmd["ngames"], cmd["sims"],
+                    cmd["max_batch"], cmd["max_queue"])
+    ref = dict(ref, game_winner=ref["game_winner"].astype(np.int8))
+    G.assert_trace_equal(ref, got, MATCH_KEYS)
+
+
+@pytest.mark.parametrize("game,evs,syms,qs,sims,b,q,ngames,pairs", [
+    (capi.GAME_OTHELLO, ("hash", "hash1"), (1, 1), ("parent", "zero"), 100, 8, 4, 16, 5),     # pairs reused by several games
+    (capi.GAME_OTHELLO, ("heuristic", "hash"), (1, 0), ("drop", "parent"), 60, 8, 4, 8, 8),
+    (capi.GAME_C4, ("hash", "uniform"), (1, 1), ("parent", "parent"), 128, 8, 4, 24, 24),
+    (capi.GAME_GO7, ("hash", "hash1"), (1, 1), ("parent", "parent"), 48, 16, 8, 3, 3),
+    (capi.GAME_GO9, ("hash1", "hash"), (0, 1), ("zero", "parent"), 32, 16, 8, 2, 1),
+])
+def test_match_vs_oracle(game, evs, syms, qs, sims, b, q, ngames, pairs):
+    seed, first = 7, 11                                   # odd first game: agent 1 opens game 0
+    oq = {"drop": O.OQ_DROP_PARENT, "parent": O.OQ_PARENT, "zero": O.OQ_ZERO}
+    o_agents = [dict(evaluator=O_EVALS[EVALS[evs[k]]], hash_salt=G.HASH_SALT.get(evs[k], 0), use_sym=syms[k], init_q=oq[qs[k]])
+                for k in range(2)]
+    g_agents = [dict(evaluator=EVALS[evs[k]], hash_salt=G.HASH_SALT.get(evs[k], 0), use_sym=syms[k], init_q=INITQ[qs[k]])
+                for k in range(2)]
+    ref = O.match(game, o_agents, seed, first, ngames, sims, b, q, max_moves_per_game=170)
+    got = run_match(game, g_agents, seed, first, ngames, sims, b, q, pairs=pairs)
+    ref["game_winner"] = ref["game_winner"].astype(np.int8)
+    G.assert_trace_equal(ref, got, MATCH_KEYS)
+    assert got["wins"] == ref["wins"] and got["draws"] == ref["draws"]
+    assert got["wins"][0] + got["wins"][1] + got["draws"] == ngames
