@@ -193,6 +193,12 @@ typedef struct {
 /* Starts a match of games first_game .. (stride as in self-play); then sprl_round / sprl_poll as usual. */
 int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents /* [2] */, uint64_t first_game, int64_t num_games);
 
+/* begin + rounds until every game is finished.  With SPRL_EVAL_EXTERNAL agents `forward` is called once per round
+ * for the WHOLE batch; it runs agent 0's network on rows [0, half) and agent 1's on [half, 2*half),
+ * half = (num_slots / 2) * max_queue (skipping a side that uses a device evaluator). */
+int sprl_run_match(sprl_engine* e, const sprl_agent_config* h_agents /* [2] */, uint64_t first_game, int64_t num_games,
+                   sprl_forward_fn forward, void* user);
+
 /* Results of the finished match: per game the winner (-1 none / 0 / 1 = Player), moves played and RNG draws used
  * (any of them may be NULL); wins[2] = games won by agent 0 / agent 1, draws (Evaluate.cpp:139-155). */
 int sprl_match_results(sprl_engine* e, int64_t cap_games, int8_t* h_winner, int32_t* h_moves, uint64_t* h_draws,

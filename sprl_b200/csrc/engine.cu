@@ -377,29 +377,44 @@ static int report_slot_failure(sprl_engine* e) {
     return fail(SPRL_E_STATE, "a slot failed for an unknown reason");
 }
 
-int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, sprl_forward_fn forward, void* user) {
-    ENGINE_CHECK(e);
-    if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
-    int rc = sprl_begin_iteration(e, first_game, num_games);
-    if (rc) return rc;
-    const int check_every = (e->cfg.evaluator == SPRL_EVAL_EXTERNAL) ? 64 : 4;
+static int run_rounds(sprl_engine* e, bool external, sprl_forward_fn forward, void* user) {
+    const int check_every = external ? 64 : 4;
     for (;;) {
         for (int i = 0; i < check_every; ++i) {
-            rc = sprl_round(e);
+            int rc = sprl_round(e);
             if (rc) return rc;
-            if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL) {
+            if (external) {
                 rc = forward(user, e->p.nn_in, sprl_eval_batch(e), const_cast<float*>(e->p.nn_logits),
                              const_cast<float*>(e->p.nn_value), (void*)e->stream);
                 if (rc) return fail(SPRL_E_STATE, "forward callback returned %d", rc);
             }
         }
         int64_t playing = 0, failed = 0;
-        rc = sprl_poll(e, &playing, &failed);
+        int rc = sprl_poll(e, &playing, &failed);
         if (rc) return rc;
         if (failed > 0) return report_slot_failure(e);
         if (playing == 0) break;
     }
     return SPRL_OK;
+}
+
+int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, sprl_forward_fn forward, void* user) {
+    ENGINE_CHECK(e);
+    if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
+    int rc = sprl_begin_iteration(e, first_game, num_games);
+    if (rc) return rc;
+    return run_rounds(e, e->cfg.evaluator == SPRL_EVAL_EXTERNAL, forward, user);
+}
+
+int sprl_run_match(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t first_game, int64_t num_games,
+                   sprl_forward_fn forward, void* user) {
+    ENGINE_CHECK(e);
+    if (!h_agents) return fail(SPRL_E_INVALID, "null agents");
+    const bool external = h_agents[0].evaluator == SPRL_EVAL_EXTERNAL || h_agents[1].evaluator == SPRL_EVAL_EXTERNAL;
+    if (external && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
+    int rc = sprl_match_begin(e, h_agents, first_game, num_games);
+    if (rc) return rc;
+    return run_rounds(e, external, forward, user);
 }
 
 static int load_game_moves(sprl_engine* e, int64_t* n_moves) {

@@ -3,7 +3,7 @@
 // constructor (a TorchScript path, or "random" to load nothing).  The reference moves the
 // module to torch::kCPU and fills a host tensor element by element (:70-97); here the module
 // lives on the engine's GPU and is run directly on the leaf-batch buffer the search kernel
-// wrote (no copy, no host round trip).  For 8x8 boards the forward pass itself is the library's
+// wrote (no copy, no host round trip).  For boards up to 8x8 the forward pass itself is the library's
 // tcgen05 kernel (sprl_evalnet_*, csrc/evalnet.cu) fed with the module's parameters; other
 // boards, or SPRL_EVALUATOR=libtorch, run the TorchScript module through LibTorch/cuDNN.
 // exp / mask / normalise of the outputs (:107-142) happen in the next search launch, on the device.
@@ -39,8 +39,8 @@ public:
 
     int evaluatorKind() const override { return SPRL_EVAL_EXTERNAL; }
 
-    int prepare(int device, int64_t batch, int planes, int rows, int cols, int actions,
-                float** d_in, float** d_logits, float** d_value) override {
+    // Moves the module to the engine's GPU and picks the forward implementation.
+    int attach(int device, int planes, int rows, int cols, int actions) override {
         if (!m_model) return -1;
         m_device = torch::Device(torch::kCUDA, (c10::DeviceIndex)device);
         m_model->to(m_device);
@@ -48,6 +48,15 @@ public:
         // the reference's worker evaluates in fp32; keep cuDNN / cuBLAS off TF32
         at::globalContext().setAllowTF32CuDNN(false);
         at::globalContext().setAllowTF32CuBLAS(false);
+        m_planes = planes; m_rows = rows; m_cols = cols; m_actions = actions;
+        const char* ev = std::getenv("SPRL_EVALUATOR");
+        if (!m_evalnet && !(ev && std::strcmp(ev, "libtorch") == 0)) createEvalnet(device, planes, rows, cols, actions);
+        return 0;
+    }
+
+    int prepare(int device, int64_t batch, int planes, int rows, int cols, int actions,
+                float** d_in, float** d_logits, float** d_value) override {
+        if (attach(device, planes, rows, cols, actions) != 0) return -1;
         auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(m_device);
         m_input = torch::zeros({ batch, planes, rows, cols }, opts);
         m_logits = torch::zeros({ batch, actions }, opts);
@@ -55,22 +64,26 @@ public:
         *d_in = m_input.data_ptr<float>();
         *d_logits = m_logits.data_ptr<float>();
         *d_value = m_value.data_ptr<float>();
-        const char* ev = std::getenv("SPRL_EVALUATOR");
-        if (!(ev && std::strcmp(ev, "libtorch") == 0)) createEvalnet(device, planes, rows, cols, actions);
         return 0;
     }
 
     ~GridNetwork() { if (m_evalnet) sprl_evalnet_destroy(m_evalnet); }
 
+    // d_in / d_logits / d_value may be any rows of a leaf-batch buffer on this GPU (a match gives each network
+    // its half of one buffer).
     int forward(const float* d_in, int64_t batch, float* d_logits, float* d_value, void* stream) override {
         if (m_evalnet) return sprl_evalnet_forward(m_evalnet, d_in, batch, d_logits, d_value, stream);
-        if (d_in != m_input.data_ptr<float>() || d_logits != m_logits.data_ptr<float>() || d_value != m_value.data_ptr<float>()) return -2;
+        if (!m_model || m_planes == 0) return -2;
         torch::NoGradGuard no_grad;
         c10::cuda::CUDAStream s = c10::cuda::getStreamFromExternal((cudaStream_t)stream, m_device.index());
         c10::cuda::CUDAStreamGuard guard(s);
-        auto output = m_model->forward({ m_input }).toTuple();
-        m_logits.copy_(output->elements()[0].toTensor());
-        m_value.copy_(output->elements()[1].toTensor().reshape({ -1 }));
+        auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(m_device);
+        torch::Tensor in = torch::from_blob(const_cast<float*>(d_in), { batch, m_planes, m_rows, m_cols }, opts);
+        torch::Tensor logits = torch::from_blob(d_logits, { batch, m_actions }, opts);
+        torch::Tensor value = torch::from_blob(d_value, { batch }, opts);
+        auto output = m_model->forward({ in }).toTuple();
+        logits.copy_(output->elements()[0].toTensor());
+        value.copy_(output->elements()[1].toTensor().reshape({ -1 }));
         return 0;
     }
 
@@ -118,6 +131,7 @@ private:
     torch::Device m_device { torch::kCPU };
     std::shared_ptr<torch::jit::script::Module> m_model;
     torch::Tensor m_input, m_logits, m_value;
+    int m_planes { 0 }, m_rows { 0 }, m_cols { 0 }, m_actions { 0 };
 };
 
 }  // namespace SPRL

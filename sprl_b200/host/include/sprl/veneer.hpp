@@ -12,6 +12,8 @@
 //   SPRL::InitQ                                       uct/UCTNode.hpp:24-28
 //   SPRL::runIteration<Impl,State,A>(...)             selfplay/SelfPlay.hpp:203-208
 //   SPRL::waitModelPath, SPRL::runWorker<NN,Impl,R,C,H,A>(...)   selfplay/GridWorker.hpp:35-55,84-91
+//   SPRL::playMatch<Impl,State,A>(...)                the game loop of Evaluate.cpp:93-157 (UCTNetworkAgent::act /
+//                                                     opponentAct inside playGame), all games concurrently
 //
 // What changes underneath: runIteration plays all `numGames` games CONCURRENTLY on one GPU
 // (one warp per tree) instead of one after the other on a CPU core; the evaluator is a handle
@@ -85,6 +87,9 @@ public:
     // forward(): run the network on d_in and leave its outputs in d_logits / d_value, on `stream`.
     virtual int prepare(int /*device*/, int64_t /*batch*/, int /*planes*/, int /*rows*/, int /*cols*/, int /*actions*/,
                         float** /*d_in*/, float** /*d_logits*/, float** /*d_value*/) { return -1; }
+    // attach(): what prepare() does without owning the buffers (second network of a match: it reads and writes
+    // its half of the first network's buffers).
+    virtual int attach(int /*device*/, int /*planes*/, int /*rows*/, int /*cols*/, int /*actions*/) { return -1; }
     virtual int forward(const float*, int64_t, float*, float*, void* /*cudaStream_t*/) { return -1; }
     virtual int getNumEvals() { return (int)m_numEvals; }
     void addEvals(uint64_t n) { m_numEvals += n; }
@@ -151,6 +156,10 @@ struct DeviceOptions {
 };
 inline DeviceOptions& deviceOptions() { static DeviceOptions o; return o; }
 
+inline int initQCode(InitQ q) {
+    return q == InitQ::PARENT ? SPRL_INITQ_PARENT : (q == InitQ::DROP_PARENT ? SPRL_INITQ_DROP_PARENT : SPRL_INITQ_ZERO);
+}
+
 // ---- runIteration (selfplay/SelfPlay.hpp:203-248) --------------------------------------------
 // Returns the embedded samples: states [n, 2H+1, R, C], distributions [n, A], outcomes [n].
 template <typename ImplNode, typename State, int ACTION_SIZE>
@@ -159,7 +168,6 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
              int numTraversals, int maxBatchSize, int maxQueueSize,
              float dirEps, float dirAlpha, InitQ initQMethod,
              ISymmetrizer<State, ACTION_SIZE>* symmetrizer, bool addNoise = true) {
-    if (initQMethod == InitQ::DROP_PARENT) throw EngineError(SPRL_E_INVALID, "InitQ::DROP_PARENT is not selected by any reference caller and is not implemented");
     const DeviceOptions& opt = deviceOptions();
     sprl_config cfg;
     check(sprl_default_config(ImplNode::GAME, &cfg));
@@ -169,7 +177,7 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
     cfg.max_games = numGames;
     cfg.sims = numTraversals; cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
     cfg.dir_eps = dirEps; cfg.dir_alpha = dirAlpha;
-    cfg.init_q = (initQMethod == InitQ::PARENT) ? SPRL_INITQ_PARENT : SPRL_INITQ_ZERO;
+    cfg.init_q = initQCode(initQMethod);
     cfg.add_noise = addNoise ? 1 : 0;
     cfg.use_sym = symmetrizer != nullptr ? 1 : 0;
     sprl_engine* e = nullptr;
@@ -205,6 +213,76 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
     network->addEvals(st.evals);
     std::cout << numGames << " games played, " << nSamples << " states collected.\n";
     return { std::move(states), std::move(dists), std::move(outcomes) };
+}
+
+// ---- playMatch: the loop of Evaluate.cpp:93-157 ------------------------------------------------
+// `numGames` games between two networks, each side with its own tree, symmetrizer and init-Q; game t gives
+// Player ZERO to network t % 2; the side to move searches numTraversals descents and plays its most-visited
+// action (agents/UCTNetworkAgent.hpp:45-105), the other tree follows (opponentAct, :107-109).  Trees are built as
+// Evaluate.cpp builds them: Dirichlet noise on, eps 0.25, alpha 0.1, default uWeight 1.0.
+struct MatchResult { int64_t wins0, wins1, draws; std::vector<int8_t> winners; std::vector<int32_t> moves; };
+
+template <typename ImplNode, typename State, int ACTION_SIZE>
+MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACTION_SIZE>* network1, int numGames,
+                      int numTraversals, int maxBatchSize, int maxQueueSize,
+                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer0, InitQ initQ0,
+                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer1, InitQ initQ1) {
+    const DeviceOptions& opt = deviceOptions();
+    INetwork<State, ACTION_SIZE>* nets[2] = { network0, network1 };
+    sprl_agent_config agents[2] = {
+        { network0->evaluatorKind(), symmetrizer0 != nullptr ? 1 : 0, initQCode(initQ0), 0 },
+        { network1->evaluatorKind(), symmetrizer1 != nullptr ? 1 : 0, initQCode(initQ1), 0 } };
+    const bool external = agents[0].evaluator == SPRL_EVAL_EXTERNAL || agents[1].evaluator == SPRL_EVAL_EXTERNAL;
+    sprl_config cfg;
+    check(sprl_default_config(ImplNode::GAME, &cfg));
+    cfg.device = opt.device; cfg.seed = opt.seed;
+    cfg.evaluator = external ? SPRL_EVAL_EXTERNAL : SPRL_EVAL_UNIFORM;
+    const int pairs = opt.numSlots > 0 ? std::min(opt.numSlots, numGames) : numGames;
+    cfg.num_slots = 2 * pairs;
+    cfg.max_games = numGames;
+    cfg.sims = numTraversals; cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
+    cfg.dir_eps = 0.25f; cfg.dir_alpha = 0.1f; cfg.u_weight = 1.0f; cfg.add_noise = 1;     // Evaluate.cpp:95-111
+    sprl_engine* e = nullptr;
+    check(sprl_create(&cfg, &e));
+    struct Guard { sprl_engine* e; ~Guard() { sprl_destroy(e); } } guard { e };
+    check(sprl_set_game_stride(e, opt.gameStride));
+    sprl_game_info gi;
+    check(sprl_game_info_get(ImplNode::GAME, &gi));
+
+    struct Ctx { INetwork<State, ACTION_SIZE>* net[2]; int64_t half, rowIn, rowLogits; } ctx { { nullptr, nullptr }, 0, 0, 0 };
+    ctx.half = (int64_t)pairs * maxQueueSize;
+    ctx.rowIn = (int64_t)(2 * gi.history + 1) * gi.cells;
+    ctx.rowLogits = gi.actions;
+    if (external) {
+        // the first external network owns the buffers of the whole batch; each network serves its own half
+        float *d_in = nullptr, *d_logits = nullptr, *d_value = nullptr;
+        const int owner = agents[0].evaluator == SPRL_EVAL_EXTERNAL ? 0 : 1;
+        if (nets[owner]->prepare(cfg.device, sprl_eval_batch(e), 2 * gi.history + 1, gi.rows, gi.cols, gi.actions, &d_in, &d_logits, &d_value) != 0)
+            throw EngineError(SPRL_E_STATE, "network could not allocate its device buffers");
+        ctx.net[owner] = nets[owner];
+        if (owner == 0 && agents[1].evaluator == SPRL_EVAL_EXTERNAL) {
+            if (nets[1] != nets[0] && nets[1]->attach(cfg.device, 2 * gi.history + 1, gi.rows, gi.cols, gi.actions) != 0)
+                throw EngineError(SPRL_E_STATE, "second network could not be attached to the device");
+            ctx.net[1] = nets[1];
+        }
+        check(sprl_bind_eval_buffers(e, d_in, d_logits, d_value));
+    }
+    sprl_forward_fn fwd = [](void* user, const float* in, int64_t, float* logits, float* value, void* stream) -> int {
+        Ctx* c = static_cast<Ctx*>(user);
+        for (int k = 0; k < 2; ++k) {
+            if (!c->net[k]) continue;
+            int rc = c->net[k]->forward(in + k * c->half * c->rowIn, c->half, logits + k * c->half * c->rowLogits,
+                                        value + k * c->half, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    };
+    check(sprl_run_match(e, agents, opt.firstGame, numGames, external ? fwd : nullptr, &ctx));
+    MatchResult r { 0, 0, 0, std::vector<int8_t>((size_t)numGames), std::vector<int32_t>((size_t)numGames) };
+    int64_t wins[2] = { 0, 0 };
+    check(sprl_match_results(e, numGames, r.winners.data(), r.moves.data(), nullptr, wins, &r.draws));
+    r.wins0 = wins[0]; r.wins1 = wins[1];
+    return r;
 }
 
 // ---- waitModelPath / runWorker (selfplay/GridWorker.hpp:35-55,84-198) ------------------------

@@ -276,8 +276,7 @@ class Engine:
                         self._capture("graph_match")
                     self._poll_loop(nn.get("graph_match"), poll_every or 64, True)
             else:
-                capi.check(self.lib.sprl_match_begin(self.handle, cfgs, first_game, num_games))
-                self._poll_loop(None, poll_every or 8, False)
+                capi.check(self.lib.sprl_run_match(self.handle, cfgs, first_game, num_games, None, None))
         finally:
             self._match_running = False
         winner = np.zeros(num_games, np.int8)

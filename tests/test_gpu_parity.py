@@ -358,3 +358,34 @@ def test_match_vs_oracle(game, evs, syms, qs, sims, b, q, ngames, pairs):
     G.assert_trace_equal(ref, got, MATCH_KEYS)
     assert got["wins"] == ref["wins"] and got["draws"] == ref["draws"]
     assert got["wins"][0] + got["wins"][1] + got["draws"] == ngames
+
+
+@pytest.mark.parametrize("game,sims,b,q,ngames,pairs,graph,second", [
+    (capi.GAME_OTHELLO, 64, 8, 4, 6, 3, False, "net"),
+    (capi.GAME_OTHELLO, 48, 8, 4, 4, 4, True, "net"),          # round + both forwards replayed as one CUDA graph
+    (capi.GAME_C4, 80, 8, 4, 8, 8, False, "uniform"),          # a network against the uniform evaluator
+])
+def test_match_external_evaluators_bit_exact(game, sims, b, q, ngames, pairs, graph, second):
+    """Two networks in one match: each reads its half of the leaf batch (planes written by the search kernel) and
+    writes its half of the logits / values; integer-exact networks, so the oracle's callbacks agree bit for bit."""
+    import torch
+    gi = capi.game_info(game)
+    nets = [IntegerNet(2 * gi.history + 1, gi.cells, gi.actions, seed=5 + k) for k in range(2)]
+    o_agents = [dict(evaluator=O.OE_CALLBACK, eval_fn=nets[0].numpy, use_sym=1, init_q=O.OQ_PARENT),
+                dict(evaluator=O.OE_CALLBACK, eval_fn=nets[1].numpy, use_sym=1, init_q=O.OQ_ZERO)]
+    g_agents = [dict(evaluator=capi.EVAL_EXTERNAL, use_sym=1, init_q=capi.INITQ_PARENT),
+                dict(evaluator=capi.EVAL_EXTERNAL, use_sym=1, init_q=capi.INITQ_ZERO)]
+    if second == "uniform":
+        o_agents[1] = dict(evaluator=O.OE_UNIFORM, use_sym=1, init_q=O.OQ_ZERO)
+        g_agents[1] = dict(evaluator=capi.EVAL_UNIFORM, use_sym=1, init_q=capi.INITQ_ZERO)
+    ref = O.match(game, o_agents, 3, 0, ngames, sims, b, q, max_moves_per_game=170)
+    dev = torch.device("cuda", 0)
+    with SP.Engine(game, capi.EVAL_EXTERNAL, seed=3, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.1,
+                   u_weight=1.0, add_noise=1, num_slots=2 * pairs, max_games=ngames, record_stats=1) as eng:
+        eng.attach_match_evaluators([nets[0].torch_fn(dev), nets[1].torch_fn(dev) if second == "net" else None],
+                                    use_cuda_graph=graph)
+        got = eng.run_match(g_agents, ngames)
+        got.update(eng.move_stats(ngames))
+    ref["game_winner"] = ref["game_winner"].astype(np.int8)
+    G.assert_trace_equal(ref, got, MATCH_KEYS)
+    assert got["wins"] == ref["wins"] and got["draws"] == ref["draws"]
