@@ -9,7 +9,7 @@ A *step* of our arm is `--rounds` search rounds of `--slots` concurrent games in
 continuous play (a slot starts its next game when one ends): every round is one
 search launch over all trees (select / expand / backup / re-root), one forward of the
 reference's network (same architecture and weights as the traced module; run by the
-library's tcgen05 kernel with fp32-level 3xTF32 arithmetic, or by LibTorch/cuDNN fp32
+library's tcgen05 kernel with fp32-level split-fp16 arithmetic, or by LibTorch/cuDNN fp32
 with --evaluator libtorch) on the leaf batch those trees produced, and the application
 of its outputs in the next launch.  `value` is MCTS simulations per second,
 whole job, from device counters over exactly K timed steps; moves/s etc. ride along.
@@ -278,16 +278,17 @@ def run_ours(args):
                     "frac": round(tf / tpeak, 5), "traffic": None, "peak_source": peak_src + " bf16 sustained",
                     "launch_ms": round(nn_ms, 4), "leaves_per_launch": batch_rows, "flop_per_leaf": NET_FLOP_PER_LEAF,
                     "note": "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
-                            "as TF32 MMAs (3xTF32 split), whose nominal dense peak is 1,100 TFLOP/s (B200_PROFILING.md)",
-                    "tf32_issued_tflops": round(3 * tf, 1), "tf32_nominal_peak_tflops": 1100.0,
-                    "tf32_issued_frac_of_nominal": round(3 * tf / 1100.0, 4), "share_of_round": round(nn_ms / (k_ms + nn_ms), 4)}
+                            "as fp16 MMAs (hi/lo split of both operands: hi*hi + hi*lo + lo*hi, fp32 accumulate) to keep fp32-level "
+                            "accuracy, so issued_frac is the tensor-pipe utilisation",
+                    "issued_tflops": round(3 * tf, 1), "issued_frac": round(3 * tf / tpeak, 4),
+                    "share_of_round": round(nn_ms / (k_ms + nn_ms), 4)}
     else:
         roofline = dict(roofline_search, network_forward_ms=round(nn_ms, 4))
     result = {
         "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(value, 1), "unit": "sims/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32 (tree statistics fp32; network 3xTF32 split on tcgen05, fp32 accumulate)" if evalnet is not None else "fp32",
+        "dtype": "fp32 (tree statistics fp32; network split-fp16 x3 on tcgen05, fp32 accumulate, max |dlogit| ~1e-7 vs fp64)" if evalnet is not None else "fp32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sims_per_move": SIMS, "max_batch": MAX_BATCH, "max_queue": MAX_QUEUE,
                    "slots_per_gpu": args.slots, "rounds_per_step": args.rounds, "network_params": n_params,

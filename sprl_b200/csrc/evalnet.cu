@@ -9,11 +9,14 @@
 // reads them.
 //
 // Design (B200, sm_100a):
-//   * One CTA per SM, persistent over tiles of TWO boards, each on an 8x8 lattice (smaller boards
-//     leave lattice positions zero) = 128 cells = the M of one tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole tower on chip:
-//     activations never leave shared memory, fp32 accumulators live in TMEM.
+//   * TWO CTAs per SM (each with half of the shared memory and 256 of the 512 TMEM columns), persistent
+//     over tiles of TWO boards, each on an 8x8 lattice (smaller boards leave lattice positions zero)
+//     = 128 cells = the M of one tcgen05.mma (cta_group::1, M=128).  A tile goes through the whole
+//     tower on chip: activations never leave shared memory, fp32 accumulators live in TMEM.  Inside a
+//     CTA the MMAs of a layer and its epilogue are serial (the next layer needs the whole image); the
+//     second CTA fills the tensor pipe meanwhile, with no extra synchronisation.
 //   * Every 3x3 convolution is an implicit GEMM with NO im2col copy.  The activation image is
-//     kept in shared memory as [channel group of 4][storage row][8 cells][4 floats], the rows of
+//     kept in shared memory as [channel group of 8][storage row][8 cells][8 halfs], the rows of
 //     the two boards interleaved and two zero rows above and below, so that a board row is one
 //     128-byte, 128-byte-aligned UMMA core matrix (K-major, no swizzle: SBO = 128 B, LBO = one
 //     channel group) and the operand of a tap with vertical offset dy is the SAME image with
@@ -22,12 +25,20 @@
 //     128-byte lines, measured 2x slower operand fetch): the taps of each dx accumulate into
 //     their own TMEM accumulator Z_dx, and the epilogue forms out[c] = Z_-1[c-1] + Z_0[c] +
 //     Z_+1[c+1] with two warp shuffles per value (cells of a board row are adjacent lanes).
-//   * fp32 accuracy on the tensor cores by the 3xTF32 split: x = hi + lo with hi = tf32(x);
-//     D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate.  (The reference evaluates in
-//     fp32; a single TF32 pass would lose 13 mantissa bits, the split keeps ~21.)
+//   * fp32 accuracy on the tensor cores by a two-term FP16 split: x = hi + lo with hi = fp16(x),
+//     lo = fp16(x - hi); D = A_hi*W_hi + A_hi*W_lo + A_lo*W_hi, fp32 accumulate (products of fp16
+//     operands are exact in fp32).  fp16 carries the same 11 significant bits as TF32, so the
+//     split keeps ~22 bits like 3xTF32, but kind::f16 runs at twice the TF32 rate and K = 16 per
+//     instruction halves the operand bytes.  fp16's narrow exponent is handled by exact
+//     power-of-two scaling: activations are stored x 2^ACT_SHIFT (so their lo parts stay normal
+//     down to 2^-7 and below that the absolute error is < 2^-29), each layer's weights x 2^s with
+//     s chosen on the host so that max|W| lands in (2^9, 2^10], and the epilogue multiplies the
+//     accumulator by 2^-(ACT_SHIFT + s).  Activations above 65504 / 2^ACT_SHIFT = 4094 would
+//     overflow: they are clamped and reported (sprl_evalnet_status fails), never silently wrong.
+//     (The reference evaluates in fp32; a single fp16/TF32 pass would lose 13 mantissa bits.)
 //   * Weights (BN folded on the host in double, split hi/lo, pre-arranged as K-major UMMA
 //     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream
-//     from L2 through a ring of 16 KB units filled by cp.async.bulk (multicast to the CTAs of a
+//     from L2 through a ring of 24 KB units (32 input channels of one vertical offset) filled by cp.async.bulk (multicast to the CTAs of a
 //     cluster) + mbarrier complete_tx; tcgen05.commit frees a unit.
 //   * Warp roles: warps 0-7 = epilogue (TMEM -> registers -> shuffles/bias/residual/ReLU ->
 //     hi/lo -> activation image; two warps per TMEM lane quarter, half of the channels each),
@@ -38,6 +49,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sprl {
@@ -45,15 +58,19 @@ namespace evalnet {
 
 constexpr int TILE_M = 128;                  // cells per tile (two 8x8 boards)
 constexpr int CH = 64;                       // tower width
-constexpr int NCG = CH / 4;                  // channel groups of 4 floats (16 B)
+constexpr int KCH = 8;                       // channels per 16-byte group (8 halfs)
+constexpr int NCG = CH / KCH;                // channel groups
+constexpr int KSTEP_CH = 2 * KCH;            // input channels per MMA (kind::f16: K = 16)
+constexpr int ACT_SHIFT = 4;                 // activations are stored x 2^ACT_SHIFT in the fp16 images
+constexpr float ACT_SCALE = 16.0f, HALF_MAX = 65504.0f;
 constexpr int SLOTS = 160;                   // 20 storage rows x 8 cells
 constexpr int CG_STRIDE = SLOTS * 16;        // bytes per channel group of the image
-constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 40,960
+constexpr int IMG_BYTES = NCG * CG_STRIDE;   // 20,480
 #ifndef SPRL_EVALNET_UNIT_KSTEPS
-#define SPRL_EVALNET_UNIT_KSTEPS 4
+#define SPRL_EVALNET_UNIT_KSTEPS 2
 #endif
-constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (8 input channels each) per weight unit
-constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 4][3 dx x (hi, lo) x 64 rows][4 floats]: 48 KB
+constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (16 input channels each) per weight unit
+constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 8][3 dx x (hi, lo) x 64 rows][8 halfs]: 24 KB = 32 input channels of one dy
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
@@ -67,7 +84,11 @@ constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA war
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
 constexpr int TMEM_COLS = 256;               // [dx * 64 + channel] = Z_dx (all three split products); [192, 256) = residual
 constexpr int RES_COL = 3 * CH;              // the block input of the current residual block, fp32, one cell per lane
-constexpr int MAX_SMEM = 232448;             // 227 KB
+#ifndef SPRL_EVALNET_CTAS_PER_SM
+#define SPRL_EVALNET_CTAS_PER_SM 2
+#endif
+constexpr int CTAS_PER_SM = SPRL_EVALNET_CTAS_PER_SM;   // resident CTAs per SM (each owns 256 TMEM columns)
+constexpr int MAX_SMEM = (232448 - (CTAS_PER_SM - 1) * 1024) / CTAS_PER_SM;   // 227 KB per SM, 1 KB reserved per extra CTA
 
 // shared memory map (bytes); the ring, the biases and the barriers follow at run-time offsets
 constexpr int OFF_AHI = 0;
@@ -75,7 +96,7 @@ constexpr int OFF_ALO = OFF_AHI + IMG_BYTES;
 constexpr int OFF_RING = OFF_ALO + IMG_BYTES;                    // 81,920
 
 struct NetDev {
-    const float* wunits;     // packed weight units in consumption order, `replicas` copies back to back
+    const unsigned short* wunits;   // packed fp16 weight units in consumption order, `replicas` copies back to back
     long long wunits_bytes;  // bytes of one copy
     int replicas;
     const float* bias;       // [n_layers][64]
@@ -87,12 +108,13 @@ struct NetDev {
     int n_layers;            // 1 stem + 2*blocks + 1 heads
     int rows, cols;          // board (<= 8 x 8): cell (r, c) lives at lattice position (r, c) of an 8 x 8 tile half
     int in_planes;
-    int in_ksteps;           // ceil(in_planes / 8)
+    int in_ksteps;           // ceil(in_planes / 16)
     int actions;
     int policy_channels;     // 2
     int nst;                 // ring stages
     float* head_act;         // [batch][(policy_channels + 1) * 64]: ReLU'd 1x1-conv head activations, consumed by k_heads
-    unsigned long long* error_flag;
+    unsigned long long* error_flag;   // [0] pipeline barrier time-out, [1] an activation left the fp16-split range
+    float inv_scale[MAX_LAYERS];      // 2^-(ACT_SHIFT + weight shift of the layer): accumulator -> real units
     long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
     int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue
 };
@@ -150,9 +172,9 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if (elect_one()) {
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
@@ -205,24 +227,38 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* v, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
 }
-__device__ __forceinline__ float tf32_round(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// Eight real-unit values -> their fp16 hi and lo images (x 2^ACT_SHIFT), one 16-byte channel group each.
+// Values beyond the fp16 range are clamped and noted in `over`.
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, bool& over) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = x[2 * j] * ACT_SCALE, b = x[2 * j + 1] * ACT_SCALE;
+        over = over || fabsf(a) > HALF_MAX || fabsf(b) > HALF_MAX;
+        a = fminf(fmaxf(a, -HALF_MAX), HALF_MAX); b = fminf(fmaxf(b, -HALF_MAX), HALF_MAX);
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 // K-major, no swizzle: rows of a core matrix 16 B apart, 8-row groups SBO apart, K chunks (16 B) LBO apart
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ULL << 46);
 }
-__device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16: D = fp32 (bit 4), A and B = fp16 (format 0), both K-major
+__device__ __forceinline__ uint32_t instr_desc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Layer geometry shared by the producer, the MMA issuer and the host packer.
 // The three horizontal taps of a vertical offset dy read the SAME operand A (horizontal shifts are
 // applied to the outputs, see the header), so their weights are stacked along N: one weight unit
-// holds, for one dy and up to UNIT_KS k-steps, [K chunk of 4][rows][4 floats] with rows =
+// holds, for one dy and up to UNIT_KS k-steps, [K chunk of 8][rows][8 halfs] with rows =
 // W_hi(dx=-1) | W_hi(0) | W_hi(+1) | W_lo(-1) | W_lo(0) | W_lo(+1), n rows each.  Per k-step three
 // MMAs with N = 3n accumulate into the same columns [dx*n + channel]: A_hi*[W_hi x3], A_hi*[W_lo x3]
 // and A_lo*[W_hi x3] -- each 4 KB read of A feeds 192 output columns.  The 1x1 head convolution is
@@ -231,8 +267,8 @@ struct LayerGeom { int ndy, ndx, ksteps, n, units_per_dy; };
 __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
     LayerGeom g;
     if (layer == 0) { g.ndy = 3; g.ndx = 3; g.ksteps = in_ksteps; g.n = CH; }
-    else if (layer == n_layers - 1) { g.ndy = 1; g.ndx = 1; g.ksteps = CH / 8; g.n = HEAD_N; }
-    else { g.ndy = 3; g.ndx = 3; g.ksteps = CH / 8; g.n = CH; }
+    else if (layer == n_layers - 1) { g.ndy = 1; g.ndx = 1; g.ksteps = CH / KSTEP_CH; g.n = HEAD_N; }
+    else { g.ndy = 3; g.ndx = 3; g.ksteps = CH / KSTEP_CH; g.n = CH; }
     g.units_per_dy = (g.ksteps + UNIT_KS - 1) / UNIT_KS;
     return g;
 }
@@ -243,7 +279,7 @@ __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return un
 // two zero rows first
 __device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __restrict__ logits, float* __restrict__ value) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,7 +364,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                 { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
                 tc_fence_after();
                 const int n1 = g.ndx * g.n;                                      // output columns of one MMA
-                const uint32_t idesc = instr_desc_tf32(TILE_M, n1);
+                const uint32_t idesc = instr_desc_f16(TILE_M, n1);
                 const bool lo_pass = net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
                 const uint32_t b_lbo = (uint32_t)(2 * n1) * 16u, b_kstep = (2u * b_lbo) >> 4, b_lo_off = ((uint32_t)n1 * 16u) >> 4;
                 const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
@@ -351,16 +387,16 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                             if (nks == UNIT_KS) {
 #pragma unroll
                                 for (int ks = 0; ks < UNIT_KS; ++ks) {
-                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
-                                    if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
+                                    if (lo_pass) umma_f16(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
                             } else {
                                 for (int ks = 0; ks < nks; ++ks) {
-                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_tf32(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
-                                    if (lo_pass) umma_tf32(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
+                                    if (lo_pass) umma_f16(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
                             }
@@ -388,8 +424,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
         const int cell = r * net.cols + c;
         const bool has_left = c > 0, has_right = c + 1 < net.cols;
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        float4* a_hi = reinterpret_cast<float4*>(smem + OFF_AHI);
-        float4* a_lo = reinterpret_cast<float4*>(smem + OFF_ALO);
+        uint4* a_hi = reinterpret_cast<uint4*>(smem + OFF_AHI);
+        uint4* a_lo = reinterpret_cast<uint4*>(smem + OFF_ALO);
+        bool over = false;
         const int cells = net.rows * net.cols, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
@@ -397,15 +434,16 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
             const long long board = tile * 2 + b;
             // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split) ----
             for (int cg = half; cg < 2 * net.in_ksteps; cg += EPI_WARPS / 4) {
-                float v[4];
+                float v[KCH];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int p = cg * 4 + j;
+                for (int j = 0; j < KCH; ++j) {
+                    const int p = cg * KCH + j;
                     v[j] = (valid && p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
                 }
-                const float4 h = make_float4(tf32_round(v[0]), tf32_round(v[1]), tf32_round(v[2]), tf32_round(v[3]));
+                uint4 h, l;
+                split8(v, h, l, over);
                 a_hi[cg * SLOTS + slot] = h;
-                a_lo[cg * SLOTS + slot] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+                a_lo[cg * SLOTS + slot] = l;
             }
             proxy_fence();
             for (int layer = 0; layer < n_layers; ++layer) {
@@ -416,6 +454,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float* bias = s_bias + layer * CH;
+                const float inv_scale = net.inv_scale[layer];                // exact power of two
                 if (layer < n_layers - 1 && net.debug >= 5) {
                     // timing experiment: no epilogue work
                 } else if (layer < n_layers - 1) {
@@ -430,7 +469,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
-                            o[i] += (has_left ? zl : 0.0f) + (has_right ? zr : 0.0f);
+                            o[i] = (o[i] + ((has_left ? zl : 0.0f) + (has_right ? zr : 0.0f))) * inv_scale;
                         }
                         if (add_res) {                                                               // block input, kept in TMEM
                             tmem_ld16(t_lane + RES_COL + q * 16, v);
@@ -441,11 +480,12 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                         for (int i = 0; i < 16; ++i) o[i] = valid ? fmaxf(o[i] + bias[q * 16 + i], 0.0f) : 0.0f;
                         if (save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int cg = q * 4 + j;
-                            const float4 h = make_float4(tf32_round(o[4 * j]), tf32_round(o[4 * j + 1]), tf32_round(o[4 * j + 2]), tf32_round(o[4 * j + 3]));
+                        for (int j = 0; j < 2; ++j) {
+                            const int cg = q * 2 + j;
+                            uint4 h, l;
+                            split8(o + KCH * j, h, l, over);
                             a_hi[cg * SLOTS + slot] = h;
-                            a_lo[cg * SLOTS + slot] = make_float4(o[4 * j] - h.x, o[4 * j + 1] - h.y, o[4 * j + 2] - h.z, o[4 * j + 3] - h.w);
+                            a_lo[cg * SLOTS + slot] = l;
                         }
                     }
                     proxy_fence();
@@ -460,12 +500,13 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __re
                         float* dst = net.head_act + board * (long long)((pc + 1) * cells);
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
-                            if (j <= pc) dst[j * cells + cell] = fmaxf(v[j] + bias[j], 0.0f);
+                            if (j <= pc) dst[j * cells + cell] = fmaxf(v[j] * inv_scale + bias[j], 0.0f);
                     }
                     t_head += clock64() - t_layer;
                 }
             }
         }
+        if (over) atomicExch(net.error_flag + 1, 1ULL);
         if (threadIdx.x == 0 && net.timing) {
             net.timing[blockIdx.x * 12 + 4] = t_bar; net.timing[blockIdx.x * 12 + 5] = t_acc; net.timing[blockIdx.x * 12 + 6] = t_head;
             net.timing[blockIdx.x * 12 + 7] = clock64() - t0;
@@ -559,29 +600,31 @@ k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restri
 static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + HB * (pc + 1) * cells + HB * 64) * sizeof(float); }
 
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
-static inline float tf32_rna_host(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return x;
-    u = (u + 0x1000u) & 0xffffe000u;
-    float y;
-    memcpy(&y, &u, 4);
-    return y;
+// Power-of-two shift that brings the largest |w| of a layer into (2^9, 2^10]: fp16 keeps 11 significant bits
+// of every weight down to 2^-13 of the largest one, and hi stays far below 65504.
+static int weight_shift(const std::vector<std::vector<float>>& b) {
+    float mx = 0.0f;
+    for (const auto& v : b) for (float w : v) mx = std::max(mx, std::fabs(w));
+    if (!(mx > 0.0f) || !std::isfinite(mx)) return 0;
+    int e;
+    std::frexp(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+    return std::max(-40, std::min(40, 10 - e));
 }
 
-// appends the units of one vertical offset: b[dx][n][k] (n < n_pad rows, k < kk), per unit of <= UNIT_KS*8
-// input channels the layout [K chunk of 4][hi rows of every dx | lo rows of every dx][4]
-static void append_units(std::vector<float>& out, const std::vector<std::vector<float>>& b, int n_pad, int kk) {
+// appends the units of one vertical offset: b[dx][n][k] (n < n_pad rows, k < kk), per unit of <= UNIT_KS*16
+// input channels the layout [K chunk of 8][hi rows of every dx | lo rows of every dx][8 halfs]; weights x 2^shift
+static void append_units(std::vector<unsigned short>& out, const std::vector<std::vector<float>>& b, int n_pad, int kk, int shift) {
     const int ndx = (int)b.size();
-    for (int k0 = 0; k0 < kk; k0 += UNIT_KS * 8)
-        for (int kc = k0 / 4; kc < std::min(kk, k0 + UNIT_KS * 8) / 4; ++kc)
+    for (int k0 = 0; k0 < kk; k0 += UNIT_KS * KSTEP_CH)
+        for (int kc = k0 / KCH; kc < std::min(kk, k0 + UNIT_KS * KSTEP_CH) / KCH; ++kc)
             for (int part = 0; part < 2; ++part)
                 for (int dx = 0; dx < ndx; ++dx)
                     for (int n = 0; n < n_pad; ++n)
-                        for (int j = 0; j < 4; ++j) {
-                            float w = b[dx][(size_t)n * kk + kc * 4 + j];
-                            float hi = tf32_rna_host(w);
-                            out.push_back(part == 0 ? hi : tf32_rna_host(w - hi));
+                        for (int j = 0; j < KCH; ++j) {
+                            const float w = std::ldexp(b[dx][(size_t)n * kk + kc * KCH + j], shift);
+                            const __half hi = __float2half_rn(w);
+                            const __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
+                            out.push_back(__half_as_ushort(v));
                         }
 }
 
@@ -633,23 +676,25 @@ static int check_conv(const sprl_conv_bn_params& c, const char* what) {
 
 static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     const int C = CH, P = p->in_planes, L = 2 + 2 * p->blocks;
-    const int in_k = 8 * ((P + 7) / 8);
+    const int in_k = KSTEP_CH * ((P + KSTEP_CH - 1) / KSTEP_CH);
     const double eps = p->bn_eps > 0 ? p->bn_eps : 1e-5;
-    std::vector<float> units, bias((size_t)L * C, 0.0f);
+    std::vector<unsigned short> units;
+    std::vector<float> bias((size_t)L * C, 0.0f);
     auto conv_layer = [&](const sprl_conv_bn_params& c, int cin, int kk, int layer) {
         std::vector<double> scale(C);
         for (int co = 0; co < C; ++co) {
             scale[co] = (double)c.bn_weight[co] / std::sqrt((double)c.bn_var[co] + eps);
             bias[(size_t)layer * C + co] = (float)(((double)c.bias[co] - (double)c.bn_mean[co]) * scale[co] + (double)c.bn_bias[co]);
         }
-        for (int dy = 0; dy < 3; ++dy) {
-            std::vector<std::vector<float>> b(3, std::vector<float>((size_t)C * kk, 0.0f));
-            for (int dx = 0; dx < 3; ++dx)
-                for (int co = 0; co < C; ++co)
-                    for (int ci = 0; ci < cin; ++ci)
-                        b[dx][(size_t)co * kk + ci] = (float)((double)c.weight[((size_t)co * cin + ci) * 9 + dy * 3 + dx] * scale[co]);
-            append_units(units, b, C, kk);
-        }
+        std::vector<std::vector<float>> b(9, std::vector<float>((size_t)C * kk, 0.0f));      // [dy * 3 + dx]
+        for (int t = 0; t < 9; ++t)
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    b[t][(size_t)co * kk + ci] = (float)((double)c.weight[((size_t)co * cin + ci) * 9 + t] * scale[co]);
+        const int shift = weight_shift(b);
+        e->dev.inv_scale[layer] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
+        for (int dy = 0; dy < 3; ++dy)
+            append_units(units, std::vector<std::vector<float>>(b.begin() + 3 * dy, b.begin() + 3 * dy + 3), C, kk, shift);
     };
     conv_layer(p->stem, P, in_k, 0);
     for (int i = 0; i < 2 * p->blocks; ++i) conv_layer(p->tower[i], C, C, 1 + i);
@@ -663,7 +708,9 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         }
         for (int ci = 0; ci < C; ++ci) b[(size_t)pc * C + ci] = p->value_conv_w[ci];
         bias[(size_t)(L - 1) * C + pc] = p->value_conv_b[0];
-        append_units(units, bb, HEAD_N, C);
+        const int shift = weight_shift(bb);
+        e->dev.inv_scale[L - 1] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
+        append_units(units, bb, HEAD_N, C, shift);
     }
     const int cells = p->rows * p->cols;
     const int A = p->actions, K = p->policy_channels * cells;
@@ -679,7 +726,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     const size_t one = units.size();
     units.resize(one * REPLICAS);
     for (int r = 1; r < REPLICAS; ++r) std::copy(units.begin(), units.begin() + one, units.begin() + r * one);
-    e->dev.wunits_bytes = (long long)(one * sizeof(float));
+    e->dev.wunits_bytes = (long long)(one * sizeof(unsigned short));
     e->dev.replicas = REPLICAS;
     e->dev.debug = getenv("SPRL_EVALNET_DEBUG") ? atoi(getenv("SPRL_EVALNET_DEBUG")) : 0;
     if (getenv("SPRL_EVALNET_TIMING") && !e->dev.timing) {
@@ -696,7 +743,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     if (!rc) rc = e->upload(vfc1_wt, &e->dev.vfc1_wt);
     if (!rc) rc = e->upload(vfc1_b, &e->dev.vfc1_b);
     if (!rc) rc = e->upload(vfc2_w, &e->dev.vfc2_w);
-    std::vector<unsigned long long> flag(1, 0ULL);
+    std::vector<unsigned long long> flag(2, 0ULL);
     const unsigned long long* fp = e->dev.error_flag;
     if (!rc) rc = e->upload(flag, &fp);
     if (rc) return rc;
@@ -705,7 +752,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     e->dev.rows = p->rows;
     e->dev.cols = p->cols;
     e->dev.in_planes = P;
-    e->dev.in_ksteps = in_k / 8;
+    e->dev.in_ksteps = in_k / KSTEP_CH;
     e->dev.actions = A;
     e->dev.policy_channels = p->policy_channels;
     return SPRL_OK;
@@ -795,7 +842,7 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     }
     e->dev.head_act = e->head_act;
     const long long tiles = (batch + 1) / 2;
-    const int max_grid = e->sm_count / CLUSTER * CLUSTER;
+    const int max_grid = e->sm_count * CTAS_PER_SM / CLUSTER * CLUSTER;
     const int grid = (int)std::min<long long>((tiles + CLUSTER - 1) / CLUSTER * CLUSTER, max_grid);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -824,10 +871,11 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     cudaError_t err = cudaSetDevice(e->device);
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
-    unsigned long long flag = 0;
-    err = cudaMemcpy(&flag, e->dev.error_flag, sizeof(flag), cudaMemcpyDeviceToHost);
+    unsigned long long flag[2] = { 0, 0 };
+    err = cudaMemcpy(flag, e->dev.error_flag, sizeof(flag), cudaMemcpyDeviceToHost);
     if (err != cudaSuccess) return fail(SPRL_E_CUDA, "evaluator kernel failed: %s", cudaGetErrorString(err));
-    if (flag) return fail(SPRL_E_CUDA, "evaluator kernel timed out on a pipeline barrier (code %llx)", flag);
+    if (flag[0]) return fail(SPRL_E_CUDA, "evaluator kernel timed out on a pipeline barrier (code %llx)", flag[0]);
+    if (flag[1]) return fail(SPRL_E_STATE, "an input or activation exceeded %.0f, the range of the fp16-split evaluator; its outputs were clamped", HALF_MAX / ACT_SCALE);
     if (e->dev.timing) {
         std::vector<long long> t(12 * 4);
         cudaMemcpy(t.data(), e->dev.timing, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
