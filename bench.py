@@ -223,22 +223,17 @@ def run_ours(args):
         # ---- roofline leg: the search launch alone, timed with events on its stream
         n_probe = 64
         eng.reset_stats()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
-        for a, b in evs:
+        evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(n_probe)]
+        for a, b, c in evs:
             a.record()
             eng.round()
             b.record()
             eng._forward()
+            c.record()
         torch.cuda.synchronize(dev)
-        k_ms = sum(a.elapsed_time(b) for a, b in evs) / n_probe
+        k_ms = sum(a.elapsed_time(b) for a, b, c in evs) / n_probe
+        nn_ms = sum(b.elapsed_time(c) for a, b, c in evs) / n_probe     # the forward of exactly the leaves each launch queued
         pst = eng.stats()
-        nn_evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        nn_evs[0].record()
-        for _ in range(8):
-            eng._forward()
-        nn_evs[1].record()
-        torch.cuda.synchronize(dev)
-        nn_ms = nn_evs[0].elapsed_time(nn_evs[1]) / 8
     eng.close()
 
     # totals over ranks
@@ -271,12 +266,13 @@ def run_ours(args):
                        "sampled_launches": n_probe, "share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
     batch_rows = args.slots * MAX_QUEUE
     if evalnet is not None:
-        # dominant kernel of the step: the evaluator's forward (every row of the leaf batch is computed)
+        # dominant kernel of the step: the evaluator's forward over the rows in use (the leaves the launch queued)
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        batch_rows = pst["evals"] / n_probe
         tf = batch_rows * NET_FLOP_PER_LEAF / (nn_ms / 1e3) / 1e12
         roofline = {"kernel": "k_evalnet", "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
                     "frac": round(tf / tpeak, 5), "traffic": None, "peak_source": peak_src + " bf16 sustained",
-                    "launch_ms": round(nn_ms, 4), "leaves_per_launch": batch_rows, "flop_per_leaf": NET_FLOP_PER_LEAF,
+                    "launch_ms": round(nn_ms, 4), "leaves_per_launch": round(batch_rows, 1), "leaf_batch_capacity": args.slots * MAX_QUEUE, "flop_per_leaf": NET_FLOP_PER_LEAF,
                     "note": "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
                             "as fp16 MMAs (hi/lo split of both operands: hi*hi + hi*lo + lo*hi, fp32 accumulate) to keep fp32-level "
                             "accuracy, so issued_frac is the tensor-pipe utilisation",

@@ -125,11 +125,18 @@ void sprl_destroy(sprl_engine* e);
 int sprl_set_stream(sprl_engine* e, void* cuda_stream);
 
 /* SPRL_EVAL_EXTERNAL: device buffers of the traced network's input and outputs
- * (networks/GridNetwork.hpp:70,99-102), batch = num_slots * max_queue rows, row
- * tree*max_queue + q:  d_in [batch, 2H+1, R, C] is WRITTEN by sprl_round;
- * d_logits [batch, A] and d_value [batch] are READ by the next sprl_round. */
+ * (networks/GridNetwork.hpp:70,99-102), capacity batch = num_slots * max_queue rows:
+ * d_in [batch, 2H+1, R, C] is WRITTEN by sprl_round; d_logits [batch, A] and d_value [batch]
+ * are READ by the next sprl_round.  A launch hands out rows compactly, in no particular
+ * order, to the leaves it queued: only rows [0, d_rows[0]) hold leaves (sprl_eval_rows), the
+ * others keep stale data and their outputs are never read. */
 int sprl_bind_eval_buffers(sprl_engine* e, float* d_in, const float* d_logits, const float* d_value);
 int64_t sprl_eval_batch(const sprl_engine* e);
+/* Device address of the row counts of the last launch (uint32_t[2], updated on the stream by every
+ * sprl_round): d_rows[0] rows from row 0 hold leaves; in match play d_rows[0] counts agent 0's rows
+ * [0, d_rows[0]) and d_rows[1] agent 1's rows [half, half + d_rows[1]).  An evaluator that can read its
+ * batch size on the device (sprl_evalnet_forward_counted) skips the rest. */
+int sprl_eval_rows(sprl_engine* e, const uint32_t** d_rows);
 
 /* Starts runIteration(num_games): games first_game .. first_game+num_games-1, game g on
  * stream (seed, g), slot s plays games s, s+num_slots, ... one after the other. */
@@ -256,6 +263,10 @@ int sprl_evalnet_update(sprl_evalnet* net, const sprl_network_params* h_params);
  * `cuda_stream`; matches sprl_forward_fn so that it can serve as the engine's evaluator. */
 int sprl_evalnet_forward(sprl_evalnet* net, const float* d_in, int64_t batch, float* d_logits, float* d_value,
                          void* cuda_stream);
+/* Same with the batch size read on the device at run time: rows [0, min(*d_rows, max_batch)) are evaluated.
+ * The launch is sized for max_batch, so it can sit in a CUDA graph while the leaf count changes every round. */
+int sprl_evalnet_forward_counted(sprl_evalnet* net, const float* d_in, const uint32_t* d_rows, int64_t max_batch,
+                                 float* d_logits, float* d_value, void* cuda_stream);
 /* Synchronises the device and reports a kernel-side failure, if any. */
 int sprl_evalnet_status(sprl_evalnet* net, uint64_t* launches);
 /* Bytes copied host -> device by one create / update, weight-ring depth and shared memory per CTA. */

@@ -19,10 +19,10 @@ INITQ_ZERO, INITQ_PARENT, INITQ_DROP_PARENT = 0, 1, 2
 EXPORTS = [
     "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
     "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
-    "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
+    "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_eval_rows", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
     "sprl_match_begin", "sprl_run_match", "sprl_match_results", "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
-    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_destroy",
+    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_forward_counted", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_destroy",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
     lib.sprl_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.sprl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.sprl_bind_eval_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sprl_eval_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.sprl_set_game_stride.argtypes = [C.c_void_p, C.c_uint64]
     lib.sprl_begin_iteration.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     lib.sprl_round.argtypes = [C.c_void_p]
@@ -120,6 +121,7 @@ def load():
     lib.sprl_evalnet_create.argtypes = [C.c_int, C.POINTER(NetworkParams), C.POINTER(C.c_void_p)]
     lib.sprl_evalnet_update.argtypes = [C.c_void_p, C.POINTER(NetworkParams)]
     lib.sprl_evalnet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sprl_evalnet_forward_counted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sprl_evalnet_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.sprl_evalnet_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.sprl_evalnet_destroy.restype = None

@@ -184,6 +184,9 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (!rc) rc = e->alloc(&p.trees, S, true);
     if (!rc) rc = e->alloc(&p.q_leaf, S * cfg->max_queue, true);
     if (!rc) rc = e->alloc(&p.q_sym, S * cfg->max_queue, true);
+    if (!rc) rc = e->alloc(&p.q_count, 2, true);
+    if (!rc) rc = e->alloc(&p.q_rows, 2, true);
+    if (!rc) rc = e->alloc(&p.q_base, S, true);
     if (!rc) rc = e->alloc(&p.root_p, S * A, true);
     if (!rc) rc = e->alloc(&p.rec_board, MG * MM * 2 * e->words, true);
     if (!rc) rc = e->alloc(&p.rec_player, MG * MM, true);
@@ -240,6 +243,13 @@ int sprl_set_game_stride(sprl_engine* e, uint64_t stride) {
     return SPRL_OK;
 }
 
+int sprl_eval_rows(sprl_engine* e, const uint32_t** d_rows) {
+    ENGINE_CHECK(e);
+    if (!d_rows) return fail(SPRL_E_INVALID, "null output");
+    *d_rows = e->p.q_rows;
+    return SPRL_OK;
+}
+
 int64_t sprl_eval_batch(const sprl_engine* e) { return e ? (int64_t)e->cfg.num_slots * e->cfg.max_queue : 0; }
 
 int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games) {
@@ -250,6 +260,9 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
     e->p.num_games = num_games;
     e->num_games = num_games;
     e->active_slots = std::min<int64_t>(num_games, e->cfg.num_slots);
+    e->p.q_half = 0;
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_count, 0, 2 * sizeof(u32), e->stream));
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_rows, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_moves, 0, (size_t)e->cfg.max_games * sizeof(int), e->stream));
     if (e->cfg.record_stats) {
@@ -283,7 +296,7 @@ int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t
         e->match.agent[k].evaluator = h_agents[k].evaluator;
         e->match.agent[k].use_sym = h_agents[k].use_sym;
         e->match.agent[k].init_q = h_agents[k].init_q;
-        e->match.agent[k].pad = 0;
+        e->match.agent[k].pad = k;                       // which half of the evaluator batch
         e->match.agent[k].hash_salt = h_agents[k].hash_salt;
     }
     if (external && e->cfg.evaluator != SPRL_EVAL_EXTERNAL)
@@ -294,6 +307,9 @@ int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t
     e->p.num_games = num_games;
     e->num_games = num_games;
     e->active_slots = std::min<int64_t>(num_games, e->match.n_pairs);
+    e->p.q_half = (u32)e->match.n_pairs * (u32)e->cfg.max_queue;
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_count, 0, 2 * sizeof(u32), e->stream));
+    ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_rows, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_moves, 0, (size_t)e->cfg.max_games * sizeof(int), e->stream));
     if (e->cfg.record_stats) {
@@ -344,7 +360,7 @@ int sprl_round(sprl_engine* e) {
     if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
     if (e->match_open) {
         search_launch_match_round(e->cfg.game, e->p, e->match, e->stream);
-        e->launches += 1;
+        e->launches += 2;               // the search kernel and the row-counter flip
         ENGINE_CUDA(e, cudaGetLastError());
         return SPRL_OK;
     }

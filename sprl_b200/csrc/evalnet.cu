@@ -280,8 +280,10 @@ __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return un
 __device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
-k_evalnet(NetDev net, const float* __restrict__ in, long long batch, float* __restrict__ logits, float* __restrict__ value) {
+k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsigned* __restrict__ d_rows,
+          float* __restrict__ logits, float* __restrict__ value) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (d_rows) batch = min((long long)*d_rows, batch);          // batch size decided on the device by the previous kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_layers = net.n_layers, nst = net.nst;
     const uint32_t s_base = smem_u32(smem);
@@ -530,8 +532,10 @@ constexpr int HB = 64;                        // boards per CTA
 constexpr int HP_STRIDE = 68;                 // policy weight row stride in floats (65 actions padded for float4 loads)
 
 __global__ void __launch_bounds__(256)
-k_heads(NetDev net, long long batch, float* __restrict__ logits, float* __restrict__ value) {
+k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float* __restrict__ logits, float* __restrict__ value) {
     extern __shared__ __align__(16) float hs[];
+    if (d_rows) batch = min((long long)*d_rows, batch);
+    if ((long long)blockIdx.x * HB >= batch) return;
     const int pc = net.policy_channels, cells = net.rows * net.cols, K = pc * cells, A = net.actions, IN = (pc + 1) * cells;
     float* wp = hs;                           // [K][HP_STRIDE]
     float* wv = wp + K * HP_STRIDE;           // [cells][64]
@@ -823,6 +827,11 @@ int sprl_evalnet_update(sprl_evalnet* e, const sprl_network_params* params) {
 }
 
 int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, float* d_logits, float* d_value, void* cuda_stream) {
+    return sprl_evalnet_forward_counted(e, d_in, nullptr, batch, d_logits, d_value, cuda_stream);
+}
+
+int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint32_t* d_rows, int64_t batch, float* d_logits,
+                                 float* d_value, void* cuda_stream) {
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     if (batch < 0 || (batch > 0 && (!d_in || !d_logits || !d_value))) return fail(SPRL_E_INVALID, "bad argument to sprl_evalnet_forward");
     if (batch == 0) return SPRL_OK;
@@ -854,12 +863,12 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
     attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, k_evalnet, e->dev, d_in, (long long)batch, d_logits, d_value);
+    err = cudaLaunchKernelEx(&cfg, k_evalnet, e->dev, d_in, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
     e->launches += 1;
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {
         const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, 2LL * e->sm_count);
-        k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels, e->rows * e->cols), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, d_logits, d_value);
+        k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels, e->rows * e->cols), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
         e->launches += 1;
         err = cudaGetLastError();
     }

@@ -475,10 +475,17 @@ struct TreeWarp {
         acc.sims += trav;
         st.n_queued = nq;
         __syncwarp();
+        u32 row0 = 0;                                   // rows of the evaluator batch for this tree's leaves
+        if (cfg_evaluator() == SPRL_EVAL_EXTERNAL && nq > 0) {
+            const int side = MATCH ? agent.pad : 0;
+            if (lane == 0) row0 = atomicAdd(&p.q_count[side], (u32)nq) + (side ? p.q_half : 0u);
+            row0 = __shfl_sync(FULL, row0, 0);
+            if (lane == 0) p.q_base[tree] = row0;
+        }
         for (int q = 0; q < nq; ++q) {
             int s = cfg_use_sym() ? rng_uniform_int(rng, 0, G::NSYM - 1) : 0;
             if (lane == 0) p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s;
-            if (cfg_evaluator() == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)tree * p.max_queue + q);
+            if (cfg_evaluator() == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)row0 + q);
         }
         acc.evals += nq;
         __syncwarp();
@@ -608,13 +615,14 @@ struct TreeWarp {
 
     // ---- UCTTree::evaluateAndBackpropLeaves (uct/UCTTree.hpp:154-183) ----
     __device__ void apply_leaves() {
+        const size_t row0 = cfg_evaluator() == SPRL_EVAL_EXTERNAL ? (size_t)p.q_base[tree] : 0;
         for (int q = 0; q < st.n_queued; ++q) {
             size_t slot = (size_t)tree * p.max_queue + q;
             u32 leaf = p.q_leaf[slot];
             int s = p.q_sym[slot];
             H h;
             HL<W>::load(slab + leaf, h);
-            if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, slot);
+            if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, row0 + q);
             if (!(h.meta & META_EXPANDED)) expand(leaf, h.meta);
             backup(leaf, META_PLAYER(h.meta), h.net_value);
         }
@@ -916,8 +924,11 @@ __device__ __forceinline__ void order_next(const EngineParams& p, u32 parity, in
     else dst[(u32)p.n_slots - 1u - atomicAdd(cnt + 1, 1u)] = (u32)tree;
 }
 
-// After every search launch: the list just written becomes current, the other one is emptied.
+// After every search launch: the list just written becomes current, the other one is emptied; the rows handed
+// out by the launch become the evaluator's batch and the row counters restart.
 __global__ void k_flip(EngineParams p) {
+    p.q_rows[0] = p.q_count[0]; p.q_rows[1] = p.q_count[1];
+    p.q_count[0] = 0u; p.q_count[1] = 0u;
     const u32 parity = *p.order_parity;
     p.order_cnt[parity * 2u] = 0u;
     p.order_cnt[parity * 2u + 1u] = 0u;
@@ -1072,6 +1083,7 @@ template <class G> static void launch_match_begin(const EngineParams& p, const M
 }
 template <class G> static void launch_match_round(const EngineParams& p, const MatchParams& m, cudaStream_t s) {
     k_match_round<G><<<m.n_pairs, 32, 0, s>>>(p, m);
+    k_flip<<<1, 1, 0, s>>>(p);
 }
 
 #define GAME_SWITCH(game, STMT)                                   \

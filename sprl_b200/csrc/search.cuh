@@ -75,10 +75,16 @@ struct EngineParams {
     u32* q_leaf;                    // [n_slots][max_queue]
     unsigned char* q_sym;           // [n_slots][max_queue]
     float* root_p;                  // [n_slots][ACTIONS] noised priors of the decision node, by edge slot
-    // evaluator buffers (SPRL_EVAL_EXTERNAL), slot = tree * max_queue + q
+    // evaluator buffers (SPRL_EVAL_EXTERNAL).  Rows are handed out per launch, compactly: a tree with nq queued
+    // leaves takes rows q_base[tree] .. +nq-1 (one atomicAdd on q_count), so the evaluator only computes the
+    // q_rows[0] rows in use.  Match play: agent 1's rows start at q_half and are counted in q_count[1] / q_rows[1].
     float* nn_in;                   // [n_slots*max_queue][2H+1][R][C]
     const float* nn_logits;         // [n_slots*max_queue][A]
     const float* nn_value;          // [n_slots*max_queue]
+    u32* q_count;                   // [2] rows handed out by the running launch
+    u32* q_rows;                    // [2] rows of the previous launch: what the evaluator has to compute (set by k_flip)
+    u32* q_base;                    // [n_slots] first row of a tree's queued leaves
+    u32 q_half;                     // first row of agent 1 (match play)
     // per-game records, game-major: [num_games][max_moves]
     long long num_games;
     unsigned long long first_game;

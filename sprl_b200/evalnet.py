@@ -73,9 +73,15 @@ class EvalNet:
         capi.check(self.lib.sprl_evalnet_update(self.handle, C.byref(params)))
         del keep
 
-    def forward_ptr(self, d_in, batch, d_logits, d_value, stream=0):
-        capi.check(self.lib.sprl_evalnet_forward(self.handle, C.c_void_p(d_in), batch, C.c_void_p(d_logits),
-                                                  C.c_void_p(d_value), C.c_void_p(stream)))
+    def forward_ptr(self, d_in, batch, d_logits, d_value, stream=0, d_rows=None):
+        """d_rows: device address of a uint32 holding the number of rows to evaluate (<= batch), read by the
+        kernel at run time -- the engine's compact leaf batch (sprl_eval_rows); None = all `batch` rows."""
+        if d_rows:
+            capi.check(self.lib.sprl_evalnet_forward_counted(self.handle, C.c_void_p(d_in), C.c_void_p(d_rows), batch,
+                                                              C.c_void_p(d_logits), C.c_void_p(d_value), C.c_void_p(stream)))
+        else:
+            capi.check(self.lib.sprl_evalnet_forward(self.handle, C.c_void_p(d_in), batch, C.c_void_p(d_logits),
+                                                      C.c_void_p(d_value), C.c_void_p(stream)))
 
     def __call__(self, x):
         """Torch convenience: x [B, planes, 8, 8] fp32 on this GPU -> (logits [B, A], value [B, 1])."""

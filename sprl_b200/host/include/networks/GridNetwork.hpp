@@ -72,7 +72,7 @@ public:
     // d_in / d_logits / d_value may be any rows of a leaf-batch buffer on this GPU (a match gives each network
     // its half of one buffer).
     int forward(const float* d_in, int64_t batch, float* d_logits, float* d_value, void* stream) override {
-        if (m_evalnet) return sprl_evalnet_forward(m_evalnet, d_in, batch, d_logits, d_value, stream);
+        if (m_evalnet) return sprl_evalnet_forward_counted(m_evalnet, d_in, m_dRows, batch, d_logits, d_value, stream);
         if (!m_model || m_planes == 0) return -2;
         torch::NoGradGuard no_grad;
         c10::cuda::CUDAStream s = c10::cuda::getStreamFromExternal((cudaStream_t)stream, m_device.index());
@@ -86,6 +86,8 @@ public:
         value.copy_(output->elements()[1].toTensor().reshape({ -1 }));
         return 0;
     }
+
+    void setRowCount(const uint32_t* d_rows) override { m_dRows = d_rows; }
 
 private:
     // Hands the module's parameters (names of src/networks/grid_networks.py:30-80) to the library's
@@ -127,6 +129,7 @@ private:
     }
 
     sprl_evalnet* m_evalnet { nullptr };
+    const uint32_t* m_dRows { nullptr };
     std::string m_path;
     torch::Device m_device { torch::kCPU };
     std::shared_ptr<torch::jit::script::Module> m_model;

@@ -91,6 +91,9 @@ public:
     // its half of the first network's buffers).
     virtual int attach(int /*device*/, int /*planes*/, int /*rows*/, int /*cols*/, int /*actions*/) { return -1; }
     virtual int forward(const float*, int64_t, float*, float*, void* /*cudaStream_t*/) { return -1; }
+    // Device address of the number of rows in use (sprl_eval_rows); networks that can read their batch size on the
+    // device skip the unused rows.
+    virtual void setRowCount(const uint32_t* /*d_rows*/) {}
     virtual int getNumEvals() { return (int)m_numEvals; }
     void addEvals(uint64_t n) { m_numEvals += n; }
 protected:
@@ -198,6 +201,9 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
         if (network->prepare(cfg.device, sprl_eval_batch(e), 2 * gi.history + 1, gi.rows, gi.cols, gi.actions, &d_in, &d_logits, &d_value) != 0)
             throw EngineError(SPRL_E_STATE, "network could not allocate its device buffers");
         check(sprl_bind_eval_buffers(e, d_in, d_logits, d_value));
+        const uint32_t* d_rows = nullptr;
+        check(sprl_eval_rows(e, &d_rows));
+        network->setRowCount(d_rows);
     }
     check(sprl_run_iteration(e, opt.firstGame, numGames, fwd, &ctx));
 
@@ -266,6 +272,10 @@ MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, AC
             ctx.net[1] = nets[1];
         }
         check(sprl_bind_eval_buffers(e, d_in, d_logits, d_value));
+        const uint32_t* d_rows = nullptr;
+        check(sprl_eval_rows(e, &d_rows));
+        for (int k = 0; k < 2; ++k)
+            if (ctx.net[k]) ctx.net[k]->setRowCount(d_rows + k);
     }
     sprl_forward_fn fwd = [](void* user, const float* in, int64_t, float* logits, float* value, void* stream) -> int {
         Ctx* c = static_cast<Ctx*>(user);

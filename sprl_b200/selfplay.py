@@ -153,6 +153,9 @@ class Engine:
         capi.check(self.lib.sprl_bind_eval_buffers(self.handle, C.c_void_p(nn["inp"].data_ptr()),
                                                     C.c_void_p(nn["logits"].data_ptr()), C.c_void_p(nn["value"].data_ptr())))
         nn["use_graph"] = use_cuda_graph
+        rows = C.c_void_p()
+        capi.check(self.lib.sprl_eval_rows(self.handle, C.byref(rows)))
+        nn["rows"] = rows.value            # uint32[2] on the device: rows in use per launch (per agent in a match)
         self._nn = nn
 
     def attach_evalnet(self, evalnet, use_cuda_graph=True):
@@ -173,7 +176,7 @@ class Engine:
         torch = nn["torch"]
         if hasattr(ev, "forward_ptr"):
             ev.forward_ptr(nn["inp"][lo:].data_ptr(), n, nn["logits"][lo:].data_ptr(), nn["value"][lo:].data_ptr(),
-                           torch.cuda.current_stream(nn["dev"]).cuda_stream)
+                           torch.cuda.current_stream(nn["dev"]).cuda_stream, d_rows=nn["rows"] + (4 if lo else 0))
         else:
             with torch.no_grad():
                 logits, value = ev(nn["inp"][lo:lo + n])
@@ -191,7 +194,8 @@ class Engine:
             return
         if nn.get("evalnet") is not None:
             nn["evalnet"].forward_ptr(nn["inp"].data_ptr(), nn["inp"].shape[0], nn["logits"].data_ptr(),
-                                      nn["value"].data_ptr(), torch.cuda.current_stream(nn["dev"]).cuda_stream)
+                                      nn["value"].data_ptr(), torch.cuda.current_stream(nn["dev"]).cuda_stream,
+                                      d_rows=nn["rows"] if nn.get("counted", True) else None)
             return
         with torch.no_grad():
             logits, value = nn["module"](nn["inp"])
