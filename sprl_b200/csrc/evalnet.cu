@@ -227,20 +227,24 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* v, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
 }
-// Eight real-unit values -> their fp16 hi and lo images (x 2^ACT_SHIFT), one 16-byte channel group each.
-// Values beyond the fp16 range are clamped and noted in `over`.
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, bool& over) {
+// two floats -> packed fp16 pair (x0 in the low half), round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_half2_sat(float x0, float x1) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    return r;
+}
+// Eight values already in image units (real value x 2^ACT_SHIFT) -> their fp16 hi and lo parts, one 16-byte
+// channel group each.  `mx` tracks the largest magnitude seen: beyond 65504 the conversion saturates and the
+// forward is reported as out of range.
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, float& mx) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float a = x[2 * j] * ACT_SCALE, b = x[2 * j + 1] * ACT_SCALE;
-        over = over || fabsf(a) > HALF_MAX || fabsf(b) > HALF_MAX;
-        a = fminf(fmaxf(a, -HALF_MAX), HALF_MAX); b = fminf(fmaxf(b, -HALF_MAX), HALF_MAX);
-        const __half2 hh = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        const float a = x[2 * j], b = x[2 * j + 1];
+        mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
+        h[j] = pack_half2_sat(a, b);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+        l[j] = pack_half2_sat(a - hf.x, b - hf.y);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -266,7 +270,7 @@ __device__ __forceinline__ uint32_t instr_desc_f16(int m, int n) {
 struct LayerGeom { int ndy, ndx, ksteps, n, units_per_dy; };
 __host__ __device__ inline LayerGeom layer_geom(int layer, int n_layers, int in_ksteps) {
     LayerGeom g;
-    if (layer == 0) { g.ndy = 3; g.ndx = 3; g.ksteps = in_ksteps; g.n = CH; }
+    if (layer == 0) { g.ndy = 1; g.ndx = 3; g.ksteps = in_ksteps; g.n = CH; }      // stem: the three dy taps are folded into K
     else if (layer == n_layers - 1) { g.ndy = 1; g.ndx = 1; g.ksteps = CH / KSTEP_CH; g.n = HEAD_N; }
     else { g.ndy = 3; g.ndx = 3; g.ksteps = CH / KSTEP_CH; g.n = CH; }
     g.units_per_dy = (g.ksteps + UNIT_KS - 1) / UNIT_KS;
@@ -302,7 +306,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     // ---- one-time setup ----
     for (int i = threadIdx.x; i < (2 * IMG_BYTES) / 16; i += THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x; i < n_layers * CH; i += THREADS) s_bias[i] = net.bias[i];
+    for (int i = threadIdx.x; i < n_layers * CH; i += THREADS)          // conv layers work in image units (x 2^ACT_SHIFT)
+        s_bias[i] = net.bias[i] * (i < (n_layers - 1) * CH ? ACT_SCALE : 1.0f);
     if (threadIdx.x == 0) {
         for (int i = 0; i < nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CLUSTER); }
         mbar_init(bar_acc, 1);
@@ -428,22 +433,27 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint4* a_hi = reinterpret_cast<uint4*>(smem + OFF_AHI);
         uint4* a_lo = reinterpret_cast<uint4*>(smem + OFF_ALO);
-        bool over = false;
+        float mx = 0.0f;                                             // largest |image value| this thread produced
+        const float vmask = valid ? 1.0f : 0.0f, lmask = has_left ? 1.0f : 0.0f, rmask = has_right ? 1.0f : 0.0f;
         const int cells = net.rows * net.cols, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = tile * 2 + b;
-            // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split) ----
+            // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split).  The stem
+            // has few input planes, so its vertical taps are folded into K: image channel dyi * planes + p of a
+            // cell holds plane p of the cell one row above / at / below it, and the stem becomes a single-dy layer
+            // (3 MMAs per k-step instead of 9).
             for (int cg = half; cg < 2 * net.in_ksteps; cg += EPI_WARPS / 4) {
                 float v[KCH];
 #pragma unroll
                 for (int j = 0; j < KCH; ++j) {
-                    const int p = cg * KCH + j;
-                    v[j] = (valid && p < planes && board < batch) ? in[(board * planes + p) * cells + cell] : 0.0f;
+                    const int ch = cg * KCH + j, dyi = ch / planes, p = ch - dyi * planes, rr = r + dyi - 1;
+                    v[j] = (valid && dyi < 3 && rr >= 0 && rr < net.rows && board < batch)
+                               ? in[(board * planes + p) * cells + rr * net.cols + c] * ACT_SCALE : 0.0f;
                 }
                 uint4 h, l;
-                split8(v, h, l, over);
+                split8(v, h, l, mx);
                 a_hi[cg * SLOTS + slot] = h;
                 a_lo[cg * SLOTS + slot] = l;
             }
@@ -456,7 +466,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float* bias = s_bias + layer * CH;
-                const float inv_scale = net.inv_scale[layer];                // exact power of two
+                // accumulator -> image units for the conv layers (real units for the heads); exact powers of two
+                const float inv_scale = net.inv_scale[layer] * (layer < n_layers - 1 ? ACT_SCALE : 1.0f);
                 if (layer < n_layers - 1 && net.debug >= 5) {
                     // timing experiment: no epilogue work
                 } else if (layer < n_layers - 1) {
@@ -471,21 +482,22 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
-                            o[i] = (o[i] + ((has_left ? zl : 0.0f) + (has_right ? zr : 0.0f))) * inv_scale;
+                            o[i] = fmaf(zl, lmask, fmaf(zr, rmask, o[i]));
                         }
-                        if (add_res) {                                                               // block input, kept in TMEM
+                        if (add_res) {                                                               // block input (image units), kept in TMEM
                             tmem_ld16(t_lane + RES_COL + q * 16, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] += v[i];
-                        }
+                            for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, v[i] + bias[q * 16 + i]), 0.0f) * vmask;
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = valid ? fmaxf(o[i] + bias[q * 16 + i], 0.0f) : 0.0f;
+                            for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, bias[q * 16 + i]), 0.0f) * vmask;
+                        }
                         if (save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const int cg = q * 2 + j;
                             uint4 h, l;
-                            split8(o + KCH * j, h, l, over);
+                            split8(o + KCH * j, h, l, mx);
                             a_hi[cg * SLOTS + slot] = h;
                             a_lo[cg * SLOTS + slot] = l;
                         }
@@ -508,7 +520,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                 }
             }
         }
-        if (over) atomicExch(net.error_flag + 1, 1ULL);
+        if (mx > HALF_MAX) atomicExch(net.error_flag + 1, 1ULL);
         if (threadIdx.x == 0 && net.timing) {
             net.timing[blockIdx.x * 12 + 4] = t_bar; net.timing[blockIdx.x * 12 + 5] = t_acc; net.timing[blockIdx.x * 12 + 6] = t_head;
             net.timing[blockIdx.x * 12 + 7] = clock64() - t0;
@@ -680,7 +692,7 @@ static int check_conv(const sprl_conv_bn_params& c, const char* what) {
 
 static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     const int C = CH, P = p->in_planes, L = 2 + 2 * p->blocks;
-    const int in_k = KSTEP_CH * ((P + KSTEP_CH - 1) / KSTEP_CH);
+    const int in_k = KSTEP_CH * ((3 * P + KSTEP_CH - 1) / KSTEP_CH);      // stem input channels: (dy, plane), see k_evalnet
     const double eps = p->bn_eps > 0 ? p->bn_eps : 1e-5;
     std::vector<unsigned short> units;
     std::vector<float> bias((size_t)L * C, 0.0f);
@@ -700,7 +712,21 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         for (int dy = 0; dy < 3; ++dy)
             append_units(units, std::vector<std::vector<float>>(b.begin() + 3 * dy, b.begin() + 3 * dy + 3), C, kk, shift);
     };
-    conv_layer(p->stem, P, in_k, 0);
+    {   // stem: K index dy * P + plane, one unit group with the three dx stacked along N
+        const sprl_conv_bn_params& c = p->stem;
+        std::vector<std::vector<float>> b(3, std::vector<float>((size_t)C * in_k, 0.0f));
+        for (int co = 0; co < C; ++co) {
+            const double scale = (double)c.bn_weight[co] / std::sqrt((double)c.bn_var[co] + eps);
+            bias[co] = (float)(((double)c.bias[co] - (double)c.bn_mean[co]) * scale + (double)c.bn_bias[co]);
+            for (int ci = 0; ci < P; ++ci)
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx)
+                        b[dx][(size_t)co * in_k + dy * P + ci] = (float)((double)c.weight[((size_t)co * P + ci) * 9 + dy * 3 + dx] * scale);
+        }
+        const int shift = weight_shift(b);
+        e->dev.inv_scale[0] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
+        append_units(units, b, C, in_k, shift);
+    }
     for (int i = 0; i < 2 * p->blocks; ++i) conv_layer(p->tower[i], C, C, 1 + i);
     {   // heads: rows 0..pc-1 policy_conv, row pc value_conv
         const int pc = p->policy_channels;
@@ -768,7 +794,7 @@ static int validate(const sprl_network_params* p) {
         return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles boards up to 8x8 (two per MMA); %dx%d boards run through the LibTorch module", p->rows, p->cols);
     if (p->channels != CH) return fail(SPRL_E_INVALID, "tower width must be %d channels, got %d", CH, p->channels);
     if (p->blocks < 0 || 2 + 2 * p->blocks > MAX_LAYERS) return fail(SPRL_E_INVALID, "unsupported number of residual blocks %d", p->blocks);
-    if (p->in_planes < 1 || p->in_planes > CH) return fail(SPRL_E_INVALID, "unsupported number of input planes %d", p->in_planes);
+    if (p->in_planes < 1 || 3 * p->in_planes > CH) return fail(SPRL_E_INVALID, "unsupported number of input planes %d (at most %d)", p->in_planes, CH / 3);
     if (p->policy_channels < 1 || p->policy_channels > 2 || p->value_channels != 1 || p->value_hidden != 64)
         return fail(SPRL_E_INVALID, "unsupported head shape (policy channels %d, value channels %d, value hidden %d)",
                     p->policy_channels, p->value_channels, p->value_hidden);
