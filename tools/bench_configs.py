@@ -67,4 +67,24 @@ for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5
     print(json.dumps({"config": kind + "_selfplay", "sims_per_move": sims, "batch_queue": [b, q], "slots": slots,
                       "sims_per_sec": round(st["sims"] / dt, 1), "moves_per_sec": round(st["moves"] / dt, 1),
                       "evals_per_sec": round(st["evals"] / dt, 1), "failed_slots": failed,
-                      "evaluator": "library (tcgen05, 3xTF32)" if library else "traced module, LibTorch/cuDNN fp32"}), flush=True)
+                      "evaluator": "library (tcgen05, fp16 split)" if library else "traced module, LibTorch/cuDNN fp32"}), flush=True)
+
+# ---- match play (Evaluate.cpp): two random-init Othello networks, each side its own tree and evaluator
+pairs, games = 4096, 8192
+nets = [EvalNet(make_network("othello", k), device=0) for k in (0, 1)]
+with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, seed=0, sims=400, max_batch=8, max_queue=4, dir_eps=0.25, dir_alpha=0.1,
+               u_weight=1.0, add_noise=1, num_slots=2 * pairs, max_games=games) as eng:
+    eng.attach_match_evaluators(nets, use_cuda_graph=True)
+    agents = [dict(evaluator=capi.EVAL_EXTERNAL, use_sym=1, init_q=capi.INITQ_PARENT)] * 2
+    eng.reset_stats()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    res = eng.run_match(agents, games)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    st = eng.stats()
+print(json.dumps({"config": "othello_match_play", "sims_per_move": 400, "batch_queue": [8, 4], "pairs_of_trees": pairs, "games": games,
+                  "wins_agent0": res["wins"][0], "wins_agent1": res["wins"][1], "draws": res["draws"],
+                  "games_per_sec": round(games / dt, 1), "sims_per_sec": round(st["sims"] / dt, 1),
+                  "moves_per_sec": round(st["moves"] / dt, 1), "wall_s": round(dt, 2),
+                  "evaluator": "two library evaluators (tcgen05, fp16 split), one per side"}), flush=True)
