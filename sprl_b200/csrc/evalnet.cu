@@ -82,6 +82,18 @@ constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA war
 #define SPRL_EVALNET_CLUSTER 2
 #endif
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
+#ifndef SPRL_EVALNET_PAIR
+#define SPRL_EVALNET_PAIR 0
+#endif
+// Experiment switch, off by default.  CTA pair (tcgen05 cta_group::2): the two CTAs of a cluster run ONE MMA of
+// M = 256 -- each supplies its own tile (128 rows of A, its own accumulators) and HALF of the weight rows (B), so a
+// CTA stores and reads only half of every weight unit.  The leader (cluster rank 0) issues; the peer's MMA warp relays
+// "my half has landed" / "my image is ready" to the leader's barriers.  Correct (1.4e-7) and the MMAs issue 28 %
+// faster, but the two tiles of a pair then move in lockstep and the relay adds latency: 1.65 ms against 1.45 ms for
+// two independent CTAs (profiles/r1h_evalnet_pair_variants.txt), so the independent CTAs stay the default.
+constexpr bool PAIR = SPRL_EVALNET_PAIR != 0;
+static_assert(!PAIR || CLUSTER == 2, "the CTA pair is a cluster of two");
+constexpr int UNIT_SLOT = PAIR ? UNIT_BYTES / 2 : UNIT_BYTES;   // bytes of a ring stage in one CTA
 constexpr int TMEM_COLS = 256;               // [dx * 64 + channel] = Z_dx (all three split products); [192, 256) = residual
 constexpr int RES_COL = 3 * CH;              // the block input of the current residual block, fp32, one cell per lane
 #ifndef SPRL_EVALNET_CTAS_PER_SM
@@ -120,7 +132,7 @@ struct NetDev {
 };
 
 __host__ __device__ inline int smem_bytes_for(int n_layers, int nst) {
-    return OFF_RING + nst * UNIT_BYTES + n_layers * CH * 4 + (2 * nst + 1) * 8 + 16;
+    return OFF_RING + nst * UNIT_SLOT + n_layers * CH * 4 + (3 * nst + 2) * 8 + 16;
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -190,6 +202,42 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
                      ::"r"(bar), "h"(mask) : "memory");
     }
 }
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// arrives on the mbarrier at the same offset in both CTAs of the pair once the pair's MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    if (elect_one()) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    if (elect_one()) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a barrier the peer CTA arrives on
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, unsigned long long* error_flag, int where) {
+    for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {
+            if (error_flag) atomicExch(error_flag, 0xDEAD0000ULL | (unsigned)where);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -249,6 +297,10 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo, flo
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+__device__ __forceinline__ void mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (PAIR) umma_f16_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+    else umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+}
 // K-major, no swizzle: rows of a core matrix 16 B apart, 8-row groups SBO apart, K chunks (16 B) LBO apart
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
@@ -291,8 +343,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_layers = net.n_layers, nst = net.nst;
     const uint32_t s_base = smem_u32(smem);
-    const int off_bias = OFF_RING + nst * UNIT_BYTES, off_bars = off_bias + n_layers * CH * 4, off_tmem = off_bars + (2 * nst + 1) * 8;
+    const int off_bias = OFF_RING + nst * UNIT_SLOT, off_bars = off_bias + n_layers * CH * 4, off_tmem = off_bars + (3 * nst + 2) * 8;
     const uint32_t bar_full = s_base + off_bars, bar_empty = bar_full + nst * 8, bar_acc = bar_empty + nst * 8;
+    const uint32_t bar_pfull = bar_acc + 8, bar_img = bar_pfull + nst * 8;      // pair mode, used in the leader: peer's half / image
     float* s_bias = reinterpret_cast<float*>(smem + off_bias);
     const long long n_tiles = (batch + 1) / 2;
     // every CTA of a cluster walks the same number of tiles (the multicast ring is shared);
@@ -309,18 +362,27 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     for (int i = threadIdx.x; i < n_layers * CH; i += THREADS)          // conv layers work in image units (x 2^ACT_SHIFT)
         s_bias[i] = net.bias[i] * (i < (n_layers - 1) * CH ? ACT_SCALE : 1.0f);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CLUSTER); }
+        for (int i = 0; i < nst; ++i) {
+            mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, PAIR ? 1 : CLUSTER); mbar_init(bar_pfull + 8 * i, 1);
+        }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_img, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + off_tmem), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
     proxy_fence();
-    tc_fence_before();
     __syncthreads();
     cluster_sync_all();                               // peers' barriers exist before anything is multicast
+    if (warp == MMA_WARP) {                           // pair mode: a collective of the two CTAs' MMA warps
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + off_tmem), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + off_tmem), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + off_tmem), 0);
 
@@ -347,10 +409,15 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                         for (int u = 0; u < g.units_per_dy; ++u) {
                             const uint32_t bytes = (uint32_t)unit_bytes(g, u);
                             { long long a = clock64(); mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1); t_wait += clock64() - a; }
-                            mbar_expect_tx(bar_full + 8 * s, bytes);       // the whole unit: one slice from every CTA of the cluster
                             const uint32_t slice = bytes / CLUSTER;
-                            bulk_g2s_multicast(s_base + OFF_RING + s * UNIT_BYTES + crank * slice, src + crank * slice, slice,
-                                               bar_full + 8 * s, CMASK);
+                            if (PAIR) {                                     // this CTA's half of the rows, kept to itself
+                                mbar_expect_tx(bar_full + 8 * s, slice);
+                                bulk_g2s(s_base + OFF_RING + s * UNIT_SLOT, src + crank * slice, slice, bar_full + 8 * s);
+                            } else {
+                                mbar_expect_tx(bar_full + 8 * s, bytes);   // the whole unit: one slice from every CTA of the cluster
+                                bulk_g2s_multicast(s_base + OFF_RING + s * UNIT_SLOT + crank * slice, src + crank * slice, slice,
+                                                   bar_full + 8 * s, CMASK);
+                            }
                             src += bytes;
                             if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                         }
@@ -363,17 +430,24 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         __syncwarp();
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) =====
-        uint32_t s = 0, ph = 0;
+        uint32_t s = 0, ph = 0, img_phase = 0;
+        const bool leader = !PAIR || crank == 0;
+        const uint32_t lead_pfull = PAIR ? map_to_cta(bar_pfull, 0) : 0u, lead_img = PAIR ? map_to_cta(bar_img, 0) : 0u;
         long long t_bar = 0, t_full = 0, t_issue = 0, t_commit = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer) {
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
                 { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
+                if (PAIR) {                                                      // ... in the peer CTA as well
+                    if (!leader) mbar_arrive_cluster(lead_img);
+                    else { long long a = clock64(); mbar_wait_cluster(bar_img, img_phase, net.error_flag, 4); img_phase ^= 1u; t_bar += clock64() - a; }
+                }
                 tc_fence_after();
                 const int n1 = g.ndx * g.n;                                      // output columns of one MMA
-                const uint32_t idesc = instr_desc_f16(TILE_M, n1);
+                const int nb = PAIR ? n1 / 2 : n1;                               // weight rows held by this CTA
+                const uint32_t idesc = instr_desc_f16(PAIR ? 2 * TILE_M : TILE_M, n1);
                 const bool lo_pass = net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
-                const uint32_t b_lbo = (uint32_t)(2 * n1) * 16u, b_kstep = (2u * b_lbo) >> 4, b_lo_off = ((uint32_t)n1 * 16u) >> 4;
+                const uint32_t b_lbo = (uint32_t)(2 * nb) * 16u, b_kstep = (2u * b_lbo) >> 4, b_lo_off = ((uint32_t)nb * 16u) >> 4;
                 const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
                 const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
                 constexpr uint32_t A_KSTEP = (2u * CG_STRIDE) >> 4;
@@ -386,35 +460,43 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                     for (int u = 0; u < g.units_per_dy; ++u) {
                         const int nks = unit_ksteps(g, u);
                         { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
+                        if (PAIR && !leader) {                   // relay: the leader may read this CTA's half now
+                            mbar_arrive_cluster(lead_pfull + 8 * s);
+                            if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
+                            continue;
+                        }
+                        if (PAIR) { long long a = clock64(); mbar_wait_cluster(bar_pfull + 8 * s, ph, net.error_flag, 5); t_full += clock64() - a; }
                         tc_fence_after();
                         const long long t_i0 = clock64();
-                        const uint64_t bd = b0 + s * (UNIT_BYTES >> 4);
+                        const uint64_t bd = b0 + s * (UNIT_SLOT >> 4);
                         const uint64_t ah = a_hi0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP;
                         if (hi_pass) {
                             if (nks == UNIT_KS) {
 #pragma unroll
                                 for (int ks = 0; ks < UNIT_KS; ++ks) {
-                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
-                                    if (lo_pass) umma_f16(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    mma(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    mma(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
+                                    if (lo_pass) mma(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
                             } else {
                                 for (int ks = 0; ks < nks; ++ks) {
-                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
-                                    umma_f16(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
-                                    if (lo_pass) umma_f16(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
+                                    mma(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep, idesc, acc);
+                                    mma(d_main, ah + ks * A_KSTEP, bd + ks * b_kstep + b_lo_off, idesc, 1u);
+                                    if (lo_pass) mma(d_main, al + ks * A_KSTEP, bd + ks * b_kstep, idesc, 1u);
                                     acc = 1;
                                 }
                             }
                         }
                         const long long t_i1 = clock64();
-                        umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
+                        if (PAIR) umma_commit_pair(bar_empty + 8 * s);      // both producers may refill their halves
+                        else umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
                         t_issue += t_i1 - t_i0; t_commit += clock64() - t_i1;
                         if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                     }
                 }
-                umma_commit(bar_acc);                            // the accumulators of this layer are complete
+                if (PAIR) { if (leader) umma_commit_pair(bar_acc); }        // the accumulators of this layer are complete, in both CTAs
+                else umma_commit(bar_acc);
                 __syncwarp();
             }
         }
@@ -534,7 +616,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     cluster_sync_all();                               // no CTA leaves while peers may still signal its barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -629,19 +712,23 @@ static int weight_shift(const std::vector<std::vector<float>>& b) {
 
 // appends the units of one vertical offset: b[dx][n][k] (n < n_pad rows, k < kk), per unit of <= UNIT_KS*16
 // input channels the layout [K chunk of 8][hi rows of every dx | lo rows of every dx][8 halfs]; weights x 2^shift
+// In pair mode a unit is [rows of CTA 0][rows of CTA 1], each with the layout above over its half of the rows
+// (row index = dx * n_pad + n): the two CTAs of a pair each load and hold one half.
 static void append_units(std::vector<unsigned short>& out, const std::vector<std::vector<float>>& b, int n_pad, int kk, int shift) {
-    const int ndx = (int)b.size();
+    const int ndx = (int)b.size(), rows = ndx * n_pad, parts = PAIR ? 2 : 1, rows_per = rows / parts;
     for (int k0 = 0; k0 < kk; k0 += UNIT_KS * KSTEP_CH)
-        for (int kc = k0 / KCH; kc < std::min(kk, k0 + UNIT_KS * KSTEP_CH) / KCH; ++kc)
-            for (int part = 0; part < 2; ++part)
-                for (int dx = 0; dx < ndx; ++dx)
-                    for (int n = 0; n < n_pad; ++n)
+        for (int h = 0; h < parts; ++h)
+            for (int kc = k0 / KCH; kc < std::min(kk, k0 + UNIT_KS * KSTEP_CH) / KCH; ++kc)
+                for (int part = 0; part < 2; ++part)
+                    for (int r = h * rows_per; r < (h + 1) * rows_per; ++r) {
+                        const int dx = r / n_pad, n = r - dx * n_pad;
                         for (int j = 0; j < KCH; ++j) {
                             const float w = std::ldexp(b[dx][(size_t)n * kk + kc * KCH + j], shift);
                             const __half hi = __float2half_rn(w);
                             const __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
                             out.push_back(__half_as_ushort(v));
                         }
+                    }
 }
 
 }  // namespace evalnet
@@ -765,6 +852,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         if (!e->upload(z, &tp)) e->dev.timing = const_cast<long long*>(tp);
     }
     e->dev.nst = MAX_NST;
+    if (getenv("SPRL_EVALNET_NST")) e->dev.nst = std::max(2, std::min(MAX_NST, atoi(getenv("SPRL_EVALNET_NST"))));   // experiments
     while (e->dev.nst > 2 && smem_bytes_for(L, e->dev.nst) > MAX_SMEM) e->dev.nst -= 1;
     int rc = e->upload(units, &e->dev.wunits);
     if (!rc) rc = e->upload(bias, &e->dev.bias);
