@@ -257,10 +257,22 @@ def run_ours(args):
     except Exception:
         pass
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/ncu_traffic.json), used only when the
+    # capture was taken at this run's size
+    ncu_traffic = {}
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+
+    def traffic_of(kernel):
+        t = ncu_traffic.get(kernel)
+        return t["dram_bytes_per_launch"] if t and t.get("slots") == args.slots else None
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bps * sims_per_launch / (k_ms / 1e3) / 1e9
     roofline_search = {"kernel": "k_round<Othello>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                       "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                       "frac": round(achieved / peak, 5), "traffic": traffic_of("k_round"), "peak_source": peak_src,
+                       "algorithmic_bytes_per_launch": round(bps * sims_per_launch, 1),
                        "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
                        "select_depth": round(D, 3), "legal_per_node": round(L, 3), "evals_per_sim": round(ef, 4),
                        "sampled_launches": n_probe, "share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
@@ -271,7 +283,7 @@ def run_ours(args):
         batch_rows = pst["evals"] / n_probe
         tf = batch_rows * NET_FLOP_PER_LEAF / (nn_ms / 1e3) / 1e12
         roofline = {"kernel": "k_evalnet", "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": round(tf / tpeak, 5), "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                    "frac": round(tf / tpeak, 5), "traffic": traffic_of("k_evalnet"), "peak_source": peak_src + " bf16 sustained",
                     "launch_ms": round(nn_ms, 4), "leaves_per_launch": round(batch_rows, 1), "leaf_batch_capacity": args.slots * MAX_QUEUE, "flop_per_leaf": NET_FLOP_PER_LEAF,
                     "note": "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
                             "as fp16 MMAs (hi/lo split of both operands: hi*hi + hi*lo + lo*hi, fp32 accumulate) to keep fp32-level "

@@ -652,7 +652,27 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-            for (int k = 0; k < K; ++k) {
+            // four k per step: one 128-bit read of every board's activations (IN and K are multiples of 4 or the tail
+            // loop below takes over) against four 128-bit weight reads -> 8 shared-memory reads per 64 FMAs
+            int k = 0;
+            if ((IN & 3) == 0) {
+                for (; k + 4 <= K; k += 4) {
+                    float4 xv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(x + (4 * bg + i) * IN + k);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 w = *reinterpret_cast<const float4*>(wp + (k + kk) * HP_STRIDE + a0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float xs = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+                            acc[i][0] = fmaf(xs, w.x, acc[i][0]); acc[i][1] = fmaf(xs, w.y, acc[i][1]);
+                            acc[i][2] = fmaf(xs, w.z, acc[i][2]); acc[i][3] = fmaf(xs, w.w, acc[i][3]);
+                        }
+                    }
+                }
+            }
+            for (; k < K; ++k) {
                 const float4 w = *reinterpret_cast<const float4*>(wp + k * HP_STRIDE + a0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -673,7 +693,25 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-            for (int k = 0; k < cells; ++k) {
+            int k = 0;
+            if ((IN & 3) == 0 && (K & 3) == 0) {
+                for (; k + 4 <= cells; k += 4) {
+                    float4 xv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(x + (4 * bg + i) * IN + K + k);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 w = *reinterpret_cast<const float4*>(wv + (k + kk) * 64 + 4 * ag);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float xs = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+                            acc[i][0] = fmaf(xs, w.x, acc[i][0]); acc[i][1] = fmaf(xs, w.y, acc[i][1]);
+                            acc[i][2] = fmaf(xs, w.z, acc[i][2]); acc[i][3] = fmaf(xs, w.w, acc[i][3]);
+                        }
+                    }
+                }
+            }
+            for (; k < cells; ++k) {
                 const float4 w = *reinterpret_cast<const float4*>(wv + k * 64 + 4 * ag);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

@@ -62,6 +62,27 @@ def test_no_gpu_fails_loudly():
     assert lib.sprl_create(C.byref(cfg), C.byref(h)) == capi.SPRL_E_NOGPU and not h
 
 
+def test_null_handles_and_bad_options_are_rejected():
+    """Argument errors are reported before any device work (so they can be checked without a GPU)."""
+    lib = capi.load()
+    agents = (capi.AgentConfig * 2)()
+    assert lib.sprl_match_begin(None, agents, 0, 4) == capi.SPRL_E_INVALID
+    assert lib.sprl_run_match(None, agents, 0, 4, None, None) == capi.SPRL_E_INVALID
+    wins, draws = (C.c_int64 * 2)(), C.c_int64()
+    assert lib.sprl_match_results(None, 0, None, None, None, wins, C.byref(draws)) == capi.SPRL_E_INVALID
+    rows = C.c_void_p()
+    assert lib.sprl_eval_rows(None, C.byref(rows)) == capi.SPRL_E_INVALID
+    assert lib.sprl_evalnet_forward_counted(None, None, None, 4, None, None, None) == capi.SPRL_E_INVALID
+    # evaluator / init-Q ranges (uct/UCTNode.hpp:24-28; networks/OthelloHeuristic.hpp is Othello-only)
+    h = C.c_void_p()
+    for game, ev, q in [(capi.GAME_C4, capi.EVAL_OTHELLO_HEURISTIC, capi.INITQ_PARENT), (capi.GAME_OTHELLO, 9, capi.INITQ_PARENT),
+                        (capi.GAME_OTHELLO, capi.EVAL_UNIFORM, 3)]:
+        cfg = capi.default_config(game)
+        cfg.evaluator, cfg.init_q = ev, q
+        assert lib.sprl_create(C.byref(cfg), C.byref(h)) == capi.SPRL_E_INVALID and not h
+    assert capi.INITQ_DROP_PARENT == 2 and capi.EVAL_OTHELLO_HEURISTIC == 3
+
+
 def test_npy_writer_is_byte_identical_to_reference_layout(tmp_path):
     import oracle_py as O
     from sprl_b200.selfplay import write_npy

@@ -2,8 +2,8 @@
 
     python tools/profile_search.py G launches {uniform|hash|ext} rounds_per_launch [warm_rounds]
 
-`ext` is the benchmark's configuration: SPRL_EVAL_EXTERNAL with the traced 2x64 network run by
-LibTorch between search launches (no CUDA graph, so every launch is a plain kernel for ncu);
+`ext` is the benchmark's configuration: SPRL_EVAL_EXTERNAL with the 2x64 network run by the library's
+evaluator between search launches (no CUDA graph, so every launch is a plain kernel for ncu);
 `warm_rounds` search rounds are played first so the profiled launches see mid-game trees."""
 import os
 import sys
@@ -22,10 +22,9 @@ with SP.Engine(capi.GAME_OTHELLO, ev, sims=400, max_batch=8, max_queue=4, num_sl
                rounds_per_launch=rpl) as eng:
     if kind == "ext":
         import torch
-        from sprl_b200.network import make_network, trace_network
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
-        eng.attach_network(trace_network(make_network("othello", 0), torch.device("cuda", 0)), use_cuda_graph=False)
+        from sprl_b200.evalnet import EvalNet
+        from sprl_b200.network import make_network
+        eng.attach_evalnet(EvalNet(make_network("othello", 0), device=0), use_cuda_graph=False)
         eng.set_stream(torch.cuda.current_stream().cuda_stream)
         step = eng._round_with_network
     else:
