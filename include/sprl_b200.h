@@ -231,9 +231,10 @@ int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* sh
 /* ------------------------------------------------------------------ evaluator network
  * The forward pass of the controller's network (src/networks/grid_networks.py:30-80
  * BasicGridNetwork, loaded by networks/GridNetwork.hpp:37-51 and run at :99) as one persistent
- * tcgen05 kernel for boards up to 8x8 (Othello, Go 7x7, Connect Four): conv tower on the tensor
- * cores with the 3xTF32 split (fp32-level accuracy, fp32 accumulate), BatchNorm folded, head FCs in
- * a second kernel.  Larger boards (Go 9x9) keep using the traced module through sprl_forward_fn. */
+ * tcgen05 kernel for boards up to 8x8 (Othello, Go 7x7, Connect Four: two boards per MMA tile) and up
+ * to 128 cells in rows of at most 16 (Go 9x9: one board per tile): conv tower on the tensor cores with
+ * a two-term fp16 split (fp32-level accuracy, fp32 accumulate), BatchNorm folded, head FCs in a second
+ * kernel.  Other shapes keep using the traced module through sprl_forward_fn. */
 typedef struct {
     const float *weight, *bias;                             /* conv: [out, in, 3, 3], [out] */
     const float *bn_weight, *bn_bias, *bn_mean, *bn_var;    /* BatchNorm2d affine + running stats, [out] */

@@ -1,6 +1,7 @@
 // evalnet.cu -- the evaluator network's forward pass as one persistent tcgen05 kernel.
 //
-// Replaces, for boards up to 8x8 (Othello 8x8, Go 7x7, Connect Four 6x7), the LibTorch forward of the reference's traced
+// Replaces, for boards up to 8x8 (Othello 8x8, Go 7x7, Connect Four 6x7; two boards per tile) and for boards of up to
+// 128 cells in rows of at most 16 (Go 9x9; one board per tile), the LibTorch forward of the reference's traced
 // `BasicGridNetwork` (/root/reference/cpp/src/networks/GridNetwork.hpp:99 calling the module
 // of /root/reference/src/networks/grid_networks.py:30-80): conv3x3+BN+ReLU stem, `blocks`
 // residual blocks of two conv3x3+BN, policy head (conv1x1 -> ReLU -> FC) and value head
@@ -73,6 +74,9 @@ constexpr int UNIT_KS = SPRL_EVALNET_UNIT_KSTEPS;      // k-steps (16 input chan
 constexpr int UNIT_BYTES = UNIT_KS * 2 * (6 * CH) * 16; // [K chunk of 8][3 dx x (hi, lo) x 64 rows][8 halfs]: 24 KB = 32 input channels of one dy
 constexpr int MAX_NST = 12;                  // ring stages (as many as shared memory holds)
 constexpr int MAX_LAYERS = 16;
+// linear lattice: neighbours across a warp boundary are exchanged through shared memory,
+// [channel half][double buffer][warp of the quarter][left / right][16 values]
+constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 16 * 4;
 constexpr int HEAD_N = 16;                   // policy channels (2) + value channel (1), padded
 constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the channels
 constexpr int MMA_WARP = EPI_WARPS, PRODUCER_WARP = EPI_WARPS + 1;
@@ -82,6 +86,13 @@ constexpr int BAR1_THREADS = (EPI_WARPS + 1) * 32;   // epilogue warps + MMA war
 #define SPRL_EVALNET_CLUSTER 2
 #endif
 constexpr int CLUSTER = SPRL_EVALNET_CLUSTER;  // CTAs sharing one multicast weight stream
+#ifndef SPRL_EVALNET_ROTATE
+#define SPRL_EVALNET_ROTATE 0
+#endif
+// 1: clusters walk the vertical taps of a layer in different rotations (spreads the L2 reads of the weight stream, but
+// the fp32 accumulation order of a board then depends on which CTA evaluates it).  0: one order everywhere, so a
+// board's outputs do not depend on its row in the batch -- self-play with compact leaf rows stays reproducible.
+constexpr int ROTATE = SPRL_EVALNET_ROTATE;
 #ifndef SPRL_EVALNET_PAIR
 #define SPRL_EVALNET_PAIR 0
 #endif
@@ -118,7 +129,8 @@ struct NetDev {
     const float* vfc1_b;     // [64]
     const float* vfc2_w;     // [64] weights, then the bias
     int n_layers;            // 1 stem + 2*blocks + 1 heads
-    int rows, cols;          // board (<= 8 x 8): cell (r, c) lives at lattice position (r, c) of an 8 x 8 tile half
+    int rows, cols;          // board: cell (r, c) lives at lattice position (r, c) of an 8 x 8 tile half, or ...
+    int linear;              // ... boards wider or taller than 8 (Go 9x9): ONE board per tile, cell r * cols + c = TMEM lane
     int in_planes;
     int in_ksteps;           // ceil(in_planes / 16)
     int actions;
@@ -132,7 +144,7 @@ struct NetDev {
 };
 
 __host__ __device__ inline int smem_bytes_for(int n_layers, int nst) {
-    return OFF_RING + nst * UNIT_SLOT + n_layers * CH * 4 + (3 * nst + 2) * 8 + 16;
+    return OFF_RING + nst * UNIT_SLOT + n_layers * CH * 4 + (3 * nst + 2) * 8 + 16 + XCH_BYTES;
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -335,6 +347,7 @@ __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return un
 // two zero rows first
 __device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 
+template <bool LINEAR>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsigned* __restrict__ d_rows,
           float* __restrict__ logits, float* __restrict__ value) {
@@ -347,7 +360,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     const uint32_t bar_full = s_base + off_bars, bar_empty = bar_full + nst * 8, bar_acc = bar_empty + nst * 8;
     const uint32_t bar_pfull = bar_acc + 8, bar_img = bar_pfull + nst * 8;      // pair mode, used in the leader: peer's half / image
     float* s_bias = reinterpret_cast<float*>(smem + off_bias);
-    const long long n_tiles = (batch + 1) / 2;
+    const long long n_tiles = LINEAR ? batch : (batch + 1) / 2;
     // every CTA of a cluster walks the same number of tiles (the multicast ring is shared);
     // tiles past the end are dummies: zero input, no output
     const long long n_iters = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -404,7 +417,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                     int dy_bytes = 0;
                     for (int u = 0; u < g.units_per_dy; ++u) dy_bytes += unit_bytes(g, u);
                     for (int t = 0; t < g.ndy; ++t) {
-                        const int dyi = (t + cluster_id) % g.ndy;
+                        const int dyi = (t + ROTATE * cluster_id) % g.ndy;
                         const unsigned char* src = layer_src + (size_t)dyi * dy_bytes;
                         for (int u = 0; u < g.units_per_dy; ++u) {
                             const uint32_t bytes = (uint32_t)unit_bytes(g, u);
@@ -454,9 +467,10 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                 const uint32_t d_main = tmem;
                 uint32_t acc = 0;                        // 0 for the layer's very first MMA only
                 for (int t = 0; t < g.ndy; ++t) {
-                    const int dyi = (t + cluster_id) % g.ndy;                    // same rotation as the producer
+                    const int dyi = (t + ROTATE * cluster_id) % g.ndy;           // same order as the producer
                     const int dy = g.ndy == 3 ? dyi - 1 : 0;
-                    const uint32_t a_off = (uint32_t)(16 + 16 * dy);             // in 16-byte slots: two storage rows per board row
+                    // in 16-byte slots: two storage rows per board row, or one row of `cols` cells in the linear lattice
+                    const uint32_t a_off = (uint32_t)(16 + (LINEAR ? net.cols : 16) * dy);
                     for (int u = 0; u < g.units_per_dy; ++u) {
                         const int nks = unit_ksteps(g, u);
                         { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
@@ -508,8 +522,14 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         const int m = (warp & 3) * 32 + lane;                        // cell 0..127 = TMEM lane
         const int half = warp >> 2;                                  // which half of the channels this warp finishes
         const int slot = cell_slot(m);
-        const int g8 = m >> 3, c = m & 7, r = g8 >> 1, b = g8 & 1;
+        const int g8 = m >> 3;
+        const int r = LINEAR ? m / net.cols : g8 >> 1, c = LINEAR ? m - r * net.cols : m & 7, b = LINEAR ? 0 : g8 & 1;
         const bool valid = r < net.rows && c < net.cols;             // lattice positions outside the board stay zero
+        // linear lattice: the left / right neighbour of lane 0 / 31 lives in another warp of the same channel half
+        float* xch = reinterpret_cast<float*>(smem + off_tmem + 16) + half * (2 * 4 * 2 * 16);
+        const int wq = warp & 3;
+        const bool xl = LINEAR && lane == 0 && wq > 0, xr = LINEAR && lane == 31 && wq < 3;
+        uint32_t xbuf = 0;
         const int cell = r * net.cols + c;
         const bool has_left = c > 0, has_right = c + 1 < net.cols;
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -521,7 +541,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
-            const long long board = tile * 2 + b;
+            const long long board = LINEAR ? tile : tile * 2 + b;
             // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split).  The stem
             // has few input planes, so its vertical taps are folded into K: image channel dyi * planes + p of a
             // cell holds plane p of the cell one row above / at / below it, and the stem becomes a single-dy layer
@@ -561,11 +581,28 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                         float o[16], v[16], w[16];
                         tmem_ld16(t_lane + CH + q * 16, o);                                          // dx = 0
                         tmem_ld16x2(t_lane + q * 16, t_lane + 2 * CH + q * 16, v, w);                // dx = -1, dx = +1
+                        if (LINEAR) {
+                            // publish what the neighbouring warps need: lane 31's Z_-1 (for the next warp's lane 0)
+                            // and lane 0's Z_+1 (for the previous warp's lane 31); double-buffered per iteration
+                            float* mine = xch + (xbuf * 4 + wq) * 32;
+                            if (lane == 31) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) mine[i] = v[i];
+                            }
+                            if (lane == 0) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) mine[16 + i] = w[i];
+                            }
+                            if (half == 0) named_bar(2, 128); else named_bar(3, 128);   // constant ids: the kernel reserves 4 barriers
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                            float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                            if (xl) zl = xch[(xbuf * 4 + wq - 1) * 32 + i];
+                            if (xr) zr = xch[(xbuf * 4 + wq + 1) * 32 + 16 + i];
                             o[i] = fmaf(zl, lmask, fmaf(zr, rmask, o[i]));
                         }
+                        xbuf ^= 1u;
                         if (add_res) {                                                               // block input (image units), kept in TMEM
                             tmem_ld16(t_lane + RES_COL + q * 16, v);
 #pragma unroll
@@ -624,7 +661,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
 // ---- heads: policy_fc and value_fc1/fc2 over the 1x1-conv activations k_evalnet left in HBM ----
 // 64 boards per CTA, weights staged once in shared memory, 4 boards x 4 outputs per thread.
 constexpr int HB = 64;                        // boards per CTA
-constexpr int HP_STRIDE = 68;                 // policy weight row stride in floats (65 actions padded for float4 loads)
+constexpr int HP_STRIDE = 84;                 // policy weight row stride in floats (up to 82 actions, padded for float4 loads)
 
 __global__ void __launch_bounds__(256)
 k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float* __restrict__ logits, float* __restrict__ value) {
@@ -635,7 +672,7 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     float* wp = hs;                           // [K][HP_STRIDE]
     float* wv = wp + K * HP_STRIDE;           // [cells][64]
     float* x = wv + cells * 64;               // [HB][IN]
-    float* hid = x + HB * IN;                 // [HB][64]
+    float* hid = x + HB * IN;                 // [HB][65]
     const int t = threadIdx.x;
     for (int i = t; i < K * HP_STRIDE; i += 256) { const int k = i / HP_STRIDE, a = i - k * HP_STRIDE; wp[i] = a < A ? net.pfc_wt[k * A + a] : 0.0f; }
     for (int i = t; i < cells * 64; i += 256) wv[i] = net.vfc1_wt[i];
@@ -723,18 +760,19 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) hid[(4 * bg + i) * 64 + 4 * ag + j] = fmaxf(acc[i][j] + net.vfc1_b[4 * ag + j], 0.0f);
+                for (int j = 0; j < 4; ++j) hid[(4 * bg + i) * 65 + 4 * ag + j] = fmaxf(acc[i][j] + net.vfc1_b[4 * ag + j], 0.0f);
         }
         __syncthreads();
         if (t < nb) {   // value_fc2 + tanh
             float s = net.vfc2_w[64];
-            for (int j = 0; j < 64; ++j) { const int jj = (j + t) & 63; s = fmaf(net.vfc2_w[jj], hid[t * 64 + jj], s); }   // rotated start: no bank conflicts
+            // same summation order for every board (its outputs must not depend on its row); rows of 65 floats: no bank conflicts
+            for (int j = 0; j < 64; ++j) s = fmaf(net.vfc2_w[j], hid[t * 65 + j], s);
             value[b0 + t] = tanhf(s);
         }
     }
 }
 
-static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + HB * (pc + 1) * cells + HB * 64) * sizeof(float); }
+static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + HB * (pc + 1) * cells + HB * 65) * sizeof(float); }
 
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
 // Power-of-two shift that brings the largest |w| of a layer into (2^9, 2^10]: fp16 keeps 11 significant bits
@@ -907,6 +945,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     e->dev.n_layers = L;
     e->dev.rows = p->rows;
     e->dev.cols = p->cols;
+    e->dev.linear = (p->rows > 8 || p->cols > 8) ? 1 : 0;
     e->dev.in_planes = P;
     e->dev.in_ksteps = in_k / KSTEP_CH;
     e->dev.actions = A;
@@ -916,8 +955,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
 
 static int validate(const sprl_network_params* p) {
     if (!p) return fail(SPRL_E_INVALID, "null network parameters");
-    if (p->rows < 1 || p->cols < 1 || p->rows > 8 || p->cols > 8)
-        return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles boards up to 8x8 (two per MMA); %dx%d boards run through the LibTorch module", p->rows, p->cols);
+    if (p->rows < 1 || p->cols < 1 || p->cols > 16 || p->rows * p->cols > TILE_M)
+        return fail(SPRL_E_INVALID, "the tcgen05 evaluator tiles boards up to 8x8 (two per MMA) or up to %d cells with rows of at most 16 (one per MMA); got %dx%d", TILE_M, p->rows, p->cols);
     if (p->channels != CH) return fail(SPRL_E_INVALID, "tower width must be %d channels, got %d", CH, p->channels);
     if (p->blocks < 0 || 2 + 2 * p->blocks > MAX_LAYERS) return fail(SPRL_E_INVALID, "unsupported number of residual blocks %d", p->blocks);
     if (p->in_planes < 1 || 3 * p->in_planes > CH) return fail(SPRL_E_INVALID, "unsupported number of input planes %d (at most %d)", p->in_planes, CH / 3);
@@ -955,9 +994,11 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err)); }
     if (prop.major != 10) { delete e; return fail(SPRL_E_NOGPU, "the tcgen05 evaluator needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
     e->sm_count = prop.multiProcessorCount;
-    err = cudaFuncSetAttribute(k_evalnet, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    err = cudaFuncSetAttribute(k_evalnet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
-    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes(params->policy_channels, 64));
+    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)heads_smem_bytes(params->policy_channels, std::max(64, params->rows * params->cols)));
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     rc = pack_and_upload(e, params);
     if (rc) { e->release(); delete e; return rc; }
@@ -1002,7 +1043,7 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
         e->head_cap = batch;
     }
     e->dev.head_act = e->head_act;
-    const long long tiles = (batch + 1) / 2;
+    const long long tiles = e->dev.linear ? batch : (batch + 1) / 2;
     const int max_grid = e->sm_count * CTAS_PER_SM / CLUSTER * CLUSTER;
     const int grid = (int)std::min<long long>((tiles + CLUSTER - 1) / CLUSTER * CLUSTER, max_grid);
     cudaLaunchConfig_t cfg = {};
@@ -1015,7 +1056,8 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
     attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, k_evalnet, e->dev, d_in, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
+    err = e->dev.linear ? cudaLaunchKernelEx(&cfg, k_evalnet<true>, e->dev, d_in, (long long)batch, (const unsigned*)d_rows, d_logits, d_value)
+                        : cudaLaunchKernelEx(&cfg, k_evalnet<false>, e->dev, d_in, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
     e->launches += 1;
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {

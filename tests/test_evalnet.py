@@ -29,8 +29,8 @@ def randomized(net, seed):
 def test_evalnet_rejects_unsupported_shapes():
     lib = capi.load()
     h = C.c_void_p()
-    # Go 9x9 does not fit the 8x8 lattice: stays on the TorchScript path
-    p, keep = network_params(make_network("go9", 0).state_dict(), rows=9, cols=9)
+    # more than 128 cells do not fit one MMA tile
+    p, keep = network_params(make_network("go9", 0).state_dict(), rows=12, cols=12)
     assert lib.sprl_evalnet_create(0, C.byref(p), C.byref(h)) == capi.SPRL_E_INVALID and not h
     assert b"8x8" in lib.sprl_last_error()
     # wrong tower width
@@ -75,9 +75,10 @@ def test_evalnet_matches_fp64_forward(batch, blocks, planes):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,rows,cols,batch", [("c4", 6, 7, 131), ("go7", 7, 7, 77)])
+@pytest.mark.parametrize("kind,rows,cols,batch", [("c4", 6, 7, 131), ("go7", 7, 7, 77), ("go9", 9, 9, 203)])
 def test_evalnet_smaller_boards(kind, rows, cols, batch):
-    """Connect Four (6x7, 7 actions) and Go 7x7 (17 planes, 6 blocks, 50 actions) on the 8x8 lattice."""
+    """Connect Four (6x7, 7 actions) and Go 7x7 (17 planes, 6 blocks, 50 actions) on the 8x8 lattice; Go 9x9 (82 actions)
+    on the linear lattice, one board per tile, neighbours across warp boundaries exchanged through shared memory."""
     net = randomized(make_network(kind, 3), 9)
     planes = net.conv.in_channels
     x = (torch.rand(batch, planes, rows, cols) > 0.5).float()
@@ -152,3 +153,38 @@ def test_selfplay_with_evalnet_tracks_libtorch():
     for s, d, o in ((sa, da, oa), (sb, db, ob)):
         assert s.shape[0] == d.shape[0] == o.shape[0] and s.shape[0] % 8 == 0
         assert np.allclose(d.sum(1), 1.0, atol=1e-5) and set(np.unique(o)) <= {-1.0, 0.0, 1.0}
+
+
+@pytest.mark.gpu
+def test_evalnet_outputs_do_not_depend_on_the_row():
+    """The engine hands leaf rows out in no fixed order (one atomicAdd per tree), so reproducible self-play needs
+    a board's outputs to be bit-identical wherever it sits in the batch, whoever its tile partner is."""
+    net = randomized(make_network("othello", 1), 4)
+    ev = EvalNet(net, device=0)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(1501, 3, 8, 8, generator=g) > 0.5).float().cuda()
+    perm = torch.randperm(x.shape[0], generator=g).cuda()
+    l0, v0 = ev(x)
+    l1, v1 = ev(x[perm])
+    assert torch.equal(l0[perm], l1) and torch.equal(v0[perm], v1)
+    l2, v2 = ev(x[:77])                                       # a different grid size, other CTAs
+    assert torch.equal(l0[:77], l2) and torch.equal(v0[:77], v2)
+    ev.status()
+
+
+@pytest.mark.gpu
+def test_selfplay_through_the_evaluator_is_reproducible():
+    """Same seed, same network: identical samples, although leaf rows are handed out by atomics in a different order."""
+    import numpy as np
+    from sprl_b200 import selfplay as SP
+    outs = []
+    for _ in range(2):
+        ev = EvalNet(make_network("othello", 0), device=0)
+        with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, seed=5, sims=64, max_batch=8, max_queue=4, num_slots=96,
+                       max_games=160) as eng:
+            eng.attach_evalnet(ev, use_cuda_graph=True)
+            outs.append(eng.run_iteration(160))
+        ev.close()
+    assert outs[0][0].shape[0] > 160 * 8 * 20
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

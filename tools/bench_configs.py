@@ -1,7 +1,7 @@
 """Throughput of the other BASELINE.json configurations on one B200 (bench.py measures config 3/4):
   config 2: Othello environment only -- perft(1..11) and random-rollout sweep (steps/s);
   config 1/5 shapes: Connect Four, Go 7x7 and Go 9x9 self-play with the reference's network shapes
-  (tcgen05 evaluator for boards up to 8x8; Go 9x9 runs the traced module through LibTorch).
+  (library evaluator on tcgen05; SPRL_BENCH_EVALUATOR=libtorch runs the traced module through LibTorch instead).
 Prints one JSON object per line."""
 import json
 import os
@@ -42,7 +42,7 @@ for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5
                                               (capi.GAME_GO9, "go9", 400, 16, 8, 0.2, 1024)):
     net = make_network(kind, 0)
     gi = capi.game_info(game)
-    library = gi.rows <= 8 and gi.cols <= 8
+    library = os.environ.get("SPRL_BENCH_EVALUATOR", "evalnet") != "libtorch"
     with SP.Engine(game, capi.EVAL_EXTERNAL, seed=0, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=alpha,
                    num_slots=slots, max_games=slots * 8) as eng:
         if library:
