@@ -140,7 +140,7 @@ struct NetDev {
     unsigned long long* error_flag;   // [0] pipeline barrier time-out, [1] an activation left the fp16-split range
     float inv_scale[MAX_LAYERS];      // 2^-(ACT_SHIFT + weight shift of the layer): accumulator -> real units
     long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
-    int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue
+    int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue, 6 = MMAs but no conv epilogue
 };
 
 __host__ __device__ inline int smem_bytes_for(int n_layers, int nst) {
@@ -459,7 +459,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                 const int n1 = g.ndx * g.n;                                      // output columns of one MMA
                 const int nb = PAIR ? n1 / 2 : n1;                               // weight rows held by this CTA
                 const uint32_t idesc = instr_desc_f16(PAIR ? 2 * TILE_M : TILE_M, n1);
-                const bool lo_pass = net.debug != 1 && net.debug < 3, hi_pass = net.debug < 3;
+                const bool hi_pass = net.debug < 3 || net.debug == 6, lo_pass = net.debug != 1 && hi_pass;
                 const uint32_t b_lbo = (uint32_t)(2 * nb) * 16u, b_kstep = (2u * b_lbo) >> 4, b_lo_off = ((uint32_t)nb * 16u) >> 4;
                 const uint64_t a_hi0 = smem_desc(s_base + OFF_AHI, CG_STRIDE, 128), a_lo0 = smem_desc(s_base + OFF_ALO, CG_STRIDE, 128);
                 const uint64_t b0 = smem_desc(s_base + OFF_RING, b_lbo, 128);
