@@ -347,6 +347,14 @@ __host__ __device__ inline int unit_bytes(const LayerGeom& g, int u) { return un
 // two zero rows first
 __device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 
+// Per-role cycle counters (reported by sprl_evalnet_status when SPRL_EVALNET_TIMING is set) are compiled in only with
+// -DSPRL_EVALNET_TIMERS: a clock read costs tens of cycles and the MMA issuer runs ~200 of them per tile.
+#ifdef SPRL_EVALNET_TIMERS
+#define NOW() clock64()
+#else
+#define NOW() 0LL
+#endif
+
 template <bool LINEAR>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsigned* __restrict__ d_rows,
@@ -403,7 +411,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         // ===== weight producer =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            long long t_wait = 0, t0 = clock64();
+            long long t_wait = 0, t0 = NOW();
             for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
                 // Every tile needs the whole 1.2 MB of weights (shared memory has no room to keep
                 // them).  The CTAs of a cluster share ONE stream: each loads 1/CLUSTER of every unit
@@ -421,7 +429,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                         const unsigned char* src = layer_src + (size_t)dyi * dy_bytes;
                         for (int u = 0; u < g.units_per_dy; ++u) {
                             const uint32_t bytes = (uint32_t)unit_bytes(g, u);
-                            { long long a = clock64(); mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1); t_wait += clock64() - a; }
+                            { long long a = NOW(); mbar_wait(bar_empty + 8 * s, ph ^ 1u, net.error_flag, 1); t_wait += NOW() - a; }
                             const uint32_t slice = bytes / CLUSTER;
                             if (PAIR) {                                     // this CTA's half of the rows, kept to itself
                                 mbar_expect_tx(bar_full + 8 * s, slice);
@@ -438,7 +446,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                     layer_src += (size_t)g.ndy * dy_bytes;
                 }
             }
-            if (net.timing) { net.timing[blockIdx.x * 12 + 8] = t_wait; net.timing[blockIdx.x * 12 + 9] = clock64() - t0; }
+            if (net.timing) { net.timing[blockIdx.x * 12 + 8] = t_wait; net.timing[blockIdx.x * 12 + 9] = NOW() - t0; }
         }
         __syncwarp();
     } else if (warp == MMA_WARP) {
@@ -446,14 +454,14 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         uint32_t s = 0, ph = 0, img_phase = 0;
         const bool leader = !PAIR || crank == 0;
         const uint32_t lead_pfull = PAIR ? map_to_cta(bar_pfull, 0) : 0u, lead_img = PAIR ? map_to_cta(bar_img, 0) : 0u;
-        long long t_bar = 0, t_full = 0, t_issue = 0, t_commit = 0, t0 = clock64();
+        long long t_bar = 0, t_full = 0, t_issue = 0, t_commit = 0, t0 = NOW();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer) {
                 const LayerGeom g = layer_geom(layer, n_layers, net.in_ksteps);
-                { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }   // the layer's input image is complete, the accumulators are drained
+                { long long a = NOW(); named_bar(1, BAR1_THREADS); t_bar += NOW() - a; }   // the layer's input image is complete, the accumulators are drained
                 if (PAIR) {                                                      // ... in the peer CTA as well
                     if (!leader) mbar_arrive_cluster(lead_img);
-                    else { long long a = clock64(); mbar_wait_cluster(bar_img, img_phase, net.error_flag, 4); img_phase ^= 1u; t_bar += clock64() - a; }
+                    else { long long a = NOW(); mbar_wait_cluster(bar_img, img_phase, net.error_flag, 4); img_phase ^= 1u; t_bar += NOW() - a; }
                 }
                 tc_fence_after();
                 const int n1 = g.ndx * g.n;                                      // output columns of one MMA
@@ -473,15 +481,15 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                     const uint32_t a_off = (uint32_t)(16 + (LINEAR ? net.cols : 16) * dy);
                     for (int u = 0; u < g.units_per_dy; ++u) {
                         const int nks = unit_ksteps(g, u);
-                        { long long a = clock64(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += clock64() - a; }
+                        { long long a = NOW(); mbar_wait(bar_full + 8 * s, ph, net.error_flag, 2); t_full += NOW() - a; }
                         if (PAIR && !leader) {                   // relay: the leader may read this CTA's half now
                             mbar_arrive_cluster(lead_pfull + 8 * s);
                             if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                             continue;
                         }
-                        if (PAIR) { long long a = clock64(); mbar_wait_cluster(bar_pfull + 8 * s, ph, net.error_flag, 5); t_full += clock64() - a; }
+                        if (PAIR) { long long a = NOW(); mbar_wait_cluster(bar_pfull + 8 * s, ph, net.error_flag, 5); t_full += NOW() - a; }
                         tc_fence_after();
-                        const long long t_i0 = clock64();
+                        const long long t_i0 = NOW();
                         const uint64_t bd = b0 + s * (UNIT_SLOT >> 4);
                         const uint64_t ah = a_hi0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP, al = a_lo0 + a_off + (uint32_t)(UNIT_KS * u) * A_KSTEP;
                         if (hi_pass) {
@@ -502,10 +510,10 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                                 }
                             }
                         }
-                        const long long t_i1 = clock64();
+                        const long long t_i1 = NOW();
                         if (PAIR) umma_commit_pair(bar_empty + 8 * s);      // both producers may refill their halves
                         else umma_commit_multicast(bar_empty + 8 * s, CMASK);   // every CTA's producer learns that this CTA is done with the unit
-                        t_issue += t_i1 - t_i0; t_commit += clock64() - t_i1;
+                        t_issue += t_i1 - t_i0; t_commit += NOW() - t_i1;
                         if (++s == (uint32_t)nst) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -515,7 +523,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
             }
         }
         if (lane == 0 && net.timing) {
-            net.timing[blockIdx.x * 12 + 0] = t_bar; net.timing[blockIdx.x * 12 + 1] = t_full; net.timing[blockIdx.x * 12 + 2] = clock64() - t0; net.timing[blockIdx.x * 12 + 3] = t_issue; net.timing[blockIdx.x * 12 + 10] = t_commit;
+            net.timing[blockIdx.x * 12 + 0] = t_bar; net.timing[blockIdx.x * 12 + 1] = t_full; net.timing[blockIdx.x * 12 + 2] = NOW() - t0; net.timing[blockIdx.x * 12 + 3] = t_issue; net.timing[blockIdx.x * 12 + 10] = t_commit;
         }
     } else {
         // ===== epilogue warps: cell m = TMEM lane m =====
@@ -539,7 +547,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         const float vmask = valid ? 1.0f : 0.0f, lmask = has_left ? 1.0f : 0.0f, rmask = has_right ? 1.0f : 0.0f;
         const int cells = net.rows * net.cols, planes = net.in_planes;
         uint32_t acc_phase = 0;
-        long long t_bar = 0, t_acc = 0, t_head = 0, t0 = clock64();
+        long long t_bar = 0, t_acc = 0, t_head = 0, t0 = NOW();
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = LINEAR ? tile : tile * 2 + b;
             // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split).  The stem
@@ -562,9 +570,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
             proxy_fence();
             for (int layer = 0; layer < n_layers; ++layer) {
                 tc_fence_before();
-                { long long a = clock64(); named_bar(1, BAR1_THREADS); t_bar += clock64() - a; }
-                { long long a = clock64(); mbar_wait(bar_acc, acc_phase, net.error_flag, 3); t_acc += clock64() - a; }
-                const long long t_layer = clock64();
+                { long long a = NOW(); named_bar(1, BAR1_THREADS); t_bar += NOW() - a; }
+                { long long a = NOW(); mbar_wait(bar_acc, acc_phase, net.error_flag, 3); t_acc += NOW() - a; }
+                const long long t_layer = NOW();
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float* bias = s_bias + layer * CH;
@@ -635,14 +643,14 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                         for (int j = 0; j < 3; ++j)
                             if (j <= pc) dst[j * cells + cell] = fmaxf(v[j] * inv_scale + bias[j], 0.0f);
                     }
-                    t_head += clock64() - t_layer;
+                    t_head += NOW() - t_layer;
                 }
             }
         }
         if (mx > HALF_MAX) atomicExch(net.error_flag + 1, 1ULL);
         if (threadIdx.x == 0 && net.timing) {
             net.timing[blockIdx.x * 12 + 4] = t_bar; net.timing[blockIdx.x * 12 + 5] = t_acc; net.timing[blockIdx.x * 12 + 6] = t_head;
-            net.timing[blockIdx.x * 12 + 7] = clock64() - t0;
+            net.timing[blockIdx.x * 12 + 7] = NOW() - t0;
         }
     }
     if (threadIdx.x == 0 && net.timing) {
