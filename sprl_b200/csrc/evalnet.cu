@@ -39,11 +39,18 @@
 //     (The reference evaluates in fp32; a single fp16/TF32 pass would lose 13 mantissa bits.)
 //   * Weights (BN folded on the host in double, split hi/lo, pre-arranged as K-major UMMA
 //     operands per tap, W_hi and W_lo stacked along N so that A_hi is read once for both) stream
-//     from L2 through a ring of 24 KB units (32 input channels of one vertical offset) filled by cp.async.bulk (multicast to the CTAs of a
-//     cluster) + mbarrier complete_tx; tcgen05.commit frees a unit.
+//     from L2 through a ring of 24 KB units (32 input channels of one vertical offset) filled by
+//     cp.async.bulk (multicast to the CTAs of a cluster) + mbarrier complete_tx; tcgen05.commit frees a unit.
 //   * Warp roles: warps 0-7 = epilogue (TMEM -> registers -> shuffles/bias/residual/ReLU ->
 //     hi/lo -> activation image; two warps per TMEM lane quarter, half of the channels each),
 //     warp 8 = MMA issuer, warp 9 = weight producer.
+//   * The stem (3 or 17 input planes) folds its three vertical taps into K (image channel dy * planes + p);
+//     boards wider than 8 (Go 9x9) use the LINEAR lattice (k_evalnet<true>): one board per tile, cell
+//     r * cols + c = TMEM lane, vertical taps = descriptor shifts by `cols` slots, and the left / right
+//     neighbours that live in another warp are exchanged through a small shared-memory scratch.
+//   * A board's outputs do not depend on its row in the batch or on its tile partner (every CTA accumulates
+//     in the same order), and the batch size may be read on the device (d_rows): the search kernel hands leaf
+//     rows out by atomics and self-play stays reproducible.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
