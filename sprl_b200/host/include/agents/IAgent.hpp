@@ -1,0 +1,6 @@
+// agents/IAgent.hpp -- include-path compatibility with the reference's cpp/src/agents/IAgent.hpp: the
+// declarations a worker or match main uses live in sprl/veneer.hpp (a handle layer over libsprl_b200.so).
+#ifndef SPRL_B200_COMPAT_AGENTS_IAGENT_HPP
+#define SPRL_B200_COMPAT_AGENTS_IAGENT_HPP
+#include "../sprl/veneer.hpp"
+#endif

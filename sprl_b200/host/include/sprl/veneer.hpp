@@ -14,6 +14,9 @@
 //   SPRL::waitModelPath, SPRL::runWorker<NN,Impl,R,C,H,A>(...)   selfplay/GridWorker.hpp:35-55,84-91
 //   SPRL::playMatch<Impl,State,A>(...)                the game loop of Evaluate.cpp:93-157 (UCTNetworkAgent::act /
 //                                                     opponentAct inside playGame), all games concurrently
+//   SPRL::UCTTree, IAgent, UCTNetworkAgent, playGame  uct/UCTTree.hpp:38-60, agents/*.hpp, evaluate/play.hpp:24-69 as
+//                                                     handles: the reference's Evaluate.cpp compiles unchanged and plays
+//                                                     one game per playGame call on the GPU (playMatch is the batched form)
 //
 // What changes underneath: runIteration plays all `numGames` games CONCURRENTLY on one GPU
 // (one warp per tree) instead of one after the other on a CPU core; the evaluator is a handle
@@ -25,10 +28,12 @@
 
 #include "../../../../include/sprl_b200.h"
 
+#include <array>
 #include <chrono>
 #include <cstdint>
 #include <filesystem>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -49,20 +54,22 @@ template <int ACTION_SIZE> struct GameActionDist { static constexpr int SIZE = A
 template <int BOARD_SIZE, int HISTORY_SIZE> struct GridState {
     static constexpr int BOARD = BOARD_SIZE, HISTORY = HISTORY_SIZE;
 };
+// games/GameNode.hpp:50-200: positions live on the device; on the host a game node is a tag that names the rules
+template <typename ImplNode, typename State, int ACTION_SIZE> struct GameNode {};
 
 // ---- games: constants of games/*.hpp and tags selecting the device rules ----
 constexpr int OTH_BOARD_WIDTH = 8;
 constexpr int OTH_BOARD_SIZE = OTH_BOARD_WIDTH * OTH_BOARD_WIDTH;
 constexpr int OTH_ACTION_SIZE = OTH_BOARD_SIZE + 1;
 constexpr int OTH_HISTORY_SIZE = 1;
-struct OthelloNode { static constexpr int GAME = SPRL_GAME_OTHELLO; };
+struct OthelloNode : GameNode<OthelloNode, GridState<OTH_BOARD_SIZE, OTH_HISTORY_SIZE>, OTH_ACTION_SIZE> { static constexpr int GAME = SPRL_GAME_OTHELLO; };
 
 constexpr int C4_NUM_ROWS = 6;
 constexpr int C4_NUM_COLS = 7;
 constexpr int C4_BOARD_SIZE = C4_NUM_ROWS * C4_NUM_COLS;
 constexpr int C4_ACTION_SIZE = C4_NUM_COLS;
 constexpr int C4_HISTORY_SIZE = 1;
-struct ConnectFourNode { static constexpr int GAME = SPRL_GAME_C4; };
+struct ConnectFourNode : GameNode<ConnectFourNode, GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> { static constexpr int GAME = SPRL_GAME_C4; };
 
 #ifndef SPRL_GO_BOARD_WIDTH
 #define SPRL_GO_BOARD_WIDTH 7                 // games/GoNode.hpp:16; 9 selects the 9x9 / komi 7.5 rules
@@ -71,7 +78,7 @@ constexpr int GO_BOARD_WIDTH = SPRL_GO_BOARD_WIDTH;
 constexpr int GO_BOARD_SIZE = GO_BOARD_WIDTH * GO_BOARD_WIDTH;
 constexpr int GO_ACTION_SIZE = GO_BOARD_SIZE + 1;
 constexpr int GO_HISTORY_SIZE = 8;
-struct GoNode { static constexpr int GAME = (GO_BOARD_WIDTH == 9) ? SPRL_GAME_GO9 : SPRL_GAME_GO7; };
+struct GoNode : GameNode<GoNode, GridState<GO_BOARD_SIZE, GO_HISTORY_SIZE>, GO_ACTION_SIZE> { static constexpr int GAME = (GO_BOARD_WIDTH == 9) ? SPRL_GAME_GO9 : SPRL_GAME_GO7; };
 
 // ---- evaluators ----
 // The reference's INetwork::evaluate(states, masks) is a host call per leaf batch.  Here an
@@ -228,11 +235,14 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
 // Evaluate.cpp builds them: Dirichlet noise on, eps 0.25, alpha 0.1, default uWeight 1.0.
 struct MatchResult { int64_t wins0, wins1, draws; std::vector<int8_t> winners; std::vector<int32_t> moves; };
 
+struct MatchSearch { float dirEps = 0.25f, dirAlpha = 0.1f, uWeight = 1.0f; bool addNoise = true; };     // Evaluate.cpp:95-111
+
 template <typename ImplNode, typename State, int ACTION_SIZE>
-MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACTION_SIZE>* network1, int numGames,
-                      int numTraversals, int maxBatchSize, int maxQueueSize,
-                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer0, InitQ initQ0,
-                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer1, InitQ initQ1) {
+MatchResult runMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACTION_SIZE>* network1, int numGames,
+                     int numTraversals, int maxBatchSize, int maxQueueSize,
+                     ISymmetrizer<State, ACTION_SIZE>* symmetrizer0, InitQ initQ0,
+                     ISymmetrizer<State, ACTION_SIZE>* symmetrizer1, InitQ initQ1,
+                     const MatchSearch& search, uint64_t firstGame, uint64_t gameStride) {
     const DeviceOptions& opt = deviceOptions();
     INetwork<State, ACTION_SIZE>* nets[2] = { network0, network1 };
     sprl_agent_config agents[2] = {
@@ -247,11 +257,11 @@ MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, AC
     cfg.num_slots = 2 * pairs;
     cfg.max_games = numGames;
     cfg.sims = numTraversals; cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
-    cfg.dir_eps = 0.25f; cfg.dir_alpha = 0.1f; cfg.u_weight = 1.0f; cfg.add_noise = 1;     // Evaluate.cpp:95-111
+    cfg.dir_eps = search.dirEps; cfg.dir_alpha = search.dirAlpha; cfg.u_weight = search.uWeight; cfg.add_noise = search.addNoise ? 1 : 0;
     sprl_engine* e = nullptr;
     check(sprl_create(&cfg, &e));
     struct Guard { sprl_engine* e; ~Guard() { sprl_destroy(e); } } guard { e };
-    check(sprl_set_game_stride(e, opt.gameStride));
+    check(sprl_set_game_stride(e, gameStride));
     sprl_game_info gi;
     check(sprl_game_info_get(ImplNode::GAME, &gi));
 
@@ -287,12 +297,79 @@ MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, AC
         }
         return 0;
     };
-    check(sprl_run_match(e, agents, opt.firstGame, numGames, external ? fwd : nullptr, &ctx));
+    check(sprl_run_match(e, agents, firstGame, numGames, external ? fwd : nullptr, &ctx));
     MatchResult r { 0, 0, 0, std::vector<int8_t>((size_t)numGames), std::vector<int32_t>((size_t)numGames) };
     int64_t wins[2] = { 0, 0 };
     check(sprl_match_results(e, numGames, r.winners.data(), r.moves.data(), nullptr, wins, &r.draws));
     r.wins0 = wins[0]; r.wins1 = wins[1];
     return r;
+}
+
+template <typename ImplNode, typename State, int ACTION_SIZE>
+MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACTION_SIZE>* network1, int numGames,
+                      int numTraversals, int maxBatchSize, int maxQueueSize,
+                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer0, InitQ initQ0,
+                      ISymmetrizer<State, ACTION_SIZE>* symmetrizer1, InitQ initQ1) {
+    return runMatch<ImplNode, State, ACTION_SIZE>(network0, network1, numGames, numTraversals, maxBatchSize, maxQueueSize,
+                                                  symmetrizer0, initQ0, symmetrizer1, initQ1, MatchSearch {},
+                                                  deviceOptions().firstGame, deviceOptions().gameStride);
+}
+
+// ---- UCTTree / IAgent / UCTNetworkAgent / playGame as the reference spells them ------------------------
+// uct/UCTTree.hpp:38-60: a tree is described by its construction arguments; the nodes live in device slabs.
+template <typename ImplNode, typename State, int ACTION_SIZE>
+class UCTTree {
+public:
+    UCTTree(std::unique_ptr<ImplNode> gameRoot, float dirEps, float dirAlpha, InitQ initQMethod,
+            ISymmetrizer<State, ACTION_SIZE>* symmetrizer, bool addNoise = true)
+        : dirEps(dirEps), dirAlpha(dirAlpha), initQMethod(initQMethod), symmetrizer(symmetrizer), addNoise(addNoise) { (void)gameRoot; }
+    float dirEps, dirAlpha;
+    InitQ initQMethod;
+    ISymmetrizer<State, ACTION_SIZE>* symmetrizer;
+    bool addNoise;
+};
+
+template <typename ImplNode, typename State, int ACTION_SIZE>
+class IAgent {                                                       // agents/IAgent.hpp:16-38
+public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
+    virtual ~IAgent() = default;
+};
+
+template <typename ImplNode, typename State, int ACTION_SIZE>
+class UCTNetworkAgent : public IAgent<ImplNode, State, ACTION_SIZE> { // agents/UCTNetworkAgent.hpp:21-40
+public:
+    UCTNetworkAgent(INetwork<State, ACTION_SIZE>* network, UCTTree<ImplNode, State, ACTION_SIZE>* tree,
+                    int numTraversals, int maxBatchSize, int maxQueueSize)
+        : network(network), tree(tree), numTraversals(numTraversals), maxBatchSize(maxBatchSize), maxQueueSize(maxQueueSize) {}
+    INetwork<State, ACTION_SIZE>* network;
+    UCTTree<ImplNode, State, ACTION_SIZE>* tree;
+    int numTraversals, maxBatchSize, maxQueueSize;
+};
+
+// evaluate/play.hpp:24-69: one game from the start position between agents[0] (Player ZERO) and agents[1]; returns the
+// winner.  Both agents must be UCTNetworkAgents with the same search budget and noise parameters (as Evaluate.cpp builds
+// them); every call plays a fresh game stream.
+template <typename ImplNode, typename State, int ACTION_SIZE>
+Player playGame(GameNode<ImplNode, State, ACTION_SIZE>* rootNode, std::array<IAgent<ImplNode, State, ACTION_SIZE>*, 2> agents,
+                bool verbose = false) {
+    (void)rootNode; (void)verbose;
+    using Agent = UCTNetworkAgent<ImplNode, State, ACTION_SIZE>;
+    Agent* a0 = dynamic_cast<Agent*>(agents[0]);
+    Agent* a1 = dynamic_cast<Agent*>(agents[1]);
+    if (!a0 || !a1) throw EngineError(SPRL_E_INVALID, "playGame: both agents must be UCTNetworkAgents (interactive agents are out of scope)");
+    if (a0->numTraversals != a1->numTraversals || a0->maxBatchSize != a1->maxBatchSize || a0->maxQueueSize != a1->maxQueueSize ||
+        a0->tree->dirEps != a1->tree->dirEps || a0->tree->dirAlpha != a1->tree->dirAlpha || a0->tree->addNoise != a1->tree->addNoise)
+        throw EngineError(SPRL_E_INVALID, "playGame: the two agents must share the search budget and the noise parameters");
+    static uint64_t gamesPlayed = 0;
+    MatchSearch search;
+    search.dirEps = a0->tree->dirEps; search.dirAlpha = a0->tree->dirAlpha; search.addNoise = a0->tree->addNoise;
+    // an even game id gives Player ZERO to the first agent (sprl_match_begin)
+    MatchResult r = runMatch<ImplNode, State, ACTION_SIZE>(a0->network, a1->network, 1, a0->numTraversals, a0->maxBatchSize,
+                                                           a0->maxQueueSize, a0->tree->symmetrizer, a0->tree->initQMethod,
+                                                           a1->tree->symmetrizer, a1->tree->initQMethod, search,
+                                                           deviceOptions().firstGame + 2 * gamesPlayed++, 1);
+    return static_cast<Player>(r.winners[0]);
 }
 
 // ---- waitModelPath / runWorker (selfplay/GridWorker.hpp:35-55,84-198) ------------------------

@@ -27,3 +27,9 @@ for f in ("out1.txt", "out2.txt", "out3.txt", "out4.txt"):
     print(f, m.group(0))
 PY
 echo "evaluate smoke ok"
+# the REFERENCE's own Evaluate.cpp, compiled unchanged against the veneer (make -C sprl_b200/host dropin): one game per playGame call
+REF_BIN=$ROOT/sprl_b200/host/bin/ref_Evaluate
+if [ -x "$REF_BIN" ]; then
+  time "$REF_BIN" c4_0.pt c4_1.pt 6 64 8 4 1 1 1 1 | tail -3 | tee out5.txt
+  grep -q "Player 0 wins:" out5.txt && echo "reference Evaluate.cpp drop-in ok"
+fi
