@@ -88,6 +88,7 @@ public:
     }
 
     void setRowCount(const uint32_t* d_rows) override { m_dRows = d_rows; }
+    int checkStatus() override { return m_evalnet ? sprl_evalnet_status(m_evalnet, nullptr) : 0; }
 
 private:
     // Hands the module's parameters (names of src/networks/grid_networks.py:30-80) to the library's

@@ -101,6 +101,9 @@ public:
     // Device address of the number of rows in use (sprl_eval_rows); networks that can read their batch size on the
     // device skip the unused rows.
     virtual void setRowCount(const uint32_t* /*d_rows*/) {}
+    // After a run: 0, or an SPRL_E_* code when the evaluator reported a failure (e.g. an activation outside the range
+    // of the library evaluator's fp16 split); the message is in sprl_last_error().
+    virtual int checkStatus() { return 0; }
     virtual int getNumEvals() { return (int)m_numEvals; }
     void addEvals(uint64_t n) { m_numEvals += n; }
 protected:
@@ -213,6 +216,7 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
         network->setRowCount(d_rows);
     }
     check(sprl_run_iteration(e, opt.firstGame, numGames, fwd, &ctx));
+    check(network->checkStatus());
 
     int64_t nMoves = 0, nSamples = 0;
     check(sprl_iteration_counts(e, &nMoves, &nSamples));
@@ -298,6 +302,7 @@ MatchResult runMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACT
         return 0;
     };
     check(sprl_run_match(e, agents, firstGame, numGames, external ? fwd : nullptr, &ctx));
+    for (int k = 0; k < 2; ++k) check(nets[k]->checkStatus());
     MatchResult r { 0, 0, 0, std::vector<int8_t>((size_t)numGames), std::vector<int32_t>((size_t)numGames) };
     int64_t wins[2] = { 0, 0 };
     check(sprl_match_results(e, numGames, r.winners.data(), r.moves.data(), nullptr, wins, &r.draws));

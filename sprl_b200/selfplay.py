@@ -253,6 +253,7 @@ class Engine:
                         break
         else:
             capi.check(self.lib.sprl_run_iteration(self.handle, first_game, num_games, None, None))
+        self._check_evaluators()
         return self.collect_samples() if collect else None
 
     # -- match play (Evaluate.cpp) ----------------------------------------------------------
@@ -283,6 +284,7 @@ class Engine:
                 capi.check(self.lib.sprl_run_match(self.handle, cfgs, first_game, num_games, None, None))
         finally:
             self._match_running = False
+        self._check_evaluators()
         winner = np.zeros(num_games, np.int8)
         moves = np.zeros(num_games, np.int32)
         draws = np.zeros(num_games, np.uint64)
@@ -305,6 +307,14 @@ class Engine:
                 self._raise_slot_failure()
             if playing == 0:
                 return
+
+    def _check_evaluators(self):
+        """Raises when a library evaluator reported a failure during the run (pipeline time-out, or an activation
+        outside the range of its fp16 split): outputs are never silently clamped."""
+        nn = self._nn or {}
+        for ev in [nn.get("evalnet")] + list(nn.get("match_evaluators") or []):
+            if ev is not None and hasattr(ev, "status"):
+                ev.status()
 
     def _raise_slot_failure(self):
         # run_iteration's C path formats the message; reuse it through a zero-round call

@@ -188,3 +188,16 @@ def test_selfplay_through_the_evaluator_is_reproducible():
     assert outs[0][0].shape[0] > 160 * 8 * 20
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_evalnet_reports_out_of_range_activations():
+    """The fp16 split covers inputs and activations up to 4,094; beyond that the forward is reported, not silently clamped."""
+    net = make_network("othello", 2)
+    ev = EvalNet(net, device=0)
+    x = torch.full((4, 3, 8, 8), 5000.0).cuda()
+    ev(x)
+    with pytest.raises(capi.SprlError) as err:
+        ev.status()
+    assert "range" in str(err.value)
+    ev.close()
