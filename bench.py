@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=16384, help="concurrent games per GPU")
     ap.add_argument("--rounds", type=int, default=256, help="search rounds per step")
-    ap.add_argument("--e2e-games", type=int, default=16384, help="games per e2e step per GPU (one slot per game)")
+    ap.add_argument("--e2e-games", type=int, default=8192, help="games per e2e step per GPU (one slot per game)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
