@@ -321,7 +321,7 @@ def run_ours(args):
         e2e["moves_per_sec"] = round(float(agg[1]) / (float(tm) / 1e3), 1)
         e2e["ms_per_step"] = round(float(tm) / args.e2e_steps, 1)
         result["e2e"] = e2e
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the reported CPU baseline: rank 0 at N = 1 only
         result["cpu_baseline"] = cpu_baseline(args, threads=1, seconds=args.ref_seconds)
     if world > 1:
         dist.barrier()
