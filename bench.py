@@ -327,7 +327,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
 
 
 def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
@@ -477,10 +477,20 @@ def run_reference(args):
            "cpu_baseline": {"value": round(sims_s, 1), "unit": "sims/s", "cores": threads, "kind": last["kind"], "sample": last["sample"],
                             "cpu": last.get("cpu")},
            "e2e": {"value": round(sims_s, 1), "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the real stdout."""
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 if __name__ == "__main__":
+    # libraries (NCCL's version banner, torch) write to stdout: keep fd 1 clean for the JSON line
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
