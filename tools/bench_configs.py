@@ -38,8 +38,9 @@ for game, name in ((capi.GAME_C4, "c4"), (capi.GAME_GO7, "go7"), (capi.GAME_GO9,
                       "steps_per_sec": round(steps / (r["elapsed_ms"] / 1e3), 1)}), flush=True)
 
 # ---- self-play of the other games (network through LibTorch on device buffers)
-for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5, 4096), (capi.GAME_GO7, "go7", 400, 16, 8, 0.2, 2048),
-                                              (capi.GAME_GO9, "go9", 400, 16, 8, 0.2, 1024)):
+SCALE = int(os.environ.get("SPRL_BENCH_SLOT_SCALE", "1"))      # concurrent games = SCALE x the defaults below
+for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5, 4096 * SCALE), (capi.GAME_GO7, "go7", 400, 16, 8, 0.2, 2048 * SCALE),
+                                              (capi.GAME_GO9, "go9", 400, 16, 8, 0.2, 1024 * SCALE)):
     net = make_network(kind, 0)
     gi = capi.game_info(game)
     library = os.environ.get("SPRL_BENCH_EVALUATOR", "evalnet") != "libtorch"
