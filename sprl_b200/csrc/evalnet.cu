@@ -555,19 +555,36 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
         const int cells = net.rows * net.cols, planes = net.in_planes;
         uint32_t acc_phase = 0;
         long long t_bar = 0, t_acc = 0, t_head = 0, t0 = NOW();
+        // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split).  The stem
+        // has few input planes, so its vertical taps are folded into K: image channel dyi * planes + p of a
+        // cell holds plane p of the cell one row above / at / below it, and the stem becomes a single-dy layer
+        // (3 MMAs per k-step instead of 9).
+        auto load_planes = [&](long long tile_, int cg, float* v) {
+            const long long board_ = LINEAR ? tile_ : tile_ * 2 + b;
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+                const int ch = cg * KCH + j, dyi = ch / planes, p = ch - dyi * planes, rr = r + dyi - 1;
+                v[j] = (valid && dyi < 3 && rr >= 0 && rr < net.rows && board_ < batch)
+                           ? in[(board_ * planes + p) * cells + rr * net.cols + c] * ACT_SCALE : 0.0f;
+            }
+        };
+        // the first channel group of the NEXT tile is fetched while this tile's head MMAs run (a global round trip per
+        // tile otherwise sits between two tiles); further groups (Go: 51 stem channels) are loaded in place
+        float vnext[KCH];
+        load_planes(blockIdx.x, half, vnext);
         for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const long long board = LINEAR ? tile : tile * 2 + b;
-            // ---- input planes -> image (the reference's planes are 0/1, but any fp32 input is split).  The stem
-            // has few input planes, so its vertical taps are folded into K: image channel dyi * planes + p of a
-            // cell holds plane p of the cell one row above / at / below it, and the stem becomes a single-dy layer
-            // (3 MMAs per k-step instead of 9).
             for (int cg = half; cg < 2 * net.in_ksteps; cg += EPI_WARPS / 4) {
                 float v[KCH];
+#ifdef SPRL_EVALNET_NO_PREFETCH
+                if (false) {
+#else
+                if (cg == half) {
+#endif
 #pragma unroll
-                for (int j = 0; j < KCH; ++j) {
-                    const int ch = cg * KCH + j, dyi = ch / planes, p = ch - dyi * planes, rr = r + dyi - 1;
-                    v[j] = (valid && dyi < 3 && rr >= 0 && rr < net.rows && board < batch)
-                               ? in[(board * planes + p) * cells + rr * net.cols + c] * ACT_SCALE : 0.0f;
+                    for (int j = 0; j < KCH; ++j) v[j] = vnext[j];
+                } else {
+                    load_planes(tile, cg, v);
                 }
                 uint4 h, l;
                 split8(v, h, l, mx);
@@ -578,6 +595,9 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
             for (int layer = 0; layer < n_layers; ++layer) {
                 tc_fence_before();
                 { long long a = NOW(); named_bar(1, BAR1_THREADS); t_bar += NOW() - a; }
+#ifndef SPRL_EVALNET_NO_PREFETCH
+                if (layer == n_layers - 1 && tile + gridDim.x < tile_end) load_planes(tile + gridDim.x, half, vnext);
+#endif
                 { long long a = NOW(); mbar_wait(bar_acc, acc_phase, net.error_flag, 3); t_acc += NOW() - a; }
                 const long long t_layer = NOW();
                 acc_phase ^= 1u;
