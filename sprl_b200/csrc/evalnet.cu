@@ -280,19 +280,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
                  : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* v, float* w) {
-    uint32_t r[16], q[16];
+// three 16-column loads of a lane's accumulators in flight at once, one wait
+__device__ __forceinline__ void tmem_ld16x3(uint32_t ta, uint32_t tb, uint32_t tc, float* u, float* v, float* w) {
+    uint32_t p[16], r[16], q[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7]),
+                   "=r"(p[8]), "=r"(p[9]), "=r"(p[10]), "=r"(p[11]), "=r"(p[12]), "=r"(p[13]), "=r"(p[14]), "=r"(p[15])
+                 : "r"(ta) : "memory");
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(ta) : "memory");
+                 : "r"(tb) : "memory");
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
                    "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-                 : "r"(tb) : "memory");
+                 : "r"(tc) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
+    for (int i = 0; i < 16; ++i) { u[i] = __uint_as_float(p[i]); v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
 }
 // two floats -> packed fp16 pair (x0 in the low half), round to nearest, saturating at +-65504
 __device__ __forceinline__ uint32_t pack_half2_sat(float x0, float x1) {
@@ -614,8 +619,7 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
                     for (int q = 2 * half; q < 2 * half + 2; ++q) {
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = hi half + lo half of accumulator dx
                         float o[16], v[16], w[16];
-                        tmem_ld16(t_lane + CH + q * 16, o);                                          // dx = 0
-                        tmem_ld16x2(t_lane + q * 16, t_lane + 2 * CH + q * 16, v, w);                // dx = -1, dx = +1
+                        tmem_ld16x3(t_lane + CH + q * 16, t_lane + q * 16, t_lane + 2 * CH + q * 16, o, v, w);   // dx = 0, -1, +1
                         if (LINEAR) {
                             // publish what the neighbouring warps need: lane 31's Z_-1 (for the next warp's lane 0)
                             // and lane 0's Z_+1 (for the previous warp's lane 31); double-buffered per iteration
