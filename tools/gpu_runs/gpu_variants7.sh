@@ -1,0 +1,5 @@
+run() { python bench.py --no-e2e --no-cpu-baseline --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('sims/s %.2f M  k_round %.4f ms  evalnet %.4f ms' % (d['value']/1e6, d['roofline_search']['launch_ms'], d['roofline']['launch_ms']))"; }
+for v in 32 24 40 32; do echo "=== blocks per SM $v"; tools/build_search_variant.sh -DSPRL_SEARCH_BLOCKS_PER_SM=$v && run; done
