@@ -178,6 +178,35 @@ def test_sample_round_trip_properties():
     assert set(np.unique(colour)) <= {0.0, 1.0}
 
 
+def test_headline_configuration_at_scale():
+    """BASELINE.json's configuration (Othello, 400 sims/move, 8/4 leaf batching, D4 symmetry, Dirichlet 0.25 / 0.3,
+    InitQ::PARENT) over 1,024 concurrent games: the first games are bit-identical to the oracle's (a game's result does
+    not depend on how many other games share the GPU), and the whole iteration satisfies the reference's invariants."""
+    n, head = 1024, 3
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, seed=0, sims=400, max_batch=8, max_queue=4, dir_eps=0.25, dir_alpha=0.3,
+                   num_slots=n, max_games=n, record_stats=1) as eng:
+        states, dists, outcomes = eng.run_iteration(n)
+        got = eng.move_stats(n)
+        st = eng.stats()
+    ref = O.selfplay(O.OG_OTHELLO, O.OE_HASHNET, 0, 0, head, 400, 8, 4, 0.25, 0.3)
+    m = int(ref["game_moves"].sum())
+    assert np.array_equal(got["game_moves"][:head], ref["game_moves"]) and np.array_equal(got["game_rng_draws"][:head], ref["game_rng_draws"])
+    for k in ("move_N", "move_W", "move_P", "move_root_N", "move_root_W", "move_action", "move_traversals", "move_player"):
+        assert np.array_equal(got[k][:m], ref[k]), k
+    assert np.array_equal(states[:8 * m], ref["states"]) and np.array_equal(outcomes[:8 * m], ref["outcomes"])
+    # invariants over all games (SURVEY 8a: Q7 whole batches, Q2/Q4 root visit bookkeeping, A17 sample layout)
+    assert st["games"] == n and states.shape[0] == dists.shape[0] == outcomes.shape[0] == 8 * st["moves"]
+    assert (got["move_traversals"] >= 400).all() and (got["move_traversals"] < 408).all()
+    assert np.array_equal(got["move_N"].sum(1) <= got["move_traversals"], np.ones(len(got["move_traversals"]), bool))
+    first = np.concatenate([[0], np.cumsum(got["game_moves"])[:-1]])
+    assert np.array_equal(got["move_root_N"][first], got["move_traversals"][first].astype(np.float32))      # fresh root: N() = its own descents
+    assert np.array_equal(got["move_N"][first].sum(1), got["move_traversals"][first] - 4)                   # Q4: queued 4 times before it expands
+    assert np.allclose(dists.sum(1), 1.0, atol=1e-5) and (dists >= 0).all()
+    assert set(np.unique(outcomes)) <= {-1.0, 0.0, 1.0}
+    assert 50 <= got["game_moves"].mean() <= 64 and got["game_moves"].max() <= 128
+    assert st["sims"] == int(got["move_traversals"].astype(np.int64).sum())
+
+
 # ------------------------------------------------- external evaluator (the traced-network path)
 class IntegerNet:
     """A network whose outputs are exact in fp32 on any device: integer weights on 0/1 planes,
