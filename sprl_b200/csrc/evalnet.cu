@@ -961,11 +961,13 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     e->dev.wunits_bytes = (long long)(one * sizeof(unsigned short));
     e->dev.replicas = REPLICAS;
     e->dev.debug = getenv("SPRL_EVALNET_DEBUG") ? atoi(getenv("SPRL_EVALNET_DEBUG")) : 0;
+#ifdef SPRL_EVALNET_TIMERS        // per-role cycle counters: only in builds that compile the clock reads in
     if (getenv("SPRL_EVALNET_TIMING") && !e->dev.timing) {
         std::vector<long long> z(1024 * 12, 0);
         const long long* tp = nullptr;
         if (!e->upload(z, &tp)) e->dev.timing = const_cast<long long*>(tp);
     }
+#endif
     e->dev.nst = MAX_NST;
     if (getenv("SPRL_EVALNET_NST")) e->dev.nst = std::max(2, std::min(MAX_NST, atoi(getenv("SPRL_EVALNET_NST"))));   // experiments
     while (e->dev.nst > 2 && smem_bytes_for(L, e->dev.nst) > MAX_SMEM) e->dev.nst -= 1;
