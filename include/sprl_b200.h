@@ -112,6 +112,9 @@ typedef struct {
     int64_t max_games;      /* capacity of the per-game records (games per iteration) */
     int record_stats;       /* keep per-move root N/W/P for sprl_move_stats (parity tests) */
     int rounds_per_launch;  /* device evaluators: search rounds per kernel launch; 0 = default */
+    int fix_symmetry_mask;  /* 0 = the reference (quirk: the evaluator masks a symmetrised policy with the UN-symmetrised
+                             * legal mask, uct/UCTTree.hpp:136-149, networks/GridNetwork.hpp:117-125, so legal moves can get
+                             * prior 0); 1 = the mask is symmetrised with the state.  Not the reference's behaviour. */
 } sprl_config;
 
 /* Fills a config with the reference's Othello worker constants (OTHWorker.cpp:12-28,

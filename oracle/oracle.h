@@ -72,6 +72,8 @@ typedef struct {
     oracle_eval_cb eval_cb;
     void* eval_user;
     uint64_t hash_salt; /* OE_HASHNET: 0 = the plain net, other values = independent nets (matches) */
+    int fix_symmetry_mask; /* NOT the reference: symmetrise the legal mask together with the state before the
+                            * evaluator masks its policy (repairs quirk Q3, uct/UCTTree.hpp:136-149).  Default 0. */
 } oracle_selfplay_cfg;
 
 typedef struct {

@@ -332,6 +332,11 @@ static void tree_evaluate_and_backprop(otree* t, onode** leaves, int n) {
             syms[i] = orng_uniform_int(t->rng, 0, gi->nsym - 1);
             ostate s = states[i];
             for (int h = 0; h < s.size; ++h) osym_cells(t->game, syms[i], s.hist[h], states[i].hist[h]);
+            if (t->cfg->fix_symmetry_mask) {        /* option, not the reference: the mask follows the state */
+                float m[OG_MAXA];
+                memcpy(m, masks[i], sizeof(m));
+                osym_dist(t->game, syms[i], m, masks[i]);
+            }
         }
     }
     evaluate_batch(t->cfg, gi, states, (const float (*)[OG_MAXA])masks, n, policy, value);

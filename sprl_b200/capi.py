@@ -42,7 +42,7 @@ class Config(C.Structure):
                 ("dir_eps", C.c_float), ("dir_alpha", C.c_float), ("u_weight", C.c_float),
                 ("add_noise", C.c_int), ("use_sym", C.c_int), ("init_q", C.c_int),
                 ("units_per_tree", C.c_int64), ("max_games", C.c_int64), ("record_stats", C.c_int),
-                ("rounds_per_launch", C.c_int)]
+                ("rounds_per_launch", C.c_int), ("fix_symmetry_mask", C.c_int)]
 
 
 class Stats(C.Structure):

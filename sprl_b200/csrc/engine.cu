@@ -175,6 +175,7 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     p.sims = cfg->sims; p.max_batch = cfg->max_batch; p.max_queue = cfg->max_queue;
     p.dir_eps = cfg->dir_eps; p.dir_alpha = cfg->dir_alpha; p.u_weight = cfg->u_weight;
     p.add_noise = cfg->add_noise; p.use_sym = cfg->use_sym; p.init_q = cfg->init_q;
+    p.fix_symmetry_mask = cfg->fix_symmetry_mask ? 1 : 0;
     p.rounds_per_launch = (cfg->evaluator == SPRL_EVAL_EXTERNAL) ? 1 : e->cfg.rounds_per_launch;
     p.record_stats = cfg->record_stats;
     p.game_stride = 1;

@@ -563,6 +563,10 @@ struct TreeWarp {
         const int player = META_PLAYER(h.meta);
         P pos;
         hdr_to_pos<G>(h, pos);
+        // the legal mask the evaluator applies to its (symmetrised-frame) policy: the reference hands it the
+        // UN-symmetrised one (quirk Q3); with fix_symmetry_mask it is symmetrised like the state
+        P mpos = pos;
+        if (p.fix_symmetry_mask && cfg_use_sym()) mpos.legal = sym_bits(pos.legal, s);
         float value = 0.0f;
         for (int i = lane; i < G::ACTIONS; i += 32) sm.pol[i] = 0.0f;
         __syncwarp();
@@ -571,7 +575,7 @@ struct TreeWarp {
             float uniform = 1.0f / (float)n;
             for (int base = 0; base < n; base += 32) {
                 int k = base + lane;
-                if (k < n) sm.pol[legal_action<G>(pos, k)] = uniform;
+                if (k < n) sm.pol[legal_action<G>(mpos, k)] = uniform;
             }
             __syncwarp();
             if constexpr (G::KIND == GAME_OTHELLO) {
@@ -591,23 +595,23 @@ struct TreeWarp {
             for (int base = 0; base < n; base += 32) {
                 int k = base + lane;
                 if (k < n) {
-                    int i = legal_action<G>(pos, k);        // mask index == policy index (symmetrised frame)
+                    int i = legal_action<G>(mpos, k);       // mask index == policy index (symmetrised frame)
                     sm.pol[i] = (ev == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
                                                                     : det_expf(p.nn_logits[slot * G::ACTIONS + i]);
                 }
             }
             __syncwarp();
             float sum = 0.0f;                                // GameActionDist::sum, ascending index
-            for_each_legal(pos, [&](int i) { sum += sm.pol[i]; });
+            for_each_legal(mpos, [&](int i) { sum += sm.pol[i]; });
             __syncwarp();
             if (sum == 0.0f) {
                 float uniform = 1.0f / (float)n;
-                for (int base = 0; base < n; base += 32) { int k = base + lane; if (k < n) sm.pol[legal_action<G>(pos, k)] = uniform; }
+                for (int base = 0; base < n; base += 32) { int k = base + lane; if (k < n) sm.pol[legal_action<G>(mpos, k)] = uniform; }
             } else {
                 float inv = 1.0f / sum;                      // operator/(dist, float) = multiply by the reciprocal
                 for (int base = 0; base < n; base += 32) {
                     int k = base + lane;
-                    if (k < n) { int i = legal_action<G>(pos, k); sm.pol[i] = sm.pol[i] * inv; }
+                    if (k < n) { int i = legal_action<G>(mpos, k); sm.pol[i] = sm.pol[i] * inv; }
                 }
             }
             __syncwarp();

@@ -107,6 +107,7 @@ struct EngineParams {
     int sims, max_batch, max_queue;
     float dir_eps, dir_alpha, u_weight;
     int add_noise, use_sym, init_q;
+    int fix_symmetry_mask;          // option (not the reference): mask the policy with the symmetrised legal mask
     int rounds_per_launch;
     unsigned long long* counters;   // [0] slots that finished all their games, [1] slots in error
     // launch order of the trees (longest first): warp w of a launch serves tree order[parity][w].  Trees

@@ -166,6 +166,7 @@ struct DeviceOptions {
     int numSlots = 0;          // 0 = one slot per game
     uint64_t firstGame = 0;    // stream id of the first game of the next runIteration
     uint64_t gameStride = 1;
+    bool fixSymmetryMask = false;   // not the reference: symmetrise the legal mask with the state (repairs quirk Q3)
 };
 inline DeviceOptions& deviceOptions() { static DeviceOptions o; return o; }
 
@@ -193,6 +194,7 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
     cfg.init_q = initQCode(initQMethod);
     cfg.add_noise = addNoise ? 1 : 0;
     cfg.use_sym = symmetrizer != nullptr ? 1 : 0;
+    cfg.fix_symmetry_mask = opt.fixSymmetryMask ? 1 : 0;
     sprl_engine* e = nullptr;
     check(sprl_create(&cfg, &e));
     struct Guard { sprl_engine* e; ~Guard() { sprl_destroy(e); } } guard { e };
@@ -262,6 +264,7 @@ MatchResult runMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACT
     cfg.max_games = numGames;
     cfg.sims = numTraversals; cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
     cfg.dir_eps = search.dirEps; cfg.dir_alpha = search.dirAlpha; cfg.u_weight = search.uWeight; cfg.add_noise = search.addNoise ? 1 : 0;
+    cfg.fix_symmetry_mask = opt.fixSymmetryMask ? 1 : 0;
     sprl_engine* e = nullptr;
     check(sprl_create(&cfg, &e));
     struct Guard { sprl_engine* e; ~Guard() { sprl_destroy(e); } } guard { e };

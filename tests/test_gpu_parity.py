@@ -418,3 +418,19 @@ def test_match_external_evaluators_bit_exact(game, sims, b, q, ngames, pairs, gr
     ref["game_winner"] = ref["game_winner"].astype(np.int8)
     G.assert_trace_equal(ref, got, MATCH_KEYS)
     assert got["wins"] == ref["wins"] and got["draws"] == ref["draws"]
+
+
+@pytest.mark.parametrize("game,ev,sims,alpha,ngames", [(capi.GAME_OTHELLO, "hash", 120, 0.3, 8), (capi.GAME_OTHELLO, "uniform", 64, 0.3, 6),
+                                                       (capi.GAME_C4, "hash", 128, 0.5, 10), (capi.GAME_GO7, "hash", 60, 0.2, 3)])
+def test_fix_symmetry_mask_option_vs_oracle(game, ev, sims, alpha, ngames):
+    """The non-default repair of quirk Q3 (the legal mask is symmetrised with the state): bit-exact against the oracle
+    run with the same option, and every visited move of every root then has a positive prior."""
+    oe = O.OE_HASHNET if ev == "hash" else O.OE_UNIFORM
+    b, q = (16, 8) if game == capi.GAME_GO7 else (8, 4)
+    ref = O.selfplay(game, oe, 31, 0, ngames, sims, b, q, 0.25, alpha, add_noise=False, fix_symmetry_mask=True, max_moves_per_game=170)
+    got = run_engine(game, EVALS[ev], 31, 0, ngames, sims, b, q, 0.25, alpha, 0, 1, capi.INITQ_PARENT, fix_symmetry_mask=1)
+    compare_selfplay(ref, got)
+    assert (got["move_P"][got["move_N"] > 0] > 0).all()
+    if game == capi.GAME_OTHELLO:      # with the quirk, roots whose legal set is not symmetric lose priors
+        quirk = O.selfplay(game, oe, 31, 0, ngames, sims, b, q, 0.25, alpha, add_noise=False, max_moves_per_game=170)
+        assert not np.array_equal(quirk["move_P"][:8], got["move_P"][:8])
