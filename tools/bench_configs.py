@@ -70,6 +70,32 @@ for game, kind, sims, b, q, alpha, slots in ((capi.GAME_C4, "c4", 512, 8, 4, 0.5
                       "evals_per_sec": round(st["evals"] / dt, 1), "failed_slots": failed,
                       "evaluator": "library (tcgen05, fp16 split)" if library else "traced module, LibTorch/cuDNN fp32"}), flush=True)
 
+# ---- config 3 throughput mode: Othello, 400 sims/move, leaf queue per tree swept at a constant leaf-batch capacity (65,536 rows)
+for b, q in ((8, 4), (16, 8), (32, 16), (64, 32)):
+    slots = 65536 // q
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, seed=0, sims=400, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.3,
+                   num_slots=slots, max_games=slots * 8) as eng:
+        eng.attach_evalnet(EvalNet(make_network("othello", 0), device=0), use_cuda_graph=True)
+        eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        eng.begin_iteration(0, slots * 8)
+        eng._capture()
+        g = eng._nn["graph"]
+        for _ in range(60):
+            g.replay()
+        torch.cuda.synchronize()
+        eng.reset_stats()
+        t0 = time.time()
+        for _ in range(200):
+            g.replay()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        st = eng.stats()
+        playing, failed = eng.poll()
+    print(json.dumps({"config": "othello_queue_sweep", "sims_per_move": 400, "batch_queue": [b, q], "slots": slots,
+                      "sims_per_sec": round(st["sims"] / dt, 1), "moves_per_sec": round(st["moves"] / dt, 1),
+                      "evals_per_sim": round(st["evals"] / max(1, st["sims"]), 4), "rows_in_use": round(st["evals"] / 200 / 65536, 4),
+                      "round_ms": round(dt / 200 * 1e3, 3), "failed_slots": failed}), flush=True)
+
 # ---- match play (Evaluate.cpp): two random-init Othello networks, each side its own tree and evaluator
 pairs, games = 4096, 8192
 nets = [EvalNet(make_network("othello", k), device=0) for k in (0, 1)]
