@@ -118,10 +118,11 @@ __host__ __device__ __forceinline__ int nth_set_bit32(u32 x, int k) {
 // k-th (0-based) set bit of a 64-bit word; k must be < popcount.
 __host__ __device__ __forceinline__ int nth_set_bit64(u64 x, int k) {
 #ifdef __CUDA_ARCH__
-    u32 lo = (u32)x;
-    int c = __popc(lo);
-    if (k < c) return nth_set_bit32(lo, k);
-    return 32 + nth_set_bit32((u32)(x >> 32), k - c);
+    // one copy of the 32-bit bisection (the kernels inline this at ~30 sites: code size matters more than a select)
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    const int c = __popc(lo);
+    const bool upper = k >= c;
+    return (upper ? 32 : 0) + nth_set_bit32(upper ? hi : lo, upper ? k - c : k);
 #else
     for (int i = 0; i < k; ++i) x &= x - 1;
     return __builtin_ctzll(x);

@@ -1,0 +1,8 @@
+run() { python bench.py --no-e2e --no-cpu-baseline --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('sims/s %.2f M  k_round %.4f ms  evalnet %.4f ms' % (d['value']/1e6, d['roofline_search']['launch_ms'], d['roofline']['launch_ms']))"; }
+echo "=== default"; tools/build_search_variant.sh && run
+echo "=== noinline legal_action"; tools/build_search_variant.sh -DSPRL_NOINLINE_LEGAL_ACTION && run
+echo "=== default again"; tools/build_search_variant.sh && run
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
