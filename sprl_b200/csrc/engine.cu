@@ -185,6 +185,8 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (!rc) rc = e->alloc(&p.trees, S, true);
     if (!rc) rc = e->alloc(&p.q_leaf, S * cfg->max_queue, true);
     if (!rc) rc = e->alloc(&p.q_sym, S * cfg->max_queue, true);
+    if (!rc) rc = e->alloc(&p.q_path, S * cfg->max_queue * 32, false);
+    if (!rc) rc = e->alloc(&p.q_plen, S * cfg->max_queue, true);
     if (!rc) rc = e->alloc(&p.q_count, 2, true);
     if (!rc) rc = e->alloc(&p.q_rows, 2, true);
     if (!rc) rc = e->alloc(&p.q_base, S, true);

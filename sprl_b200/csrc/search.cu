@@ -126,9 +126,11 @@ __device__ __forceinline__ void hdr_to_pos(const Hdr<G::W>& h, typename G::P& p)
 }
 
 // shared-memory scratch of one warp
+constexpr int DESCENT_MAX = 32;        // edges of a descent recorded for the parallel backup (deeper ones walk parent links)
 struct WarpScratch {
     float pol[96];      // dense per-action vector (policy / pdf)
     float aux[96];      // per-slot vector (noise, cdf)
+    u32 path[DESCENT_MAX]; // own edges of the nodes on the last descent, root first: path[0] = the tree's dummy edge (unit 0)
 };
 
 // ---- the warp that owns a tree -----------------------------------------------------------------
@@ -158,6 +160,7 @@ struct TreeWarp {
     uint4* slab;            // current slab
     WarpScratch& sm;
     AgentCfg agent;         // match play: this side's evaluator / symmetrizer / init-Q (unused in self-play)
+    int sel_edges;          // own edges recorded in sm.path by the last select_leaf (0: the descent was deeper than DESCENT_MAX)
     int game_step;          // game_index stride: slots (self-play) or pairs (match play)
 
     // per-tree options: the engine's in self-play, the side's in match play
@@ -297,6 +300,18 @@ struct TreeWarp {
     }
 
     // ---- UCTTree::backup (uct/UCTTree.hpp:261-273) by walking parent links ----
+    // With the descent's own edges at hand (n_path of them, root first) every level is updated by its own lane: the W's
+    // of one backup are distinct words, and each update is the reference's `W += 1 + estimate * sign(player)`.
+    __device__ void backup_path(const u32* path, int n_path, int leaf_player, float value) {
+        const float est = -value * (leaf_player == 0 ? 1.0f : -1.0f);
+        if (lane < n_path) {
+            const int up = n_path - 1 - lane;                       // plies above the leaf: players alternate
+            const float term = 1.0f + est * (((leaf_player ^ up) & 1) == 0 ? 1.0f : -1.0f);
+            float* w = reinterpret_cast<float*>(slab + path[lane]) + 1;
+            *w = *w + term;
+        }
+        __syncwarp();
+    }
     __device__ void backup(u32 leaf, int leaf_player, float value) {
         float est = -value * (leaf_player == 0 ? 1.0f : -1.0f);
         u32 cur = leaf;
@@ -361,6 +376,7 @@ struct TreeWarp {
         int depth = 0;
         bool have = false;
         H h;
+        if (lane == 0) sm.path[0] = 0u;                 // the root's own edge is the tree's dummy edge
         for (;;) {
             if (!have) HL<W>::load(slab + cur, h);
             have = false;
@@ -437,9 +453,11 @@ struct TreeWarp {
             n_own = child_n;
             cur = child;
             ++depth;
+            if (lane == 0 && depth < DESCENT_MAX) sm.path[depth] = edge_unit;
             __syncwarp();
         }
         acc.depth_sum += depth;
+        sel_edges = depth < DESCENT_MAX ? depth + 1 : 0;
         leaf_hdr = h;
         return cur;
     }
@@ -456,16 +474,18 @@ struct TreeWarp {
             if (META_TERMINAL(h.meta)) {
                 u32 wn = META_WINNER(h.meta);
                 float value = (wn == WINNER_NONE) ? 0.0f : ((int)wn - 1 == player ? 1.0f : -1.0f);
-                backup(leaf, player, value);
+                if (sel_edges) backup_path(sm.path, sel_edges, player, value); else backup(leaf, player, value);
                 acc.leaves_terminal += 1;
                 continue;
             } else if (h.meta & META_EVALUATED) {
                 expand(leaf, h.meta);
-                backup(leaf, player, h.net_value);
+                if (sel_edges) backup_path(sm.path, sel_edges, player, h.net_value); else backup(leaf, player, h.net_value);
                 acc.leaves_gray += 1;
                 continue;
             } else {
-                if (lane == 0) p.q_leaf[(size_t)tree * p.max_queue + nq] = leaf;
+                const size_t qs = (size_t)tree * p.max_queue + nq;
+                if (lane == 0) { p.q_leaf[qs] = leaf; p.q_plen[qs] = (unsigned char)sel_edges; }
+                if (lane < sel_edges) p.q_path[qs * DESCENT_MAX + lane] = sm.path[lane];      // for the backup in the next launch
                 ++nq;
                 acc.leaves_empty += 1;
             }
@@ -642,7 +662,9 @@ struct TreeWarp {
             HL<W>::load(slab + leaf, h);
             if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, row0 + q);
             if (!(h.meta & META_EXPANDED)) expand(leaf, h.meta);
-            backup(leaf, META_PLAYER(h.meta), h.net_value);
+            const int n_path = p.q_plen[slot];
+            if (n_path) backup_path(p.q_path + slot * DESCENT_MAX, n_path, META_PLAYER(h.meta), h.net_value);
+            else backup(leaf, META_PLAYER(h.meta), h.net_value);
         }
         st.n_queued = 0;
     }

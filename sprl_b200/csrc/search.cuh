@@ -74,6 +74,8 @@ struct EngineParams {
     int n_slots;
     u32* q_leaf;                    // [n_slots][max_queue]
     unsigned char* q_sym;           // [n_slots][max_queue]
+    u32* q_path;                    // [n_slots][max_queue][32] own edges of the nodes on the leaf's descent, root first
+    unsigned char* q_plen;          // [n_slots][max_queue] how many of them (0: deeper than 32, back up by parent links)
     float* root_p;                  // [n_slots][ACTIONS] noised priors of the decision node, by edge slot
     // evaluator buffers (SPRL_EVAL_EXTERNAL).  Rows are handed out per launch, compactly: a tree with nq queued
     // leaves takes rows q_base[tree] .. +nq-1 (one atomicAdd on q_count), so the evaluator only computes the

@@ -1,0 +1,5 @@
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-e2e --no-cpu-baseline --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('sims/s %.2f M  k_round %.4f ms  evalnet %.4f ms' % (d['value']/1e6, d['roofline_search']['launch_ms'], d['roofline']['launch_ms']))"
