@@ -378,9 +378,6 @@ struct TreeWarp {
         H h;
         if (lane == 0) sm.path[0] = 0u;                 // the root's own edge is the tree's dummy edge
         for (;;) {
-            // the first 32 edges are fetched together with the header (one dependent round trip per level, not two):
-            // a record's edges follow its header, and SLAB_SLACK keeps the speculative read inside the slab
-            const uint4 e_first = slab[cur + HDR + lane];
             if (!have) HL<W>::load(slab + cur, h);
             have = false;
             if (META_TERMINAL(h.meta) || !(h.meta & META_EXPANDED)) break;
@@ -398,7 +395,7 @@ struct TreeWarp {
                 int k = ch * 32 + lane;
                 val[ch] = -__int_as_float(0x7f800000);
                 if (k < n) {
-                    e[ch] = ch == 0 ? e_first : slab[cur + HDR + k];
+                    e[ch] = slab[cur + HDR + k];
                     float prior = (cur == ROOT_UNIT && p.add_noise) ? p.root_p[(size_t)tree * G::ACTIONS + k] : __uint_as_float(e[ch].x);
                     float w = __uint_as_float(e[ch].y), nv = __uint_as_float(e[ch].z);
                     float q = w / (1.0f + nv);
