@@ -167,6 +167,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #ifdef SPRL_EVALNET_TESTWAIT
     asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#elif defined(SPRL_EVALNET_WAIT_HINT_NS)
+    // with a suspend-time hint the waiting warp sleeps in hardware until the phase completes (or the hint elapses)
+    // instead of polling: waiting warps were a third of the kernel's executed instructions
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)SPRL_EVALNET_WAIT_HINT_NS) : "memory");
 #else
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -710,17 +715,34 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     const int pc = net.policy_channels, cells = net.rows * net.cols, K = pc * cells, A = net.actions, IN = (pc + 1) * cells;
     float* wp = hs;                           // [K][HP_STRIDE]
     float* wv = wp + K * HP_STRIDE;           // [cells][64]
-    float* x = wv + cells * 64;               // [HB][IN]
-    float* hid = x + HB * IN;                 // [HB][65]
+    float* xbuf = wv + cells * 64;            // [2][HB][IN]: the next 64 boards arrive (cp.async) while these are computed
+    float* hid = xbuf + 2 * HB * IN;          // [HB][65]
     const int t = threadIdx.x;
+    // stages the activations of boards b0 .. b0+63 into buffer `which` (rows past the batch are zero)
+    auto stage = [&](long long b0, int which) {
+        if (b0 < batch) {
+            const int nb = (int)(batch - b0 < HB ? batch - b0 : HB);
+            float* dst = xbuf + which * HB * IN;
+            const float* src = net.head_act + b0 * IN;          // 64 * IN floats per CTA step: 16-byte aligned
+            const int n16 = nb * IN / 4;
+            for (int i = t; i < n16; i += 256)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * i)), "l"(src + 4 * i) : "memory");
+            for (int i = 4 * n16 + t; i < HB * IN; i += 256) dst[i] = i < nb * IN ? src[i] : 0.0f;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage((long long)blockIdx.x * HB, 0);
     for (int i = t; i < K * HP_STRIDE; i += 256) { const int k = i / HP_STRIDE, a = i - k * HP_STRIDE; wp[i] = a < A ? net.pfc_wt[k * A + a] : 0.0f; }
     for (int i = t; i < cells * 64; i += 256) wv[i] = net.vfc1_wt[i];
     const int ag = t & 15, bg = t >> 4;       // 16 output groups x 16 board groups
-    for (long long b0 = (long long)blockIdx.x * HB; b0 < batch; b0 += (long long)gridDim.x * HB) {
-        __syncthreads();
+    int cur = 0;
+    for (long long b0 = (long long)blockIdx.x * HB; b0 < batch; b0 += (long long)gridDim.x * HB, cur ^= 1) {
+        __syncthreads();                                         // everyone is done with the other buffer and with hid
         const int nb = (int)(batch - b0 < HB ? batch - b0 : HB);
-        for (int i = t; i < HB * IN; i += 256) x[i] = i < nb * IN ? net.head_act[b0 * IN + i] : 0.0f;
+        stage(b0 + (long long)gridDim.x * HB, cur ^ 1);          // prefetch the next step
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // this step's rows have landed
         __syncthreads();
+        const float* x = xbuf + cur * HB * IN;
         // policy_fc: outputs 4*ag .. 4*ag+3 for boards 4*bg .. 4*bg+3 (+ the outputs beyond 64, one per thread row)
         for (int a0 = 4 * ag; a0 < A; a0 += 64) {
             float acc[4][4];
@@ -811,7 +833,7 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     }
 }
 
-static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + HB * (pc + 1) * cells + HB * 65) * sizeof(float); }
+static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + 2 * HB * (pc + 1) * cells + HB * 65) * sizeof(float); }
 
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
 // Power-of-two shift that brings the largest |w| of a layer into (2^9, 2^10]: fp16 keeps 11 significant bits
@@ -1102,7 +1124,7 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
     e->launches += 1;
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) {
-        const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, 2LL * e->sm_count);
+        const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, (long long)e->sm_count);     // one resident CTA per SM (its weights are staged once)
         k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels, e->rows * e->cols), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
         e->launches += 1;
         err = cudaGetLastError();
