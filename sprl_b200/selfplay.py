@@ -404,9 +404,14 @@ def run_worker(run_name, save_dir, game, num_iters, init_games, init_sims, init_
     """SPRL::runWorker: per iteration wait for the controller's model, play the games, write
     <save_dir>/<run>_iteration_<i>_{states,distributions,outcomes}.npy.  Iteration 0 uses the
     uniform evaluator (the reference passes RandomNetwork as initialNetwork, OTHWorker.cpp:51)
-    and the init* search parameters.  (The reference self-initialises maxBatchSize/maxQueueSize
+    and the init* search parameters; later iterations load the traced module with `load_model` (default: torch.jit.load onto
+    the engine's GPU).  (The reference self-initialises maxBatchSize/maxQueueSize
     for iter > 0, GridWorker.hpp:120-121, which is undefined behaviour; the intended values are used.)"""
     os.makedirs(save_dir, exist_ok=True)
+    if load_model is None:
+        def load_model(path):
+            import torch
+            return torch.jit.load(path, map_location=torch.device("cuda", device)).eval()
     for it in range(num_iters):
         print(f"Starting iteration {it}...", flush=True)
         model_path = wait_model_path(it - 1, run_name, wait_interval, settle, root)
@@ -421,7 +426,12 @@ def run_worker(run_name, save_dir, game, num_iters, init_games, init_sims, init_
         else:
             print("Using traced PyTorch network...", flush=True)
             eng = Engine(game, capi.EVAL_EXTERNAL, **opts)
-            eng.attach_network(load_model(model_path))
+            module = load_model(model_path)
+            try:        # the library's tcgen05 evaluator fed with the module's parameters; other shapes run the module itself
+                from .evalnet import EvalNet
+                eng.attach_evalnet(EvalNet(module, device=device, rows=eng.gi.rows, cols=eng.gi.cols))
+            except (capi.SprlError, KeyError):
+                eng.attach_network(module)
         with eng:
             states, dists, outcomes = eng.run_iteration(n_games, first_game=first)
         base = os.path.join(save_dir, f"{run_name}_iteration_{it}")

@@ -3,6 +3,8 @@ against the CPU oracle on the same seeded inputs and against the golden fixtures
 produced by the unmodified reference.  Integer / index work is compared bit-exact;
 fp32 search statistics are compared bit-exact too (the kernels keep the reference's
 operand order, no FMA); sampled distributions within 1e-6 (pow)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -434,3 +436,22 @@ def test_fix_symmetry_mask_option_vs_oracle(game, ev, sims, alpha, ngames):
     if game == capi.GAME_OTHELLO:      # with the quirk, roots whose legal set is not symmetric lose priors
         quirk = O.selfplay(game, oe, 31, 0, ngames, sims, b, q, 0.25, alpha, add_noise=False, max_moves_per_game=170)
         assert not np.array_equal(quirk["move_P"][:8], got["move_P"][:8])
+
+
+def test_python_run_worker_writes_the_reference_files(tmp_path):
+    """SPRL::runWorker's file contract through the Python worker: iteration 0 with the uniform evaluator, iteration 1
+    with the controller's traced module (run by the library evaluator), three .npy files per iteration."""
+    import torch
+    from sprl_b200.network import make_network, trace_network
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "data", "models", "unit"))
+    trace_network(make_network("othello", 0), "cpu").save(os.path.join(root, "data", "models", "unit", "traced_unit_iteration_0.pt"))
+    save_dir = os.path.join(root, "data", "games", "unit", "0", "3")
+    SP.run_worker("unit", save_dir, capi.GAME_OTHELLO, 2, 12, 32, 1, 1, 12, 48, 8, 4, 0.25, 0.3, root=root, wait_interval=0.1, settle=0.0)
+    for it in (0, 1):
+        base = os.path.join(save_dir, f"unit_iteration_{it}")
+        s, d, o = np.load(base + "_states.npy"), np.load(base + "_distributions.npy"), np.load(base + "_outcomes.npy")
+        assert s.shape[1:] == (3, 8, 8) and d.shape == (s.shape[0], 65) and o.shape == (s.shape[0],)
+        assert s.shape[0] % 8 == 0 and s.shape[0] >= 12 * 8 * 20
+        assert np.allclose(d.sum(1), 1, atol=1e-5) and set(np.unique(o)) <= {-1.0, 0.0, 1.0}
+        assert open(base + "_outcomes.npy", "rb").read(8) == b"\x93NUMPY\x01\x00"
