@@ -400,8 +400,8 @@ def cpu_baseline(args, threads, seconds):
     if not os.path.exists(ref_worker_path()):
         return cpu_baseline_port(seconds)
     model = traced_model_file()
-    # ~1,100 sims/s/core with this network: size the sample in moves
-    moves = max(2, int(seconds * 1100 / SIMS))
+    # ~3,000 sims/s/core with this network on the B200 boxes' hosts (measured): size the sample in moves
+    moves = max(2, int(seconds * 3000 / SIMS))
     games = max(1, (moves + 29) // 30)
     per_game = (moves + games - 1) // games
     procs = []
