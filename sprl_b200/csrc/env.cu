@@ -37,7 +37,7 @@ int use_device(int device) {
 }
 
 // ---- compact position record exchanged with the host ----------------------------
-struct PosRec {
+struct alignas(16) PosRec {
     u64 b[4];       // b0 words, then b1 words (W each; unused = 0)
     u64 legal[2];
     int action;     // action taken from this position (-1: none)
@@ -194,24 +194,53 @@ __global__ void k_perft_count(const PosRec* __restrict__ level, int64_t n,
     }
 }
 
+// One warp expands 32 parents together: the children of the 32 parents are numbered by a warp scan,
+// the warp reserves their slots with ONE atomicAdd, and lane j generates child j (its parent found by
+// a binary search over the scan), so lanes stay busy whatever the parents' move counts are and
+// neighbouring lanes write neighbouring records.
 template <class G>
 __global__ void k_perft_expand(PerftLevels lv, int depth, int64_t n, PosRec* __restrict__ next,
                                unsigned long long* __restrict__ cursor) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const PosRec& r = lv.level[depth][i];
-    if (r.terminal) return;
-    typename G::P par, nx;
-    rec_to_pos<G>(r, par);
-    int nl = par.n_legal();
-    unsigned long long at = atomicAdd(cursor, (unsigned long long)nl);
-    PerftHist<G::W> hist = { &lv, depth, (u32)i };
-    for (int k = 0; k < nl; ++k) {
-        G::next(par, legal_action<G>(par, k), hist, nx);
-        PosRec o;
-        pos_to_rec<G>(nx, o);
-        o.parent = (u32)i;
-        next[at + k] = o;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t i0 = i - lane;
+    const PosRec* __restrict__ level = lv.level[depth];
+    int nl = 0;
+    if (i < n) {
+        const PosRec& r = level[i];
+        if (!r.terminal) nl = __popcll(r.legal[0]) + __popcll(r.legal[1]) + r.pass_legal;
+    }
+    int incl = nl;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    const int excl = incl - nl;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(FULL, base, 0);
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        int src = 0;        // last lane whose first child is <= j
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = src + step;
+            const int e = __shfl_sync(FULL, excl, cand & 31);
+            if (cand < 32 && e <= j) src = cand;
+        }
+        const int first = __shfl_sync(FULL, excl, src);
+        if (j < total) {
+            typename G::P par, nx;
+            rec_to_pos<G>(level[i0 + src], par);
+            PerftHist<G::W> hist = { &lv, depth, (u32)(i0 + src) };
+            G::next(par, legal_action<G>(par, j - first), hist, nx);
+            PosRec o;
+            pos_to_rec<G>(nx, o);
+            o.parent = (u32)(i0 + src);
+            next[base + j] = o;
+        }
     }
 }
 
@@ -328,8 +357,13 @@ static int env_perft_impl(int depth, uint64_t* count, float* elapsed_ms) {
     if (depth < 0 || depth >= 40) return fail(SPRL_E_INVALID, "perft depth %d out of range", depth);
     cudaEvent_t e0, e1;
     SPRL_CUDA(cudaEventCreate(&e0)); SPRL_CUDA(cudaEventCreate(&e1));
-    std::vector<PosRec*> levels;
-    auto cleanup = [&]() { for (PosRec* p : levels) cudaFree(p); cudaEventDestroy(e0); cudaEventDestroy(e1); };
+    std::vector<PosRec*> levels;        // every level stays resident (PerftHist walks the ancestors)
+    std::vector<PosRec*> owned;         // separate allocations of levels that did not fit the arena
+    // Frontier arena taken before the timed region; 2 GiB holds every level of Othello perft(11).
+    PosRec* arena = nullptr;
+    size_t arena_recs = depth >= 6 ? ((size_t)2 << 30) / sizeof(PosRec) : (size_t)1 << 16, arena_used = 0;
+    if (cudaMalloc((void**)&arena, arena_recs * sizeof(PosRec)) != cudaSuccess) { cudaGetLastError(); arena = nullptr; arena_recs = 0; }
+    auto cleanup = [&]() { for (PosRec* p : owned) cudaFree(p); cudaFree(arena); cudaEventDestroy(e0); cudaEventDestroy(e1); };
     PerftLevels lv;
     for (int i = 0; i < 40; ++i) lv.level[i] = nullptr;
     DeviceBuf<unsigned long long> dctr;
@@ -339,7 +373,11 @@ static int env_perft_impl(int depth, uint64_t* count, float* elapsed_ms) {
     PosRec r0;
     pos_to_rec<G>(start, r0);
     PosRec* d0 = nullptr;
-    SPRL_CUDA(cudaMalloc((void**)&d0, sizeof(PosRec)));
+    if (arena_recs) { d0 = arena; arena_used = 1; }
+    else {
+        if (cudaMalloc((void**)&d0, sizeof(PosRec)) != cudaSuccess) { cleanup(); return fail(SPRL_E_CUDA, "perft: out of device memory"); }
+        owned.push_back(d0);
+    }
     levels.push_back(d0);
     lv.level[0] = d0;
     cudaError_t err = cudaMemcpy(d0, &r0, sizeof(PosRec), cudaMemcpyHostToDevice);
@@ -357,8 +395,12 @@ static int env_perft_impl(int depth, uint64_t* count, float* elapsed_ms) {
         if (d == depth - 1) { result = terminals_above + h[0]; break; }
         if (h[0] == 0) { result = terminals_above; break; }
         PosRec* nxt = nullptr;
-        err = cudaMalloc((void**)&nxt, (size_t)h[0] * sizeof(PosRec));
-        if (err != cudaSuccess) { cleanup(); return fail(SPRL_E_CAPACITY, "perft frontier of %llu positions: %s", h[0], cudaGetErrorString(err)); }
+        if (arena_used + h[0] <= arena_recs) { nxt = arena + arena_used; arena_used += h[0]; }
+        else {
+            err = cudaMalloc((void**)&nxt, (size_t)h[0] * sizeof(PosRec));
+            if (err != cudaSuccess) { cleanup(); return fail(SPRL_E_CAPACITY, "perft frontier of %llu positions: %s", h[0], cudaGetErrorString(err)); }
+            owned.push_back(nxt);
+        }
         levels.push_back(nxt);
         lv.level[d + 1] = nxt;
         k_perft_expand<G><<<ceil_div((long long)n, 128), 128>>>(lv, d, (int64_t)n, nxt, dctr.p + 2);

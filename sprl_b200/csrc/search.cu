@@ -1071,34 +1071,38 @@ __global__ void __launch_bounds__(32) k_match_round(EngineParams p, MatchParams 
 
 // ---- sample writer: selfPlay's symmetrised samples (selfplay/SelfPlay.hpp:86-96,127-136,
 //      148-189) embedded as in runWorker (selfplay/GridWorker.hpp:146-196) ----
-// One block per recorded move; writes S consecutive rows of states / distributions / outcomes.
+// One block per (game, move slot); writes S consecutive rows of states / distributions / outcomes.
 template <class G>
 __global__ void k_emit(EngineParams p, const long long* __restrict__ game_row0, int S,
                        float* __restrict__ states, float* __restrict__ dists, float* __restrict__ outcomes) {
     constexpr int W = G::W, PLANES = 2 * G::HISTORY + 1, ROW = PLANES * G::CELLS;
-    const long long g = blockIdx.x / p.max_moves;
-    const int m = (int)(blockIdx.x - g * p.max_moves);
+    const long long g = blockIdx.x;         // grid = (games, max_moves)
+    const int m = (int)blockIdx.y;
     if (m >= p.rec_moves[g]) return;
     const size_t ri = (size_t)g * p.max_moves + m;
     const int player = p.rec_player[ri];
     const unsigned char wn = p.rec_winner[g];
     const float outcome = (wn == WINNER_NONE) ? 0.0f : ((int)wn - 1 == player ? 1.0f : -1.0f);
     const long long row0 = game_row0[g] + (long long)m * S;
-    for (int idx = threadIdx.x; idx < S * ROW; idx += blockDim.x) {
-        int s = idx / ROW, rem = idx - s * ROW, plane = rem / G::CELLS, to = rem - plane * G::CELLS;
-        float v;
-        if (plane == PLANES - 1) v = player == 0 ? 1.0f : 0.0f;
-        else {
-            int t = plane >> 1, which = plane & 1;       // 0: mover's stones, 1: opponent's
-            v = 0.0f;
+    // one thread per (symmetry, cell): the source cell is found once and serves every plane; a warp's
+    // stores to a plane are contiguous
+    for (int idx = threadIdx.x; idx < S * G::CELLS; idx += blockDim.x) {
+        const int s = idx / G::CELLS, to = idx - s * G::CELLS;
+        const int from = S > 1 ? sym_cell<G>(sym_inverse<G>(s), to) : to;
+        const int w = from >> 6, sh = from & 63;
+        float* out = states + (row0 + s) * ROW + to;
+#pragma unroll
+        for (int t = 0; t < G::HISTORY; ++t) {          // plane 2t: mover's stones, 2t+1: opponent's
+            float mine = 0.0f, theirs = 0.0f;
             if (t <= m) {
                 const unsigned long long* rb = p.rec_board + (ri - t) * 2 * W;
-                int colour = which == 0 ? player : 1 - player;
-                int from = S > 1 ? sym_cell<G>(sym_inverse<G>(s), to) : to;
-                v = ((rb[colour * W + (from >> 6)] >> (from & 63)) & 1ULL) ? 1.0f : 0.0f;
+                mine = ((rb[player * W + w] >> sh) & 1ULL) ? 1.0f : 0.0f;
+                theirs = ((rb[(1 - player) * W + w] >> sh) & 1ULL) ? 1.0f : 0.0f;
             }
+            out[(2 * t) * G::CELLS] = mine;
+            out[(2 * t + 1) * G::CELLS] = theirs;
         }
-        states[(row0 + s) * ROW + rem] = v;
+        out[(PLANES - 1) * G::CELLS] = player == 0 ? 1.0f : 0.0f;
     }
     for (int idx = threadIdx.x; idx < S * G::ACTIONS; idx += blockDim.x) {
         int s = idx / G::ACTIONS, j = idx - s * G::ACTIONS;
@@ -1118,7 +1122,7 @@ template <class G> static void launch_round(const EngineParams& p, cudaStream_t 
 }
 template <class G> static void launch_emit(const EngineParams& p, const long long* row0, int S, float* st, float* di,
                                            float* ou, cudaStream_t s) {
-    k_emit<G><<<(unsigned)(p.num_games * p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
+    k_emit<G><<<dim3((unsigned)p.num_games, (unsigned)p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
 }
 
 template <class G> static void launch_match_begin(const EngineParams& p, const MatchParams& m, cudaStream_t s) {
