@@ -20,18 +20,13 @@ __device__ __forceinline__ int sym_cell(int s, int from) {     // to = f_s(from)
         int r = from / 7, c = from - r * 7;
         return s == 1 ? r * 7 + (6 - c) : from;
     }
+    // D4 element s = optional transpose, then optional flips of the row / column index:
+    // 0 (r,c)  1 (c,w-1-r)  2 (w-1-r,w-1-c)  3 (w-1-c,r)  4 (r,w-1-c)  5 (w-1-c,w-1-r)  6 (w-1-r,c)  7 (c,r)
     const int w = G::COLS;
-    int r = from / w, c = from - r * w, tr, tc;
-    switch (s) {
-    case 0: tr = r; tc = c; break;
-    case 1: tr = c; tc = w - 1 - r; break;
-    case 2: tr = w - 1 - r; tc = w - 1 - c; break;
-    case 3: tr = w - 1 - c; tc = r; break;
-    case 4: tr = r; tc = w - 1 - c; break;
-    case 5: tr = w - 1 - c; tc = w - 1 - r; break;
-    case 6: tr = w - 1 - r; tc = c; break;
-    default: tr = c; tc = r; break;
-    }
+    const int r = from / w, c = from - r * w;
+    const bool swap = (0xAA >> s) & 1, flip_r = (0x6C >> s) & 1, flip_c = (0x36 >> s) & 1;
+    const int a = swap ? c : r, b = swap ? r : c;
+    const int tr = flip_r ? w - 1 - a : a, tc = flip_c ? w - 1 - b : b;
     return tr * w + tc;
 }
 template <class G>
@@ -1103,11 +1098,17 @@ __global__ void k_emit(EngineParams p, const long long* __restrict__ game_row0, 
             out[(2 * t + 1) * G::CELLS] = theirs;
         }
         out[(PLANES - 1) * G::CELLS] = player == 0 ? 1.0f : 0.0f;
+        if constexpr (G::ACTIONS == G::CELLS + 1)        // placements move with their cells: new[f_s(i)] = old[i]
+            dists[(row0 + s) * G::ACTIONS + to] = p.rec_pdf[ri * G::ACTIONS + from];
     }
-    for (int idx = threadIdx.x; idx < S * G::ACTIONS; idx += blockDim.x) {
-        int s = idx / G::ACTIONS, j = idx - s * G::ACTIONS;
-        int i = S > 1 ? sym_action<G>(sym_inverse<G>(s), j) : j;    // new[f_s(i)] = old[i]
-        dists[(row0 + s) * G::ACTIONS + j] = p.rec_pdf[ri * G::ACTIONS + i];
+    if constexpr (G::ACTIONS != G::CELLS + 1) {         // Connect Four: actions are columns
+        for (int idx = threadIdx.x; idx < S * G::ACTIONS; idx += blockDim.x) {
+            int s = idx / G::ACTIONS, j = idx - s * G::ACTIONS;
+            int i = S > 1 ? sym_action<G>(sym_inverse<G>(s), j) : j;    // new[f_s(i)] = old[i]
+            dists[(row0 + s) * G::ACTIONS + j] = p.rec_pdf[ri * G::ACTIONS + i];
+        }
+    } else if (threadIdx.x < S) {                        // the pass action maps to itself
+        dists[(row0 + threadIdx.x) * G::ACTIONS + G::CELLS] = p.rec_pdf[ri * G::ACTIONS + G::CELLS];
     }
     if (threadIdx.x < S) outcomes[row0 + threadIdx.x] = outcome;
 }

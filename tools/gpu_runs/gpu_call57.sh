@@ -8,3 +8,4 @@ python -c "
 import json
 d=json.load(open('gpurun_out/bench_32k.json'))
 print('32k slots: sims/s %.2f M  k_round %.4f ms  evalnet %.4f ms' % (d['value']/1e6, d['roofline_search']['launch_ms'], d['roofline']['launch_ms']))"
+timeout 300 python tools/explore_overlap.py 16384 2>&1 | grep "groups="
