@@ -206,6 +206,65 @@ struct Othello {
         return out;
     }
 
+#ifdef __CUDACC__
+    // ---- warp-cooperative forms for kernels in which one warp owns a position (k_round): lane l walks
+    //      direction l & 7 with per-lane shift amounts, branch-free, and the eight partial sets are OR-reduced
+    //      by redux.sync.  All 32 lanes call with the same arguments and get the same result. ----
+    struct LaneDir { int l, r; u64 keep; };
+    __device__ static __forceinline__ LaneDir lane_dir(int lane) {
+        const int d = lane & 7;
+        const int amount = (0x71987198u >> (4 * d)) & 0xF;       // 8, 9, 1, 7, 8, 9, 1, 7
+        const bool left = (0x87 >> d) & 1;                       // d = 0, 1, 2, 7 shift towards higher cells
+        LaneDir k;
+        k.l = left ? amount : 0;
+        k.r = left ? 0 : amount;
+        k.keep = ((0x0E >> d) & 1) ? NOT_COL0 : (((0xE0 >> d) & 1) ? NOT_COL7 : ~0ULL);
+        return k;
+    }
+    __device__ static __forceinline__ u64 shift_lane(u64 x, const LaneDir& k) { return ((x << k.l) >> k.r) & k.keep; }
+    __device__ static __forceinline__ u64 warp_or(u64 x) {
+        const u32 lo = __reduce_or_sync(0xffffffffu, (u32)x), hi = __reduce_or_sync(0xffffffffu, (u32)(x >> 32));
+        return ((u64)hi << 32) | lo;
+    }
+    __device__ static __forceinline__ u64 mobility_warp(u64 own, u64 opp, const LaneDir& k) {
+        u64 t = shift_lane(own, k) & opp;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t |= shift_lane(t, k) & opp;
+        return warp_or(shift_lane(t, k) & ~(own | opp));
+    }
+    __device__ static __forceinline__ u64 flips_warp(u64 own, u64 opp, int sq, const LaneDir& k) {
+        u64 t = shift_lane(1ULL << sq, k) & opp;                 // the run of opponent stones next to sq
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t |= shift_lane(t, k) & opp;
+        return warp_or((shift_lane(t, k) & own) ? t : 0ULL);    // closed by an own stone
+    }
+    // next() with the direction loops spread over the lanes
+    __device__ static void next_warp(const P& par, int action, int lane, P& p) {
+        const LaneDir k = lane_dir(lane);
+        u64 own = par.b[par.player].w0, opp = par.b[1 - par.player].w0;
+        if (action != CELLS) {
+            u64 f = flips_warp(own, opp, action, k);
+            own |= f | (1ULL << action);
+            opp &= ~f;
+        }
+        p.b[par.player] = Bits<1>(own);
+        p.b[1 - par.player] = Bits<1>(opp);
+        p.player = 1 - par.player;
+        p.depth = par.depth + 1;
+        p.action = (unsigned char)action;
+        u64 m_new = mobility_warp(opp, own, k);
+        p.legal = Bits<1>(m_new);
+        p.pass_legal = (m_new == 0);
+        p.terminal = (m_new == 0) && (mobility_warp(own, opp, k) == 0);
+        p.winner = WINNER_NONE;
+        if (p.terminal) {
+            int c0 = p.b[0].count(), c1 = p.b[1].count();
+            if (c0 > c1) p.winner = WINNER_ZERO;
+            if (c1 > c0) p.winner = WINNER_ONE;
+        }
+    }
+#endif
+
     __host__ __device__ static void set_mask(P& p) {          // actionMask, :156-177
         u64 m = mobility(p.b[p.player].w0, p.b[1 - p.player].w0);
         p.legal = Bits<1>(m);

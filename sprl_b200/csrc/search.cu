@@ -253,6 +253,8 @@ struct TreeWarp {
                 }
                 child.legal = legal;
             }
+        } else if constexpr (G::KIND == GAME_OTHELLO) {
+            G::next_warp(par, action, lane, child);          // called by the whole warp with uniform arguments
         } else {
             G::next(par, action, NoHistory(), child);
         }
