@@ -609,26 +609,31 @@ struct TreeWarp {
             unsigned long long hh = 0;
             if (ev == SPRL_EVAL_HASHNET) { hh = hashnet_salt(state_hash(unit, player, s), cfg_salt()); value = hashnet_value(hh); }
             else value = p.nn_value[slot];
+            // Each lane holds the raw prior of its k-th legal action; GameActionDist::sum adds them in ascending
+            // index order = ascending k, done with one shuffle per element.  Up to 32 legal actions (the usual
+            // case) the values stay in registers until they are normalised.
+            float sum = 0.0f, v = 0.0f;
+            int i = 0;
             for (int base = 0; base < n; base += 32) {
-                int k = base + lane;
+                const int k = base + lane;
+                v = 0.0f;
                 if (k < n) {
-                    int i = legal_action<G>(mpos, k);       // mask index == policy index (symmetrised frame)
-                    sm.pol[i] = (ev == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
-                                                                    : det_expf(p.nn_logits[slot * G::ACTIONS + i]);
+                    i = legal_action<G>(mpos, k);           // mask index == policy index (symmetrised frame)
+                    v = (ev == SPRL_EVAL_HASHNET) ? hashnet_prior_raw(hh, i)
+                                                  : det_expf(p.nn_logits[slot * G::ACTIONS + i]);
+                    if (n > 32) sm.pol[i] = v;
                 }
+                const int cnt = min(32, n - base);
+                for (int j = 0; j < cnt; ++j) sum += __shfl_sync(FULL, v, j);
             }
-            __syncwarp();
-            float sum = 0.0f;                                // GameActionDist::sum, ascending index
-            for_each_legal(mpos, [&](int i) { sum += sm.pol[i]; });
-            __syncwarp();
-            if (sum == 0.0f) {
-                float uniform = 1.0f / (float)n;
-                for (int base = 0; base < n; base += 32) { int k = base + lane; if (k < n) sm.pol[legal_action<G>(mpos, k)] = uniform; }
+            const float uniform = 1.0f / (float)n;
+            const float inv = 1.0f / sum;                    // operator/(dist, float) = multiply by the reciprocal
+            if (n <= 32) {
+                if (lane < n) sm.pol[i] = (sum == 0.0f) ? uniform : v * inv;
             } else {
-                float inv = 1.0f / sum;                      // operator/(dist, float) = multiply by the reciprocal
                 for (int base = 0; base < n; base += 32) {
-                    int k = base + lane;
-                    if (k < n) { int i = legal_action<G>(mpos, k); sm.pol[i] = sm.pol[i] * inv; }
+                    const int k = base + lane;
+                    if (k < n) { i = legal_action<G>(mpos, k); sm.pol[i] = (sum == 0.0f) ? uniform : sm.pol[i] * inv; }
                 }
             }
             __syncwarp();

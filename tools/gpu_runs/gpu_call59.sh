@@ -1,4 +1,4 @@
-# Othello child creation with the direction loops spread over the lanes (next_warp): parity + bench
+# k_round instruction diet (next_warp, shuffle prior sum): parity + bench
 set -x
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --no-e2e --no-cpu-baseline --steps 3 2>/dev/null | python -c "
