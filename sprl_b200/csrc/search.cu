@@ -557,20 +557,6 @@ struct TreeWarp {
         return h;
     }
 
-    // every legal action in ascending index order (the pass last), one bit per step instead of an nth-set-bit search
-    template <class F>
-    __device__ __forceinline__ static void for_each_legal(const P& pos, F f) {
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            unsigned long long bits = pos.legal.word(w);
-            while (bits) {
-                f(w * 64 + __ffsll((long long)bits) - 1);
-                bits &= bits - 1ULL;
-            }
-        }
-        if (pos.pass_legal) f(G::CELLS);
-    }
-
     // ---- INetwork::evaluate for one leaf + inverse symmetry + UCTNode::addNetworkOutput ----
     // Policy entries live in the SYMMETRISED frame but are masked with the leaf's
     // un-symmetrised mask (uct/UCTTree.hpp:136-149, networks/GridNetwork.hpp:117-125:
