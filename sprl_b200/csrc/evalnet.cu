@@ -717,6 +717,9 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     float* wv = wp + K * HP_STRIDE;           // [cells][64]
     float* xbuf = wv + cells * 64;            // [2][HB][IN]: the next 64 boards arrive (cp.async) while these are computed
     float* hid = xbuf + 2 * HB * IN;          // [HB][65]
+    float* wt = hid + HB * 65;                // [K]: weights of output 64 when it is the only one past 64 (the pass action)
+    const bool lone_tail = A == 65;
+    const int a_main = lone_tail ? 64 : A;
     const int t = threadIdx.x;
     // stages the activations of boards b0 .. b0+63 into buffer `which` (rows past the batch are zero)
     auto stage = [&](long long b0, int which) {
@@ -734,6 +737,7 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     stage((long long)blockIdx.x * HB, 0);
     for (int i = t; i < K * HP_STRIDE; i += 256) { const int k = i / HP_STRIDE, a = i - k * HP_STRIDE; wp[i] = a < A ? net.pfc_wt[k * A + a] : 0.0f; }
     for (int i = t; i < cells * 64; i += 256) wv[i] = net.vfc1_wt[i];
+    if (lone_tail) for (int k = t; k < K; k += 256) wt[k] = net.pfc_wt[k * A + 64];
     const int ag = t & 15, bg = t >> 4;       // 16 output groups x 16 board groups
     int cur = 0;
     for (long long b0 = (long long)blockIdx.x * HB; b0 < batch; b0 += (long long)gridDim.x * HB, cur ^= 1) {
@@ -744,7 +748,7 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
         __syncthreads();
         const float* x = xbuf + cur * HB * IN;
         // policy_fc: outputs 4*ag .. 4*ag+3 for boards 4*bg .. 4*bg+3 (+ the outputs beyond 64, one per thread row)
-        for (int a0 = 4 * ag; a0 < A; a0 += 64) {
+        for (int a0 = 4 * ag; a0 < a_main; a0 += 64) {
             float acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -784,6 +788,20 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (4 * bg + i < nb && a0 + j < A) logits[(b0 + 4 * bg + i) * A + a0 + j] = acc[i][j] + net.pfc_b[a0 + j];
+        }
+        if (lone_tail) {
+            // Output 64 (Othello's pass) alone would cost the two lanes per warp that own outputs 0..3 a second full pass
+            // over K, i.e. double the policy phase for every warp.  Instead each warp takes 8 boards, the lanes split K
+            // (stride 32, ascending) and a butterfly adds the 32 partial sums: the same order for every board.
+            const int wid = t >> 5, ln = t & 31;
+            for (int i = 0; i < HB / 8; ++i) {
+                const int b = wid * (HB / 8) + i;
+                float sacc = 0.0f;
+                for (int k = ln; k < K; k += 32) sacc = fmaf(x[b * IN + k], wt[k], sacc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (ln == 0 && b < nb) logits[(b0 + b) * A + 64] = sacc + net.pfc_b[64];
+            }
         }
         {   // value_fc1 + ReLU
             float acc[4][4];
@@ -833,7 +851,7 @@ k_heads(NetDev net, long long batch, const unsigned* __restrict__ d_rows, float*
     }
 }
 
-static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + 2 * HB * (pc + 1) * cells + HB * 65) * sizeof(float); }
+static inline size_t heads_smem_bytes(int pc, int cells = 64) { return (size_t)(pc * cells * HP_STRIDE + cells * 64 + 2 * HB * (pc + 1) * cells + HB * 65 + pc * cells) * sizeof(float); }
 
 // ---- host: BN folding, hi/lo split, operand packing ------------------------------------------
 // Power-of-two shift that brings the largest |w| of a layer into (2^9, 2^10]: fp16 keeps 11 significant bits
