@@ -1,0 +1,3 @@
+# 8 GPUs with the round's final kernels
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 > gpurun_out/bench_8gpu_w.json 2> gpurun_out/bench_8gpu_w.err; echo rc=$?
+cat gpurun_out/bench_8gpu_w.json | cut -c1-400
