@@ -1078,8 +1078,8 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     err = cudaFuncSetAttribute(k_evalnet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
-    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)heads_smem_bytes(params->policy_channels, std::max(64, params->rows * params->cols)));
+    if (heads_smem_bytes(params->policy_channels, params->rows * params->cols) > 227 * 1024) { delete e; return fail(SPRL_E_INVALID, "head layers of %d channels x %d cells do not fit k_heads' shared memory", params->policy_channels, params->rows * params->cols); }
+    err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // the attribute is per process: always the maximum, whatever this evaluator's board
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     rc = pack_and_upload(e, params);
     if (rc) { e->release(); delete e; return rc; }
