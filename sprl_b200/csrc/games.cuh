@@ -206,7 +206,7 @@ struct Othello {
         return out;
     }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && (!defined(__CUDA_ARCH__) || __CUDA_ARCH__ >= 800)     // redux.sync: sm_80 and later
     // ---- warp-cooperative forms for kernels in which one warp owns a position (k_round): lane l walks
     //      direction l & 7 with per-lane shift amounts, branch-free, and the eight partial sets are OR-reduced
     //      by redux.sync.  All 32 lanes call with the same arguments and get the same result. ----
