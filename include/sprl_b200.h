@@ -214,6 +214,38 @@ int sprl_run_match(sprl_engine* e, const sprl_agent_config* h_agents /* [2] */, 
 int sprl_match_results(sprl_engine* e, int64_t cap_games, int8_t* h_winner, int32_t* h_moves, uint64_t* h_draws,
                        int64_t* wins /* [2] */, int64_t* draws);
 
+/* ------------------------------------------------------------------ step-wise trees
+ * UCTTree's public surface (uct/UCTTree.hpp:38-210) for many independent trees at once: what the move loops of
+ * selfPlay (selfplay/SelfPlay.hpp:82-146) and UCTNetworkAgent::act / opponentAct (agents/UCTNetworkAgent.hpp:42-108)
+ * do by hand -- search some descents, read the decision node's statistics, advance by an action of the CALLER's
+ * choice.  Search constants, evaluator, symmetrizer, noise and init-Q come from the engine's config. */
+
+/* UCTTree(root = start position, ...) (uct/UCTTree.hpp:38-57) for trees 0 .. num_trees-1 (<= num_slots); tree i draws
+ * from stream first_game + i * stride, as game i of an iteration would. */
+int sprl_begin_trees(sprl_engine* e, uint64_t first_game, int64_t num_trees);
+/* while (traversals < sims) { searchAndGetLeaves(maxBatch, maxQueue); evaluateAndBackpropLeaves(leaves); } for every
+ * live tree (uct/UCTTree.hpp:76-184 as driven by selfplay/SelfPlay.hpp:100-108; the loop adds whole batches, so a tree
+ * ends with sims .. sims + max_batch - 1 descents since its last advance).  Returns when every tree has spent its
+ * budget and all evaluations are backed up.  forward: as in sprl_run_iteration (NULL for device evaluators). */
+int sprl_search(sprl_engine* e, int sims, sprl_forward_fn forward, void* user);
+/* The two halves of one such loop trip, for callers that drive the evaluator themselves (a CUDA graph, another
+ * stream): sprl_search_batch enqueues ONE searchAndGetLeaves batch per live tree (leaf planes -> d_in, row counts ->
+ * sprl_eval_rows); after the network has written d_logits / d_value, sprl_apply_evaluations enqueues
+ * evaluateAndBackpropLeaves (:124-184) for the queued leaves.  Both asynchronous on the engine's stream. */
+int sprl_search_batch(sprl_engine* e);
+int sprl_apply_evaluations(sprl_engine* e);
+/* getDecisionNode() (uct/UCTTree.hpp:62) of every tree: its EdgeStatistics (uct/UCTNode.hpp:45-60) as dense rows
+ * N, W, P [num_trees, A] (P = the child priors in use: Dirichlet-mixed when add_noise; 0 before the node is expanded),
+ * the node's own N / W (the tree-level edge, uct/UCTTree.hpp:301), player to move, terminal flag, winner (-1/0/1),
+ * descents since the last advance, and the legal mask [num_trees, A] (GameNode::getActionMask).  Host arrays; any
+ * may be NULL.  Synchronises the stream. */
+int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, float* h_P, float* h_root_N, float* h_root_W,
+                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask);
+/* advanceDecision(h_actions[i]) for tree i (uct/UCTTree.hpp:197-210: prune the siblings, clear the kept subtree's
+ * statistics, keep its cached evaluations); -1 leaves a tree where it is.  An illegal action fails with
+ * SPRL_E_INVALID.  A tree whose new decision node is terminal stops (sprl_poll counts it as finished). */
+int sprl_advance(sprl_engine* e, const int32_t* h_actions, int64_t n_actions);
+
 typedef struct {
     uint64_t sims, evals, moves, games;
     uint64_t depth_sum, legal_sum, nodes_visited;
@@ -275,6 +307,16 @@ int sprl_evalnet_forward_counted(sprl_evalnet* net, const float* d_in, const uin
 int sprl_evalnet_status(sprl_evalnet* net, uint64_t* launches);
 /* Bytes copied host -> device by one create / update, weight-ring depth and shared memory per CTA. */
 int sprl_evalnet_info(sprl_evalnet* net, int64_t* upload_bytes, int32_t* ring_stages, int32_t* smem_bytes);
+/* Which kernel runs the conv tower.  AUTO: the resident-weight kernel (csrc/evalnet_resident.cuh: weights of one
+ * residual block stay in shared memory for a whole launch, one launch per block) when the board is at most 8x8 and
+ * a block fits, else the streaming kernel (weights re-read from L2 per tile; also Go 9x9).  Both compute the same
+ * arithmetic in the same order; STREAMING / RESIDENT force one of them (tests, A/B timing). */
+#define SPRL_EVALNET_PATH_AUTO 0
+#define SPRL_EVALNET_PATH_STREAMING 1
+#define SPRL_EVALNET_PATH_RESIDENT 2
+int sprl_evalnet_set_path(sprl_evalnet* net, int path);
+/* Launches of the resident-weight kernel per forward (0: the streaming kernel is in use). */
+int sprl_evalnet_phases(sprl_evalnet* net);
 void sprl_evalnet_destroy(sprl_evalnet* net);
 
 #ifdef __cplusplus

@@ -9,8 +9,13 @@
 //   match    <game> <evaluator0> <evaluator1> <seed> <first_game> <ngames> <sims> <batch> <queue>
 //            <sym0 0|1> <initq0> <sym1 0|1> <initq1> <out.trace>
 //
+//   npy      x <out.npy> <d0> [<d1> ...]       the array value[i] = 0.25 * i - 3 of that shape through the reference's own
+//                                              npy::write_npy (utils/npy.hpp:616-639), as selfplay/GridWorker.hpp:173-196 calls it
+//
 // evaluator = hash | hash1 (a second, independent HashNet) | uniform (networks/RandomNetwork.hpp)
-//           | heuristic (networks/OthelloHeuristic.cpp, Othello only).
+//           | heuristic (networks/OthelloHeuristic.cpp, Othello only)
+//           | pt:<file> (builds with -DSPRL_REF_WITH_TORCH only, `make ref_torch`: the reference's LibTorch
+//             GridNetwork, networks/GridNetwork.hpp:37-145, on a TorchScript file -- its own exp / mask / sum / divide).
 //
 // game = othello | c4 | go.  Randomness comes from random_shim.cpp (the
 // contract stream of oracle/oracle_rng.h).  `selfplay` runs every game twice:
@@ -33,6 +38,11 @@
 #include "selfplay/SelfPlay.hpp"
 #include "symmetry/ConnectFourSymmetrizer.hpp"
 #include "symmetry/D4GridSymmetrizer.hpp"
+
+#include "utils/npy.hpp"
+#ifdef SPRL_REF_WITH_TORCH
+#include "networks/GridNetwork.hpp"
+#endif
 
 #include "hashnet.hpp"
 
@@ -190,6 +200,12 @@ std::unique_ptr<INetwork<StateOf<D>, D::A>> makeEvaluator(const std::string& kin
     if (kind == "hash") return std::make_unique<SPRLREF::HashNet<D::R * D::C, D::H, D::A>>(0);
     if (kind == "hash1") return std::make_unique<SPRLREF::HashNet<D::R * D::C, D::H, D::A>>(1);
     if (kind == "uniform") return std::make_unique<RandomNetwork<State, D::A>>();
+#ifdef SPRL_REF_WITH_TORCH
+    if (kind.rfind("pt:", 0) == 0) {
+        torch::set_num_threads(1);
+        return std::make_unique<GridNetwork<D::R, D::C, D::H, D::A>>(kind.substr(3));
+    }
+#endif
     if constexpr (std::is_same_v<typename D::Node, OthelloNode>) {
         if (kind == "heuristic") return std::make_unique<OthelloHeuristic>();
     }
@@ -494,7 +510,20 @@ int dispatch(int argc, char** argv) {
     return 2;
 }
 
+// ---- npy: the reference's writer on a known array ------------------------------------------------
+static int cmdNpy(int argc, char** argv) {
+    npy::npy_data_ptr<float> d {};
+    size_t n = 1;
+    for (int i = 4; i < argc; ++i) { d.shape.push_back(std::strtoul(argv[i], 0, 10)); n *= d.shape.back(); }
+    std::vector<float> v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = 0.25f * (float)i - 3.0f;
+    d.data_ptr = v.data();
+    npy::write_npy(argv[3], d);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 5 && std::string(argv[1]) == "npy") return cmdNpy(argc, argv);
     if (argc < 3) { std::cerr << "usage: ref_trace <perft|rollout|selfplay> <othello|c4|go> ...\n"; return 2; }
     std::string game = argv[2];
     if (game == "othello") return dispatch<OthelloDesc>(argc, argv);

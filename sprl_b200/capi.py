@@ -15,14 +15,16 @@ SPRL_E_INVALID, SPRL_E_CUDA, SPRL_E_CAPACITY, SPRL_E_STATE, SPRL_E_IO, SPRL_E_NO
 GAME_OTHELLO, GAME_C4, GAME_GO7, GAME_GO9 = 0, 1, 2, 3
 EVAL_UNIFORM, EVAL_HASHNET, EVAL_EXTERNAL, EVAL_OTHELLO_HEURISTIC = 0, 1, 2, 3
 INITQ_ZERO, INITQ_PARENT, INITQ_DROP_PARENT = 0, 1, 2
+EVALNET_PATH_AUTO, EVALNET_PATH_STREAMING, EVALNET_PATH_RESIDENT = 0, 1, 2
 
 EXPORTS = [
     "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
     "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
     "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_eval_rows", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device",
-    "sprl_match_begin", "sprl_run_match", "sprl_match_results", "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
-    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_forward_counted", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_destroy",
+    "sprl_match_begin", "sprl_run_match", "sprl_match_results", "sprl_begin_trees", "sprl_search", "sprl_search_batch",
+    "sprl_apply_evaluations", "sprl_root_stats", "sprl_advance", "sprl_move_stats", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
+    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_forward_counted", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_set_path", "sprl_evalnet_phases", "sprl_evalnet_destroy",
 ]
 
 
@@ -110,6 +112,12 @@ def load():
     lib.sprl_run_match.argtypes = [C.c_void_p, C.POINTER(AgentConfig), C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.sprl_match_results.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]
+    lib.sprl_begin_trees.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+    lib.sprl_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sprl_search_batch.argtypes = [C.c_void_p]
+    lib.sprl_apply_evaluations.argtypes = [C.c_void_p]
+    lib.sprl_root_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10
+    lib.sprl_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.sprl_move_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.POINTER(C.c_int64)]
     lib.sprl_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.sprl_reset_stats.argtypes = [C.c_void_p]
@@ -124,6 +132,8 @@ def load():
     lib.sprl_evalnet_forward_counted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sprl_evalnet_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.sprl_evalnet_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.sprl_evalnet_set_path.argtypes = [C.c_void_p, C.c_int]
+    lib.sprl_evalnet_phases.argtypes = [C.c_void_p]
     lib.sprl_evalnet_destroy.restype = None
     lib.sprl_evalnet_destroy.argtypes = [C.c_void_p]
     lib.sprl_default_config.argtypes = [C.c_int, C.POINTER(Config)]

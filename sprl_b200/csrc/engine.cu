@@ -16,6 +16,9 @@ void search_launch_emit(int game, const EngineParams& p, const long long* row0, 
                         cudaStream_t s);
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
+void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,
+                              signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s);
+void search_launch_tree_advance(int game, const EngineParams& p, int n, const int* actions, cudaStream_t s);
 int search_header_units(int game);
 }  // namespace sprl
 
@@ -32,6 +35,10 @@ struct sprl_engine {
     bool iteration_open = false;
     bool match_open = false;        // the open iteration is a match (pairs of trees)
     MatchParams match;
+    IterParams* d_iter = nullptr;   // device copy of the per-iteration values (search.cuh)
+    bool stepwise = false;          // the open iteration is a set of step-wise trees (sprl_begin_trees)
+    int step_sims = 0;
+    unsigned char* d_tree_io = nullptr;     // staging of sprl_root_stats / sprl_advance, sized for num_slots trees
     bool failed = false;            // sticky CUDA error
     uint64_t launches = 0;
     uint64_t device_bytes = 0;
@@ -100,6 +107,18 @@ static int sum_tree_stats(sprl_engine* e, sprl_stats* out) {
     out->units_per_tree = e->p.cap_units;
     out->launches = e->launches;
     out->device_bytes = e->device_bytes;
+    return SPRL_OK;
+}
+
+// Publishes the per-iteration values on the stream (see IterParams: a captured graph must not freeze them).
+static int push_iter_params(sprl_engine* e) {
+    IterParams it;
+    memset(&it, 0, sizeof(it));
+    it.num_games = e->p.num_games; it.first_game = e->p.first_game; it.game_stride = e->p.game_stride; it.q_half = e->p.q_half;
+    it.stepwise = e->stepwise ? 1 : 0; it.step_sims = e->step_sims;
+    it.agent[0] = e->match.agent[0]; it.agent[1] = e->match.agent[1];
+    cudaError_t err = cudaMemcpyAsync(e->d_iter, &it, sizeof(it), cudaMemcpyHostToDevice, e->stream);   // pageable source: staged before the call returns
+    if (err != cudaSuccess) { e->failed = true; return fail(SPRL_E_CUDA, "cudaMemcpyAsync of the iteration parameters failed: %s", cudaGetErrorString(err)); }
     return SPRL_OK;
 }
 
@@ -203,6 +222,9 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (!rc) rc = e->alloc(&p.order, S * 2, true);
     if (!rc) rc = e->alloc(&p.order_cnt, 4, true);
     if (!rc) rc = e->alloc(&p.order_parity, 1, true);
+    if (!rc) rc = e->alloc(&e->d_iter, 1, true);
+    p.iter = e->d_iter;
+    memset(&e->match, 0, sizeof(e->match));
     if (!rc && cfg->record_stats) {
         rc = e->alloc(&p.rec_N, MG * MM * A, false);
         if (!rc) rc = e->alloc(&p.rec_W, MG * MM * A, false);
@@ -264,6 +286,7 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
     e->num_games = num_games;
     e->active_slots = std::min<int64_t>(num_games, e->cfg.num_slots);
     e->p.q_half = 0;
+    e->stepwise = false;
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_count, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_rows, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
@@ -275,6 +298,7 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
         ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_W, 0, bytes, e->stream));
         ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_P, 0, bytes, e->stream));
     }
+    { int rc = push_iter_params(e); if (rc) return rc; }
     search_launch_begin(e->cfg.game, e->p, e->stream);
     e->launches += 1;
     ENGINE_CUDA(e, cudaGetLastError());
@@ -306,6 +330,7 @@ int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t
         return fail(SPRL_E_STATE, "an agent with SPRL_EVAL_EXTERNAL needs an engine created with SPRL_EVAL_EXTERNAL");
     if (external && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
     e->match.n_pairs = e->cfg.num_slots / 2;
+    e->stepwise = false;
     e->p.first_game = first_game;
     e->p.num_games = num_games;
     e->num_games = num_games;
@@ -321,6 +346,7 @@ int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t
         ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_W, 0, bytes, e->stream));
         ENGINE_CUDA(e, cudaMemsetAsync(e->p.rec_P, 0, bytes, e->stream));
     }
+    { int rc = push_iter_params(e); if (rc) return rc; }
     search_launch_match_begin(e->cfg.game, e->p, e->match, e->stream);
     e->launches += 1;
     ENGINE_CUDA(e, cudaGetLastError());
@@ -390,6 +416,8 @@ static int report_slot_failure(sprl_engine* e) {
         if (ts[i].status == ST_ERR_CAPACITY)
             return fail(SPRL_E_CAPACITY, "tree slot %zu ran out of node units (units_per_tree=%llu, game %llu move %d); raise units_per_tree",
                         i, (unsigned long long)e->p.cap_units, (unsigned long long)ts[i].game_id, ts[i].move_count);
+        if (ts[i].status == ST_ERR_ACTION)
+            return fail(SPRL_E_INVALID, "tree %zu: the action passed to sprl_advance is not legal at its decision node (or the tree still has leaves waiting for the evaluator)", i);
         if (ts[i].status == ST_ERR_MOVES)
             return fail(SPRL_E_CAPACITY, "tree slot %zu exceeded %d moves in one game", i, e->p.max_moves);
     }
@@ -544,6 +572,132 @@ int sprl_move_stats(sprl_engine* e, int64_t cap_moves, float* h_N, float* h_W, f
     if (h_game_moves) memcpy(h_game_moves, e->h_moves.data(), (size_t)e->num_games * sizeof(int));
     if (h_game_draws) ENGINE_CUDA(e, cudaMemcpyAsync(h_game_draws, e->p.rec_draws, (size_t)e->num_games * 8, cudaMemcpyDeviceToHost, e->stream));
     ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    return SPRL_OK;
+}
+
+int sprl_begin_trees(sprl_engine* e, uint64_t first_game, int64_t num_trees) {
+    ENGINE_CHECK(e);
+    if (num_trees <= 0 || num_trees > e->cfg.num_slots) return fail(SPRL_E_INVALID, "num_trees must be in 1..num_slots (%d)", e->cfg.num_slots);
+    e->stepwise = false;
+    int rc = sprl_begin_iteration(e, first_game, num_trees);      // one game per tree, started at the start position
+    if (rc) return rc;
+    e->stepwise = true;
+    e->step_sims = 0;
+    return push_iter_params(e);
+}
+
+static int stepwise_check(sprl_engine* e) {
+    if (!e->iteration_open || !e->stepwise) return fail(SPRL_E_STATE, "no step-wise trees: call sprl_begin_trees first");
+    return SPRL_OK;
+}
+
+// runs launches until no tree searched or waited for evaluations in the last one
+static int stepwise_rounds(sprl_engine* e, sprl_forward_fn forward, void* user, int max_launches) {
+    const bool external = e->cfg.evaluator == SPRL_EVAL_EXTERNAL;
+    if (external && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
+    int rc = push_iter_params(e);
+    if (rc) return rc;
+    for (int done = 0; max_launches <= 0 || done < max_launches;) {
+        const int group = max_launches > 0 ? max_launches - done : 8;
+        for (int i = 0; i < group; ++i, ++done) {
+            rc = sprl_round(e);
+            if (rc) return rc;
+            if (external) {
+                rc = forward(user, e->p.nn_in, sprl_eval_batch(e), const_cast<float*>(e->p.nn_logits), const_cast<float*>(e->p.nn_value), (void*)e->stream);
+                if (rc) return fail(SPRL_E_STATE, "forward callback returned %d", rc);
+            }
+        }
+        unsigned long long c[4] = { 0, 0, 0, 0 };
+        ENGINE_CUDA(e, cudaMemcpyAsync(c, e->p.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+        ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (c[1] > 0) return report_slot_failure(e);
+        if (c[3] == 0) break;
+    }
+    return SPRL_OK;
+}
+
+int sprl_search(sprl_engine* e, int sims, sprl_forward_fn forward, void* user) {
+    ENGINE_CHECK(e);
+    int rc = stepwise_check(e);
+    if (rc) return rc;
+    if (sims < 0) return fail(SPRL_E_INVALID, "sims must not be negative");
+    e->step_sims = sims;
+    return stepwise_rounds(e, forward, user, 0);
+}
+
+int sprl_search_batch(sprl_engine* e) {
+    ENGINE_CHECK(e);
+    int rc = stepwise_check(e);
+    if (rc) return rc;
+    e->step_sims = 0x7fffffff;
+    rc = push_iter_params(e);
+    if (!rc) rc = sprl_round(e);
+    return rc;
+}
+
+int sprl_apply_evaluations(sprl_engine* e) {
+    ENGINE_CHECK(e);
+    int rc = stepwise_check(e);
+    if (rc) return rc;
+    e->step_sims = 0;               // every tree only applies what is queued, then waits
+    rc = push_iter_params(e);
+    if (!rc) rc = sprl_round(e);
+    return rc;
+}
+
+int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, float* h_P, float* h_root_N, float* h_root_W,
+                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask) {
+    ENGINE_CHECK(e);
+    int rc = stepwise_check(e);
+    if (rc) return rc;
+    const int64_t n = e->num_games;
+    if (cap_trees < n) return fail(SPRL_E_CAPACITY, "%lld trees do not fit the caller's capacity %lld", (long long)n, (long long)cap_trees);
+    const size_t A = (size_t)e->gi.actions, S = (size_t)e->cfg.num_slots;
+    // staging: N, W, P [S][A] floats | root_N, root_W [S] floats | traversals [S] ints | player, terminal, winner [S] | mask [S][A]
+    const size_t bytes = 3 * S * A * 4 + 3 * S * 4 + 3 * S + S * A;
+    if (!e->d_tree_io) {
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_tree_io, std::max(bytes, S * sizeof(int))));
+        e->allocations.push_back(e->d_tree_io);
+    }
+    float* dN = (float*)e->d_tree_io; float* dW = dN + S * A; float* dP = dW + S * A;
+    float* drn = dP + S * A; float* drw = drn + S;
+    int* dtr = (int*)(drw + S);
+    signed char* dpl = (signed char*)(dtr + S); signed char* dte = dpl + S; signed char* dwi = dte + S; signed char* dmk = dwi + S;
+    search_launch_tree_stats(e->cfg.game, e->p, (int)n, dN, dW, dP, drn, drw, dpl, dte, dwi, dtr, dmk, e->stream);
+    e->launches += 1;
+    ENGINE_CUDA(e, cudaGetLastError());
+    if (h_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_N, dN, (size_t)n * A * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_W) ENGINE_CUDA(e, cudaMemcpyAsync(h_W, dW, (size_t)n * A * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_P) ENGINE_CUDA(e, cudaMemcpyAsync(h_P, dP, (size_t)n * A * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_root_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_N, drn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_root_W) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_W, drw, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_traversals) ENGINE_CUDA(e, cudaMemcpyAsync(h_traversals, dtr, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_player) ENGINE_CUDA(e, cudaMemcpyAsync(h_player, dpl, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    if (h_terminal) ENGINE_CUDA(e, cudaMemcpyAsync(h_terminal, dte, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    if (h_winner) ENGINE_CUDA(e, cudaMemcpyAsync(h_winner, dwi, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    if (h_mask) ENGINE_CUDA(e, cudaMemcpyAsync(h_mask, dmk, (size_t)n * A, cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    return SPRL_OK;
+}
+
+int sprl_advance(sprl_engine* e, const int32_t* h_actions, int64_t n_actions) {
+    ENGINE_CHECK(e);
+    int rc = stepwise_check(e);
+    if (rc) return rc;
+    if (!h_actions || n_actions != e->num_games) return fail(SPRL_E_INVALID, "sprl_advance takes one action per tree (%lld)", (long long)e->num_games);
+    const size_t S = (size_t)e->cfg.num_slots, A = (size_t)e->gi.actions;
+    if (!e->d_tree_io) {
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_tree_io, 3 * S * A * 4 + 3 * S * 4 + 3 * S + S * A));
+        e->allocations.push_back(e->d_tree_io);
+    }
+    ENGINE_CUDA(e, cudaMemcpyAsync(e->d_tree_io, h_actions, (size_t)n_actions * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    search_launch_tree_advance(e->cfg.game, e->p, (int)n_actions, (const int*)e->d_tree_io, e->stream);
+    e->launches += 1;
+    ENGINE_CUDA(e, cudaGetLastError());
+    unsigned long long c[4] = { 0, 0, 0, 0 };
+    ENGINE_CUDA(e, cudaMemcpyAsync(c, e->p.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (c[1] > 0) return report_slot_failure(e);
     return SPRL_OK;
 }
 

@@ -702,6 +702,8 @@ k_evalnet(NetDev net, const float* __restrict__ in, long long batch, const unsig
     }
 }
 
+#include "evalnet_resident.cuh"
+
 // ---- heads: policy_fc and value_fc1/fc2 over the 1x1-conv activations k_evalnet left in HBM ----
 // 64 boards per CTA, weights staged once in shared memory, 4 boards x 4 outputs per thread.
 constexpr int HB = 64;                        // boards per CTA
@@ -886,6 +888,23 @@ static void append_units(std::vector<unsigned short>& out, const std::vector<std
                     }
 }
 
+// Resident format (k_evalnet_resident): the weights of one vertical offset held by CTA `h` of a pair,
+// [K chunk of 8][hi rows | lo rows][8 halfs] over this CTA's half of the rows (row = dx * n_pad + n).
+static void append_resident(std::vector<unsigned short>& out, const std::vector<std::vector<float>>& b, int n_pad, int kk, int shift, int h) {
+    const int ndx = (int)b.size(), rows = ndx * n_pad, rows_per = rows / 2;
+    for (int kc = 0; kc < kk / KCH; ++kc)
+        for (int part = 0; part < 2; ++part)
+            for (int r = h * rows_per; r < (h + 1) * rows_per; ++r) {
+                const int dx = r / n_pad, n = r - dx * n_pad;
+                for (int j = 0; j < KCH; ++j) {
+                    const float w = std::ldexp(b[dx][(size_t)n * kk + kc * KCH + j], shift);
+                    const __half hi = __float2half_rn(w);
+                    const __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
+                    out.push_back(__half_as_ushort(v));
+                }
+            }
+}
+
 }  // namespace evalnet
 }  // namespace sprl
 
@@ -902,6 +921,12 @@ struct sprl_evalnet {
     int64_t upload_bytes = 0;      // host -> device bytes of one weight load
     float* head_act = nullptr;     // [head_cap][(policy_channels + 1) * 64]
     int64_t head_cap = 0;
+    // resident-weight path (k_evalnet_resident): one launch per phase, activations between phases in `act`
+    std::vector<RbPhase> phases;   // empty: this network only runs on the streaming kernel
+    const unsigned short* rb_weights = nullptr;
+    float* act = nullptr;          // [act_cap_tiles][RB_ACT_TILE_FLOATS]
+    int64_t act_cap_tiles = 0;
+    int path = 0;                  // SPRL_EVALNET_PATH_*: 0 auto (resident when the network fits), 1 streaming, 2 resident
     // First call allocates; later calls (a new generation's weights) overwrite in place, so device
     // pointers captured in a CUDA graph stay valid.
     template <typename T> int upload(const std::vector<T>& h, const T** out) {
@@ -923,6 +948,9 @@ struct sprl_evalnet {
         allocations.clear();
         if (head_act) cudaFree(head_act);
         head_act = nullptr; head_cap = 0;
+        if (act) cudaFree(act);
+        act = nullptr; act_cap_tiles = 0;
+        rb_weights = nullptr;
     }
 };
 
@@ -938,6 +966,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     const double eps = p->bn_eps > 0 ? p->bn_eps : 1e-5;
     std::vector<unsigned short> units;
     std::vector<float> bias((size_t)L * C, 0.0f);
+    struct LayerW { std::vector<std::vector<float>> b; int n_pad, kk, shift; };       // b[dy * ndx + dx][n * kk + k], kept for the resident format
+    std::vector<LayerW> layers;
     auto conv_layer = [&](const sprl_conv_bn_params& c, int cin, int kk, int layer) {
         std::vector<double> scale(C);
         for (int co = 0; co < C; ++co) {
@@ -953,6 +983,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         e->dev.inv_scale[layer] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
         for (int dy = 0; dy < 3; ++dy)
             append_units(units, std::vector<std::vector<float>>(b.begin() + 3 * dy, b.begin() + 3 * dy + 3), C, kk, shift);
+        layers.push_back(LayerW{ std::move(b), C, kk, shift });
     };
     {   // stem: K index dy * P + plane, one unit group with the three dx stacked along N
         const sprl_conv_bn_params& c = p->stem;
@@ -968,6 +999,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         const int shift = weight_shift(b);
         e->dev.inv_scale[0] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
         append_units(units, b, C, in_k, shift);
+        layers.push_back(LayerW{ std::move(b), C, in_k, shift });
     }
     for (int i = 0; i < 2 * p->blocks; ++i) conv_layer(p->tower[i], C, C, 1 + i);
     {   // heads: rows 0..pc-1 policy_conv, row pc value_conv
@@ -983,6 +1015,63 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         const int shift = weight_shift(bb);
         e->dev.inv_scale[L - 1] = std::ldexp(1.0f, -(ACT_SHIFT + shift));
         append_units(units, bb, HEAD_N, C, shift);
+        layers.push_back(LayerW{ std::move(bb), HEAD_N, C, shift });
+    }
+    // ---- resident format: phases of [stem] [conv, conv] [heads] stages, as many per launch as shared memory holds
+    std::vector<RbPhase> phases;
+    std::vector<unsigned short> rbw;
+    if (p->rows <= 8 && p->cols <= 8) {
+        const int budget = RB_MAX_SMEM - RB_OFF_W - RB_MAX_STAGES * CH * 4 - 64 - 16;
+        std::vector<std::vector<RbStage>> plan(1);
+        std::vector<int> plan_bytes(1, 0);
+        auto add_group = [&](std::vector<RbStage> group) {
+            int bytes = 0;
+            for (const RbStage& st : group) bytes += rb_stage_bytes(st.kind, st.ksteps);
+            if (!plan.back().empty() && (plan_bytes.back() + bytes > budget || plan.back().size() + group.size() > (size_t)RB_MAX_STAGES)) {
+                plan.emplace_back(); plan_bytes.push_back(0);
+            }
+            for (const RbStage& st : group) plan.back().push_back(st);
+            plan_bytes.back() += bytes;
+        };
+        add_group({ RbStage{ RB_STEM, 0, in_k / KSTEP_CH, 0, 0, 0, 0 } });
+        for (int b = 0; b < p->blocks; ++b)
+            add_group({ RbStage{ RB_CONV, 1 + 2 * b, CH / KSTEP_CH, 0, 0, 0, 0 }, RbStage{ RB_CONV, 2 + 2 * b, CH / KSTEP_CH, 0, 1, 0, 0 } });
+        add_group({ RbStage{ RB_HEADS, L - 1, CH / KSTEP_CH, 0, 0, 0, 0 } });
+        bool fits = true;
+        for (size_t i = 0; i < plan.size(); ++i) fits = fits && plan_bytes[i] <= budget;
+        if (fits) {
+            std::vector<size_t> w_at;                       // offset (in halfs) of every phase's [rank 0 | rank 1] weights
+            for (size_t i = 0; i < plan.size(); ++i) {
+                RbPhase ph;
+                memset(&ph, 0, sizeof(ph));
+                ph.n_stages = (int)plan[i].size();
+                ph.in_planes_mode = plan[i][0].kind == RB_STEM ? 1 : 0;
+                int off = 0;
+                for (int j = 0; j < ph.n_stages; ++j) {
+                    RbStage st = plan[i][j];
+                    st.w_off = off;
+                    off += rb_stage_bytes(st.kind, st.ksteps);
+                    const bool last = j + 1 == ph.n_stages;
+                    st.save_res = (!last && st.kind != RB_HEADS && plan[i][j + 1].kind == RB_CONV && !plan[i][j + 1].add_res) ? 1 : 0;
+                    st.out_global = (last && st.kind != RB_HEADS) ? 1 : 0;
+                    ph.st[j] = st;
+                }
+                ph.w_bytes = (off + 127) / 128 * 128;
+                w_at.push_back(rbw.size());
+                for (int h = 0; h < 2; ++h) {
+                    const size_t start = rbw.size();
+                    for (int j = 0; j < ph.n_stages; ++j) {
+                        const LayerW& lw = layers[ph.st[j].layer];
+                        const int ndy = rb_stage_ndy(ph.st[j].kind), ndx = (int)lw.b.size() / ndy;
+                        for (int dy = 0; dy < ndy; ++dy)
+                            append_resident(rbw, std::vector<std::vector<float>>(lw.b.begin() + ndx * dy, lw.b.begin() + ndx * dy + ndx), lw.n_pad, lw.kk, lw.shift, h);
+                    }
+                    rbw.resize(start + (size_t)ph.w_bytes / 2, 0);
+                }
+                phases.push_back(ph);
+            }
+            for (size_t i = 0; i < phases.size(); ++i) phases[i].w = reinterpret_cast<const unsigned char*>(w_at[i] * 2);   // offsets until the upload below
+        }
     }
     const int cells = p->rows * p->cols;
     const int A = p->actions, K = p->policy_channels * cells;
@@ -1012,6 +1101,11 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     if (getenv("SPRL_EVALNET_NST")) e->dev.nst = std::max(2, std::min(MAX_NST, atoi(getenv("SPRL_EVALNET_NST"))));   // experiments
     while (e->dev.nst > 2 && smem_bytes_for(L, e->dev.nst) > MAX_SMEM) e->dev.nst -= 1;
     int rc = e->upload(units, &e->dev.wunits);
+    if (!rc && !phases.empty()) {
+        rc = e->upload(rbw, &e->rb_weights);
+        for (RbPhase& ph : phases) ph.w = reinterpret_cast<const unsigned char*>(e->rb_weights) + reinterpret_cast<size_t>(ph.w);
+    }
+    if (!rc) e->phases = phases;
     if (!rc) rc = e->upload(bias, &e->dev.bias);
     if (!rc) rc = e->upload(pfc_wt, &e->dev.pfc_wt);
     if (!rc) rc = e->upload(pfc_b, &e->dev.pfc_b);
@@ -1075,8 +1169,10 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err)); }
     if (prop.major != 10) { delete e; return fail(SPRL_E_NOGPU, "the tcgen05 evaluator needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
     e->sm_count = prop.multiProcessorCount;
+    if (getenv("SPRL_EVALNET_PATH")) e->path = atoi(getenv("SPRL_EVALNET_PATH"));      // experiments: 1 streaming, 2 resident
     err = cudaFuncSetAttribute(k_evalnet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     if (heads_smem_bytes(params->policy_channels, params->rows * params->cols) > 227 * 1024) { delete e; return fail(SPRL_E_INVALID, "head layers of %d channels x %d cells do not fit k_heads' shared memory", params->policy_channels, params->rows * params->cols); }
     err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // the attribute is per process: always the maximum, whatever this evaluator's board
@@ -1125,6 +1221,41 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
     }
     e->dev.head_act = e->head_act;
     const long long tiles = e->dev.linear ? batch : (batch + 1) / 2;
+    const bool resident = !e->phases.empty() && e->path != SPRL_EVALNET_PATH_STREAMING;
+    if (e->path == SPRL_EVALNET_PATH_RESIDENT && e->phases.empty())
+        return fail(SPRL_E_STATE, "this network does not fit the resident-weight kernel (boards up to 8x8, one stage group per launch within 227 KB)");
+    if (resident) {
+        const long long quads = (tiles + 3) / 4;
+        if (e->phases.size() > 1 && quads * 4 > e->act_cap_tiles) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing((cudaStream_t)cuda_stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) return fail(SPRL_E_STATE, "sprl_evalnet_forward: first call with batch %lld inside a stream capture; run one forward of this size before capturing", (long long)batch);
+            cudaDeviceSynchronize();
+            if (e->act) cudaFree(e->act);
+            e->act = nullptr; e->act_cap_tiles = 0;
+            err = cudaMalloc((void**)&e->act, (size_t)quads * 4 * RB_ACT_TILE_FLOATS * sizeof(float));
+            if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of the inter-phase activations failed: %s", cudaGetErrorString(err));
+            e->act_cap_tiles = quads * 4;
+        }
+        const int grid = (int)std::min<long long>(2 * quads, (long long)(e->sm_count / 2 * 2));     // one CTA per SM, in pairs
+        for (RbPhase ph : e->phases) {
+            ph.act = e->act;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(RB_THREADS);
+            cfg.dynamicSmemBytes = (size_t)rb_smem_bytes(ph);
+            cfg.stream = (cudaStream_t)cuda_stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            err = cudaLaunchKernelEx(&cfg, k_evalnet_resident, e->dev, ph, d_in, (long long)batch, (const unsigned*)d_rows);
+            e->launches += 1;
+            if (err == cudaSuccess) err = cudaGetLastError();
+            if (err != cudaSuccess) break;
+        }
+    } else {
     const int max_grid = e->sm_count * CTAS_PER_SM / CLUSTER * CLUSTER;
     const int grid = (int)std::min<long long>((tiles + CLUSTER - 1) / CLUSTER * CLUSTER, max_grid);
     cudaLaunchConfig_t cfg = {};
@@ -1141,6 +1272,7 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
                         : cudaLaunchKernelEx(&cfg, k_evalnet<false>, e->dev, d_in, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
     e->launches += 1;
     if (err == cudaSuccess) err = cudaGetLastError();
+    }
     if (err == cudaSuccess) {
         const int hgrid = (int)std::min<long long>((batch + HB - 1) / HB, (long long)e->sm_count);     // one resident CTA per SM (its weights are staged once)
         k_heads<<<hgrid, 256, heads_smem_bytes(e->policy_channels, e->rows * e->cols), (cudaStream_t)cuda_stream>>>(e->dev, (long long)batch, (const unsigned*)d_rows, d_logits, d_value);
@@ -1177,6 +1309,20 @@ int sprl_evalnet_info(sprl_evalnet* e, int64_t* upload_bytes, int32_t* ring_stag
     if (ring_stages) *ring_stages = e->dev.nst;
     if (smem_bytes) *smem_bytes = smem_bytes_for(e->dev.n_layers, e->dev.nst);
     return SPRL_OK;
+}
+
+int sprl_evalnet_set_path(sprl_evalnet* e, int path) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    if (path < SPRL_EVALNET_PATH_AUTO || path > SPRL_EVALNET_PATH_RESIDENT) return fail(SPRL_E_INVALID, "unknown evaluator path %d", path);
+    if (path == SPRL_EVALNET_PATH_RESIDENT && e->phases.empty())
+        return fail(SPRL_E_STATE, "this network does not fit the resident-weight kernel");
+    e->path = path;
+    return SPRL_OK;
+}
+
+int sprl_evalnet_phases(sprl_evalnet* e) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    return (e->phases.empty() || e->path == SPRL_EVALNET_PATH_STREAMING) ? 0 : (int)e->phases.size();
 }
 
 void sprl_evalnet_destroy(sprl_evalnet* e) {

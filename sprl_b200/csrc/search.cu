@@ -283,7 +283,7 @@ struct TreeWarp {
     }
 
     __device__ void init_game() {
-        st.game_id = p.first_game + (unsigned long long)st.game_index * p.game_stride;
+        st.game_id = p.iter->first_game + (unsigned long long)st.game_index * p.iter->game_stride;
         rng.game = st.game_id; rng.ctr = 0;
         st.slab = 0; slab = slab_ptr(0);
         st.traversals = 0; st.move_count = 0; st.n_queued = 0;
@@ -495,7 +495,7 @@ struct TreeWarp {
         u32 row0 = 0;                                   // rows of the evaluator batch for this tree's leaves
         if (cfg_evaluator() == SPRL_EVAL_EXTERNAL && nq > 0) {
             const int side = MATCH ? agent.pad : 0;
-            if (lane == 0) row0 = atomicAdd(&p.q_count[side], (u32)nq) + (side ? p.q_half : 0u);
+            if (lane == 0) row0 = atomicAdd(&p.q_count[side], (u32)nq) + (side ? p.iter->q_half : 0u);
             row0 = __shfl_sync(FULL, row0, 0);
             if (lane == 0) p.q_base[tree] = row0;
         }
@@ -826,7 +826,7 @@ struct TreeWarp {
             }
             if (record) acc.games += 1;
             st.game_index += game_step;                  // static striding: game -> slot is deterministic
-            if (st.game_index < p.num_games) init_game();
+            if (st.game_index < p.iter->num_games) init_game();
             else { st.status = ST_DONE; }
         }
     }
@@ -920,6 +920,37 @@ struct TreeWarp {
         if (!advance_root(h, pos, action_slot<G>(pos, action), action)) return;
         after_move(false);
     }
+
+    // ---- UCTTree::advanceDecision(action) by the caller (uct/UCTTree.hpp:197-210), step-wise trees: the position is
+    //      recorded (history of later network inputs, superko), the tree re-roots, a finished game stops the tree ----
+    __device__ void caller_move(int action) {
+        H h;
+        HL<W>::load(slab + ROOT_UNIT, h);
+        P pos;
+        hdr_to_pos<G>(h, pos);
+        const int n = META_NLEGAL(h.meta);
+        const bool legal = !META_TERMINAL(h.meta) && action >= 0 &&
+                           ((G::HAS_PASS && action == G::CELLS) ? pos.pass_legal != 0 : (action < G::CELLS && pos.legal.test(action)));
+        if (!legal || st.n_queued > 0) { st.status = ST_ERR_ACTION; return; }
+        if (st.move_count >= p.max_moves) { st.status = ST_ERR_MOVES; return; }
+        const size_t ri = rec_index();
+        record_root(h, pos, n, ri);
+        if (p.record_stats && lane == 0) p.rec_action[ri] = action;
+        for (int i = lane; i < G::ACTIONS; i += 32) p.rec_pdf[ri * G::ACTIONS + i] = 0.0f;     // no distribution: the caller chose
+        __syncwarp();
+        if (!advance_root(h, pos, action_slot<G>(pos, action), action)) return;
+        acc.moves += 1;
+        const u32 rmeta = *HL<W>::meta_ptr(slab + ROOT_UNIT);
+        if (META_TERMINAL(rmeta)) {
+            if (lane == 0) {
+                p.rec_moves[st.game_index] = st.move_count;
+                p.rec_winner[st.game_index] = (unsigned char)META_WINNER(rmeta);
+                p.rec_draws[st.game_index] = rng.ctr;
+            }
+            acc.games += 1;
+            st.status = ST_DONE;
+        }
+    }
 };
 
 // ---- kernels -------------------------------------------------------------------------------------
@@ -938,7 +969,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_begin(EngineParams p) 
     t.st.game_index = warp;
     t.st.status = ST_IDLE;
     t.st.n_queued = 0;
-    if (t.st.game_index < p.num_games) { t.st.status = ST_PLAYING; t.init_game(); }
+    if (t.st.game_index < p.iter->num_games) { t.st.status = ST_PLAYING; t.init_game(); }
     else { t.st.status = ST_DONE; }
     t.save();
     if (lane == 0) {
@@ -960,6 +991,7 @@ __device__ __forceinline__ void order_next(const EngineParams& p, u32 parity, in
 __global__ void k_flip(EngineParams p) {
     p.q_rows[0] = p.q_count[0]; p.q_rows[1] = p.q_count[1];
     p.q_count[0] = 0u; p.q_count[1] = 0u;
+    p.counters[3] = p.counters[2]; p.counters[2] = 0ULL;
     const u32 parity = *p.order_parity;
     p.order_cnt[parity * 2u] = 0u;
     p.order_cnt[parity * 2u + 1u] = 0u;
@@ -978,17 +1010,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_rou
         return;
     }
     TreeWarp<G> t(p, warp, lane, scratch[threadIdx.x >> 5]);
+    const bool stepwise = p.iter->stepwise != 0;
+    const int sims = stepwise ? p.iter->step_sims : p.sims;
+    bool waiting = false;                       // step-wise: the budget of the current move is spent, the caller moves
     for (int iter = 0; iter < p.rounds_per_launch; ++iter) {
         if (t.st.n_queued > 0) t.apply_leaves();
-        if (t.st.traversals >= p.sims) t.finalize_move();
+        if (t.st.traversals >= sims) {
+            if (stepwise) { waiting = true; break; }
+            t.finalize_move();
+        }
         if (t.st.status != ST_PLAYING) break;
         t.search_batch();
         if (t.st.status != ST_PLAYING) break;
         if (p.evaluator == SPRL_EVAL_EXTERNAL) break;
     }
     if (t.st.status != ST_PLAYING && lane == 0) atomicAdd(&p.counters[t.st.status == ST_DONE ? 0 : 1], 1ULL);
+    if (stepwise && !waiting && t.st.status == ST_PLAYING && lane == 0) atomicAdd(&p.counters[2], 1ULL);
     t.save();
-    if (lane == 0) order_next(p, parity, warp, t.st.status == ST_PLAYING && t.st.traversals >= p.sims);
+    if (lane == 0) order_next(p, parity, warp, !stepwise && t.st.status == ST_PLAYING && t.st.traversals >= p.sims);
 }
 
 // ---- match play (Evaluate.cpp:93-157, evaluate/play.hpp:24-69): one warp per PAIR of trees ----
@@ -1003,10 +1042,10 @@ __global__ void __launch_bounds__(32) k_match_begin(EngineParams p, MatchParams 
     if (pair >= m.n_pairs) return;
     unsigned long long game_id = 0;
     for (int k = 0; k < 2; ++k) {
-        TreeWarp<G, true> t(p, k * m.n_pairs + pair, lane, scratch, &m.agent[k], m.n_pairs);
+        TreeWarp<G, true> t(p, k * m.n_pairs + pair, lane, scratch, &p.iter->agent[k], m.n_pairs);
         t.st.game_index = pair;
         t.st.n_queued = 0;
-        if (t.st.game_index < p.num_games) { t.st.status = ST_PLAYING; t.init_game(); }
+        if (t.st.game_index < p.iter->num_games) { t.st.status = ST_PLAYING; t.init_game(); }
         else t.st.status = ST_DONE;
         game_id = t.st.game_id;
         t.save();
@@ -1026,7 +1065,7 @@ __global__ void __launch_bounds__(32) k_match_round(EngineParams p, MatchParams 
     unsigned long long game_id, rng_ctr;
     long long game_index;
     {
-        TreeWarp<G, true> t(p, active * m.n_pairs + pair, lane, scratch, &m.agent[active], m.n_pairs);
+        TreeWarp<G, true> t(p, active * m.n_pairs + pair, lane, scratch, &p.iter->agent[active], m.n_pairs);
         for (int iter = 0; iter < p.rounds_per_launch; ++iter) {
             if (t.st.n_queued > 0) t.apply_leaves();
             if (t.st.traversals >= p.sims) { action = t.finalize_match_move(); break; }
@@ -1039,7 +1078,7 @@ __global__ void __launch_bounds__(32) k_match_round(EngineParams p, MatchParams 
         t.save();
     }
     if (action >= 0) {
-        TreeWarp<G, true> o(p, (active ^ 1) * m.n_pairs + pair, lane, scratch, &m.agent[active ^ 1], m.n_pairs);
+        TreeWarp<G, true> o(p, (active ^ 1) * m.n_pairs + pair, lane, scratch, &p.iter->agent[active ^ 1], m.n_pairs);
         o.follow_move(action);                      // same position: same terminal test, same next game
         if (o.st.status == ST_ERR_CAPACITY) status = ST_ERR_CAPACITY;
         else { o.st.status = status; o.st.move_count = move_count; o.st.game_id = game_id; o.rng.game = game_id; o.rng.ctr = rng_ctr; o.st.game_index = game_index; }
@@ -1055,6 +1094,62 @@ __global__ void __launch_bounds__(32) k_match_round(EngineParams p, MatchParams 
         p.trees[m.n_pairs + pair].status = status;
         atomicAdd(&p.counters[status == ST_DONE ? 0 : 1], 1ULL);
     }
+}
+
+// ---- step-wise trees: the decision node's edge statistics (getDecisionNode()->getEdgeStatistics(), uct/UCTNode.hpp:45-60)
+//      as dense [A] rows, and advanceDecision by the caller's action ----
+template <class G>
+__global__ void __launch_bounds__(32) k_tree_stats(EngineParams p, int n_trees, float* __restrict__ N, float* __restrict__ Wt, float* __restrict__ P,
+                                                   float* __restrict__ root_N, float* __restrict__ root_W, signed char* __restrict__ player,
+                                                   signed char* __restrict__ terminal, signed char* __restrict__ winner,
+                                                   int* __restrict__ traversals, signed char* __restrict__ mask) {
+    const int tree = blockIdx.x, lane = threadIdx.x;
+    if (tree >= n_trees) return;
+    const TreeState& g = p.trees[tree];
+    const uint4* slab = p.pool + ((size_t)tree * 2 + g.slab) * p.cap_units;
+    constexpr int HDR = HL<G::W>::HDR;
+    Hdr<G::W> h;
+    HL<G::W>::load(slab + ROOT_UNIT, h);
+    const int n = META_NLEGAL(h.meta);
+    const bool expanded = (h.meta & META_EXPANDED) != 0;
+    for (int i = lane; i < G::ACTIONS; i += 32) {
+        const size_t at = (size_t)tree * G::ACTIONS + i;
+        if (N) N[at] = 0.0f;
+        if (Wt) Wt[at] = 0.0f;
+        if (P) P[at] = 0.0f;
+        if (mask) mask[at] = 0;
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+        const uint4 e = slab[ROOT_UNIT + HDR + k];
+        const size_t at = (size_t)tree * G::ACTIONS + EDGE_ACTION(e.w);
+        if (N) N[at] = __uint_as_float(e.z);
+        if (Wt) Wt[at] = __uint_as_float(e.y);
+        if (P) P[at] = !expanded ? 0.0f : (p.add_noise ? p.root_p[(size_t)tree * G::ACTIONS + k] : __uint_as_float(e.x));
+        if (mask) mask[at] = 1;
+    }
+    if (lane == 0) {
+        const uint4 d = slab[0];
+        if (root_W) root_W[tree] = __uint_as_float(d.y);
+        if (root_N) root_N[tree] = __uint_as_float(d.z);
+        if (player) player[tree] = (signed char)META_PLAYER(h.meta);
+        if (terminal) terminal[tree] = (signed char)META_TERMINAL(h.meta);
+        if (winner) winner[tree] = (signed char)((int)META_WINNER(h.meta) - 1);      // device encoding: 0 none, 1 ZERO, 2 ONE
+        if (traversals) traversals[tree] = g.traversals;
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(32) k_tree_advance(EngineParams p, int n_trees, const int* __restrict__ actions) {
+    __shared__ WarpScratch scratch;
+    const int tree = blockIdx.x, lane = threadIdx.x;
+    if (tree >= n_trees) return;
+    const int action = actions[tree];
+    if (action < 0 || p.trees[tree].status != ST_PLAYING) return;      // -1: this tree stays where it is
+    TreeWarp<G> t(p, tree, lane, scratch);
+    t.caller_move(action);
+    if (t.st.status != ST_PLAYING && lane == 0) atomicAdd(&p.counters[t.st.status == ST_DONE ? 0 : 1], 1ULL);
+    t.save();
 }
 
 // ---- sample writer: selfPlay's symmetrised samples (selfplay/SelfPlay.hpp:86-96,127-136,
@@ -1119,6 +1214,14 @@ template <class G> static void launch_emit(const EngineParams& p, const long lon
     k_emit<G><<<dim3((unsigned)p.num_games, (unsigned)p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
 }
 
+template <class G> static void launch_tree_stats(const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw,
+                                                 signed char* pl, signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s) {
+    k_tree_stats<G><<<n, 32, 0, s>>>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk);
+}
+template <class G> static void launch_tree_advance(const EngineParams& p, int n, const int* actions, cudaStream_t s) {
+    k_tree_advance<G><<<n, 32, 0, s>>>(p, n, actions);
+}
+
 template <class G> static void launch_match_begin(const EngineParams& p, const MatchParams& m, cudaStream_t s) {
     k_match_begin<G><<<m.n_pairs, 32, 0, s>>>(p, m);
 }
@@ -1142,6 +1245,11 @@ void search_launch_emit(int game, const EngineParams& p, const long long* row0, 
                         cudaStream_t s) { GAME_SWITCH(game, launch_emit<G>(p, row0, S, st, di, ou, s)); }
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_begin<G>(p, m, s)); }
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_round<G>(p, m, s)); }
+void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,
+                              signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s) {
+    GAME_SWITCH(game, launch_tree_stats<G>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk, s));
+}
+void search_launch_tree_advance(int game, const EngineParams& p, int n, const int* actions, cudaStream_t s) { GAME_SWITCH(game, launch_tree_advance<G>(p, n, actions, s)); }
 int search_header_units(int game) { return (game == SPRL_GAME_GO9) ? 5 : 3; }
 
 }  // namespace sprl

@@ -30,7 +30,7 @@
 
 namespace sprl {
 
-enum { ST_IDLE = 0, ST_PLAYING = 1, ST_DONE = 2, ST_ERR_CAPACITY = 3, ST_ERR_MOVES = 4 };
+enum { ST_IDLE = 0, ST_PLAYING = 1, ST_DONE = 2, ST_ERR_CAPACITY = 3, ST_ERR_MOVES = 4, ST_ERR_ACTION = 5 };
 
 // meta word of a node header
 #define META_NLEGAL(m) ((m) & 0xffu)
@@ -66,6 +66,27 @@ struct TreeState {
     unsigned long long leaves_terminal, leaves_gray, leaves_empty;
 };
 
+struct AgentCfg {
+    int evaluator, use_sym, init_q, pad;
+    unsigned long long hash_salt;
+};
+
+// Values that change from one iteration / match to the next.  They live in device memory and are written on the
+// engine's stream by sprl_begin_iteration / sprl_match_begin: kernel arguments are frozen into a captured CUDA graph,
+// these are not, so one captured round serves every later iteration of the engine.
+struct IterParams {
+    long long num_games;
+    unsigned long long first_game;
+    unsigned long long game_stride;  // stream id of game i = first_game + i * game_stride
+    u32 q_half;                      // first evaluator row of agent 1 (match play)
+    // step-wise trees (sprl_begin_trees / sprl_search / sprl_advance): moves are made by the caller, a launch searches
+    // a tree only while it has fewer than step_sims descents for the current move
+    int stepwise;
+    int step_sims;
+    int pad;
+    AgentCfg agent[2];               // match play: the two sides
+};
+
 struct EngineParams {
     // pools
     uint4* pool;                    // [n_slots][2][cap_units]
@@ -86,11 +107,12 @@ struct EngineParams {
     u32* q_count;                   // [2] rows handed out by the running launch
     u32* q_rows;                    // [2] rows of the previous launch: what the evaluator has to compute (set by k_flip)
     u32* q_base;                    // [n_slots] first row of a tree's queued leaves
-    u32 q_half;                     // first row of agent 1 (match play)
-    // per-game records, game-major: [num_games][max_moves]
-    long long num_games;
+    u32 q_half;                     // first row of agent 1 (match play)            } host copies of the IterParams
+    // per-game records, game-major: [num_games][max_moves]                            } fields: kernels read `iter`,
+    long long num_games;             //                                                } never these
     unsigned long long first_game;
-    unsigned long long game_stride;  // stream id of game i = first_game + i * game_stride
+    unsigned long long game_stride;
+    const IterParams* iter;          // device
     int max_moves;
     unsigned long long* rec_board;  // [..][2W]
     unsigned char* rec_player;      // [..]
@@ -111,7 +133,8 @@ struct EngineParams {
     int add_noise, use_sym, init_q;
     int fix_symmetry_mask;          // option (not the reference): mask the policy with the symmetrised legal mask
     int rounds_per_launch;
-    unsigned long long* counters;   // [0] slots that finished all their games, [1] slots in error
+    unsigned long long* counters;   // [0] slots that finished all their games, [1] slots in error, [2] step-wise trees the running launch
+                                    // still searched or that wait for evaluations, [3] the same of the previous launch (k_flip)
     // launch order of the trees (longest first): warp w of a launch serves tree order[parity][w].  Trees
     // that will finish a move in the next launch (sample + re-root = several times the work of a plain
     // search batch) are listed from the front, all others from the back, by the previous launch.
@@ -125,12 +148,8 @@ struct EngineParams {
 
 // Match play (Evaluate.cpp:93-157): a game is served by a PAIR of trees, one per side; tree
 // k * n_pairs + g belongs to agent k of pair g, so that the evaluator rows of one network are contiguous.
-struct AgentCfg {
-    int evaluator, use_sym, init_q, pad;
-    unsigned long long hash_salt;
-};
 struct MatchParams {
-    AgentCfg agent[2];
+    AgentCfg agent[2];               // host copy; kernels read IterParams::agent
     int n_pairs;
 };
 

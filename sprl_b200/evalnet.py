@@ -93,6 +93,15 @@ class EvalNet:
                          torch.cuda.current_stream(x.device).cuda_stream)
         return logits, value.reshape(-1, 1)
 
+    def set_path(self, path):
+        """capi.EVALNET_PATH_AUTO / _STREAMING / _RESIDENT: which conv-tower kernel runs (same arithmetic, same order)."""
+        capi.check(self.lib.sprl_evalnet_set_path(self.handle, path))
+
+    @property
+    def phases(self):
+        """Launches of the resident-weight kernel per forward; 0 when the streaming kernel is in use."""
+        return self.lib.sprl_evalnet_phases(self.handle)
+
     def info(self):
         up, st, sm = C.c_int64(), C.c_int32(), C.c_int32()
         capi.check(self.lib.sprl_evalnet_info(self.handle, C.byref(up), C.byref(st), C.byref(sm)))

@@ -16,7 +16,7 @@ REF_TRACE = os.path.join(ORACLE_DIR, "_ref", "ref_trace")
 OG_OTHELLO, OG_C4, OG_GO7, OG_GO9 = 0, 1, 2, 3
 OE_UNIFORM, OE_HASHNET, OE_CALLBACK, OE_HEURISTIC = 0, 1, 2, 3
 OQ_ZERO, OQ_PARENT, OQ_DROP_PARENT = 0, 1, 2
-GAME_NAMES = {OG_OTHELLO: "othello", OG_C4: "c4", OG_GO7: "go"}
+GAME_NAMES = {OG_OTHELLO: "othello", OG_C4: "c4", OG_GO7: "go", OG_GO9: "go9"}
 
 _DT = {"b": np.int8, "i": np.int32, "f": np.float32, "Q": np.uint64}
 
@@ -44,9 +44,10 @@ def have_ref():
     return os.path.exists(REF_TRACE)
 
 
-def run_ref(*args):
-    """Run the verbatim-reference trace tool (only where oracle/_ref was built)."""
-    return subprocess.run([REF_TRACE, *map(str, args)], check=True, capture_output=True, text=True).stdout
+def run_ref(*args, tool="ref_trace"):
+    """Run the verbatim-reference trace tool (only where oracle/_ref was built).  tool: ref_trace, ref_trace9 (the
+    two-constant Go 9x9 build, game name "go") or ref_trace_torch (with the reference's LibTorch GridNetwork)."""
+    return subprocess.run([os.path.join(ORACLE_DIR, "_ref", tool), *map(str, args)], check=True, capture_output=True, text=True).stdout
 
 
 class GameInfo(C.Structure):

@@ -210,32 +210,7 @@ def test_headline_configuration_at_scale():
 
 
 # ------------------------------------------------- external evaluator (the traced-network path)
-class IntegerNet:
-    """A network whose outputs are exact in fp32 on any device: integer weights on 0/1 planes,
-    so every partial sum is a small integer and the summation order cannot matter.  Run by torch
-    on the GPU for the engine (the path a traced module takes: planes written by the search
-    kernel, logits/value read back in place) and by numpy for the oracle's callback evaluator."""
-
-    def __init__(self, planes, cells, actions, seed=0):
-        rs = np.random.RandomState(seed)
-        self.wp = rs.randint(-3, 4, size=(planes * cells, actions)).astype(np.float32)
-        self.wv = rs.randint(-2, 3, size=(planes * cells,)).astype(np.float32)
-        self.calls = 0
-
-    def numpy(self, x):
-        flat = np.asarray(x, np.float32).reshape(x.shape[0], -1)
-        return (flat @ self.wp) * np.float32(0.125), np.clip((flat @ self.wv) * np.float32(1.0 / 64), -1, 1)
-
-    def torch_fn(self, dev):
-        import torch
-        torch.backends.cuda.matmul.allow_tf32 = False
-        wp, wv = torch.from_numpy(self.wp).to(dev), torch.from_numpy(self.wv).to(dev)
-
-        def fn(x):
-            self.calls += 1
-            flat = x.reshape(x.shape[0], -1)
-            return (flat @ wp) * 0.125, torch.clamp((flat @ wv) * (1.0 / 64), -1, 1)
-        return fn
+from integer_net import IntegerNet  # noqa: E402  (exact in fp32 on any device)
 
 
 @pytest.mark.parametrize("game,sims,b,q,alpha,ngames,graph", [
@@ -259,6 +234,25 @@ def test_external_evaluator_bit_exact(game, sims, b, q, alpha, ngames, graph):
     assert net.calls > 0
     compare_selfplay(ref, got)
     assert st["sims"] == ref["stats"]["total_traversals"] and st["evals"] == ref["stats"]["total_evals"]
+
+
+def test_reused_engine_and_captured_graph_follow_the_new_iteration():
+    """One Engine, one captured CUDA graph, two iterations with different first_game / num_games and fewer slots than
+    games: slots start later games on the device, so the stream ids and the game count must come from the iteration
+    that is running, not from the one the graph was captured in (per-iteration values live in device memory)."""
+    import torch
+    game, sims, b, q = capi.GAME_OTHELLO, 48, 8, 4
+    gi = capi.game_info(game)
+    net = IntegerNet(2 * gi.history + 1, gi.cells, gi.actions, seed=3)
+    with SP.Engine(game, capi.EVAL_EXTERNAL, seed=9, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.3,
+                   num_slots=3, max_games=16, record_stats=1) as eng:
+        eng.attach_network(net.torch_fn(torch.device("cuda", 0)), use_cuda_graph=True)
+        for first, ngames in ((0, 7), (1000, 10), (40, 4)):
+            ref = O.selfplay(game, O.OE_CALLBACK, 9, first, ngames, sims, b, q, 0.25, 0.3, eval_fn=net.numpy, max_moves_per_game=170)
+            states, dists, outcomes = eng.run_iteration(ngames, first_game=first)
+            got = eng.move_stats(ngames)
+            got.update(states=states, distributions=dists, outcomes=outcomes)
+            compare_selfplay(ref, got)
 
 
 def test_external_evaluator_needs_a_network():
@@ -417,6 +411,15 @@ def test_match_external_evaluators_bit_exact(game, sims, b, q, ngames, pairs, gr
                                     use_cuda_graph=graph)
         got = eng.run_match(g_agents, ngames)
         got.update(eng.move_stats(ngames))
+        if graph:
+            # a second match on the same engine and the same captured graph, other agent options and game ids
+            o2 = [dict(o_agents[0], use_sym=0, init_q=O.OQ_ZERO), dict(o_agents[1], init_q=O.OQ_PARENT)]
+            g2 = [dict(g_agents[0], use_sym=0, init_q=capi.INITQ_ZERO), dict(g_agents[1], init_q=capi.INITQ_PARENT)]
+            ref2 = O.match(game, o2, 3, 77, ngames - 1, sims, b, q, max_moves_per_game=170)
+            got2 = eng.run_match(g2, ngames - 1, first_game=77)
+            got2.update(eng.move_stats(ngames - 1))
+            ref2["game_winner"] = ref2["game_winner"].astype(np.int8)
+            G.assert_trace_equal(ref2, got2, MATCH_KEYS)
     ref["game_winner"] = ref["game_winner"].astype(np.int8)
     G.assert_trace_equal(ref, got, MATCH_KEYS)
     assert got["wins"] == ref["wins"] and got["draws"] == ref["draws"]
