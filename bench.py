@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--evaluator", default="evalnet", choices=["evalnet", "libtorch"],
                     help="network forward: the library's tcgen05 kernel (default) or the traced module through LibTorch/cuDNN")
-    ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU work per reference step (bounded sample)")
+    ap.add_argument("--ref-seconds", type=float, default=20.0, help="timed window of the cpu_baseline leg (one core), seconds")
+    ap.add_argument("--ref-window", type=float, default=60.0, help="timed window of --impl reference (every core), seconds")
+    ap.add_argument("--ref-test-sims", type=int, default=0, help="smoke tests only: sims/move of the reference worker")
     return ap.parse_args()
 
 
@@ -393,34 +395,35 @@ def traced_model_file():
     return path
 
 
-def cpu_baseline(args, threads, seconds):
-    """Times the reference's CPU worker path (oracle/_ref/ref_worker: unmodified reference
-    sources + LibTorch on the CPU), `threads` single-threaded processes, on a bounded sample:
-    each process plays the first moves of its own games until about `seconds` of work."""
+def cpu_baseline(args, threads, seconds, game="othello"):
+    """Times the reference's CPU worker path (oracle/_ref/ref_worker: unmodified reference sources + LibTorch on the
+    CPU), `threads` single-threaded processes (one per host core, the reference's deployment model).  Protocol of
+    BASELINE.md section 3: every process plays one discarded warm-up game, then full games through the reference's own
+    SPRL::runIteration until `seconds` of wall time have passed (the game in progress is finished and counted)."""
     if not os.path.exists(ref_worker_path()):
         return cpu_baseline_port(seconds)
     model = traced_model_file()
-    # ~3,000 sims/s/core with this network on the B200 boxes' hosts (measured): size the sample in moves
-    moves = max(2, int(seconds * 3000 / SIMS))
-    games = max(1, (moves + 29) // 30)
-    per_game = (moves + games - 1) // games
-    procs = []
+    sims = args.ref_test_sims or SIMS
     t0 = time.time()
-    for i in range(threads):
-        procs.append(subprocess.Popen([ref_worker_path(), "othello", model, "0", str(1000 * i), str(games), str(SIMS),
-                                       str(MAX_BATCH), str(MAX_QUEUE), str(EPS), str(ALPHA), str(per_game)],
-                                      stdout=subprocess.PIPE, text=True))
+    procs = [subprocess.Popen([ref_worker_path(), game, model, "0", str(100000 * (i + 1)), str(sims), str(MAX_BATCH), str(MAX_QUEUE),
+                               str(EPS), str(ALPHA), str(seconds)], stdout=subprocess.PIPE, text=True) for i in range(threads)]
     outs = [json.loads(p.communicate()[0].strip().split("\n")[-1]) for p in procs]
     wall = time.time() - t0
     os.unlink(model)
-    sims = sum(o["sims"] for o in outs)
-    moves_done = sum(o["moves"] for o in outs)
-    slowest = max(o["seconds"] for o in outs)
-    return {"value": round(sims / slowest, 1), "unit": "sims/s", "cores": threads, "kind": "reference",
-            "moves_per_sec": round(moves_done / slowest, 2), "per_core": round(sims / slowest / threads, 1),
-            "sample": f"{threads} process(es) x first {per_game} moves of {games} game(s), {SIMS} sims/move, "
-                      f"traced 2x64 net on CPU (LibTorch, 1 thread each); {wall:.1f}s wall",
-            "cpu": cpu_model(), "host_cores": os.cpu_count()}
+    # every process has its own window (it ends at a game boundary): the aggregate is the sum of the per-process rates
+    sims_s = sum(o["sims"] / o["seconds"] for o in outs)
+    moves_s = sum(o["moves"] / o["seconds"] for o in outs)
+    window = sum(o["seconds"] for o in outs) / len(outs)
+    r = {"value": round(sims_s, 1), "unit": "sims/s", "cores": threads, "kind": "reference",
+         "moves_per_sec": round(moves_s, 2), "per_core": round(sims_s / threads, 1), "window_seconds": round(window, 2),
+         "games": sum(o["games"] for o in outs), "sims_per_move": round(sum(o["sims_per_move"] for o in outs) / len(outs), 2),
+         "sample": f"{threads} process(es), each: one discarded warm-up game, then {min(o['games'] for o in outs)}-{max(o['games'] for o in outs)} full "
+                   f"game(s) through the reference's runIteration in a {window:.1f} s window, {sims} sims/move, traced 2x64 net on CPU "
+                   f"(LibTorch, 1 thread each); {wall:.1f} s wall in all",
+         "cpu": cpu_model(), "host_cores": os.cpu_count()}
+    if args.ref_test_sims:
+        r["test_override"] = f"{sims} sims/move instead of {SIMS} (smoke test of the arm, not a measurement)"
+    return r
 
 
 def cpu_baseline_port(seconds):
@@ -456,27 +459,22 @@ def cpu_model():
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation on all host cores of the box.  One measurement: every
+    core plays a discarded warm-up game (the W warm-up steps), then full games in one window of --ref-window seconds (at
+    least 60); a step is 1/K of that window."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    total = args.steps + args.warmup
-    per_step = max(3.0, min(args.ref_seconds, 150.0 / max(1, total)))
-    vals, last = [], None
-    for i in range(total):
-        last = cpu_baseline(args, threads, per_step)
-        if i >= args.warmup:
-            vals.append(last)
-    sims_s = sum(v["value"] for v in vals) / len(vals)
-    moves_s = sum(v["moves_per_sec"] for v in vals) / len(vals)
-    out = {"impl": "reference", "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(sims_s, 1), "unit": "sims/s",
+    m = cpu_baseline(args, threads, args.ref_window)
+    out = {"impl": "reference", "metric": "othello_selfplay_mcts_sims_per_sec", "value": m["value"], "unit": "sims/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "ms_per_step": round(per_step * 1e3, 1),
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "ms_per_step": round(m.get("window_seconds", 0.0) * 1e3 / max(1, args.steps), 1),
            "config": {"workload": WORKLOAD, "sims_per_move": SIMS, "max_batch": MAX_BATCH, "max_queue": MAX_QUEUE},
-           "moves_per_sec": round(moves_s, 2),
-           "cpu_baseline": {"value": round(sims_s, 1), "unit": "sims/s", "cores": threads, "kind": last["kind"], "sample": last["sample"],
-                            "cpu": last.get("cpu")},
-           "e2e": {"value": round(sims_s, 1), "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "moves_per_sec": m.get("moves_per_sec"),
+           "cpu_baseline": {k: m[k] for k in m if k not in ("moves_per_sec",)},
+           "e2e": {"value": m["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
 

@@ -237,10 +237,12 @@ int sprl_apply_evaluations(sprl_engine* e);
 /* getDecisionNode() (uct/UCTTree.hpp:62) of every tree: its EdgeStatistics (uct/UCTNode.hpp:45-60) as dense rows
  * N, W, P [num_trees, A] (P = the child priors in use: Dirichlet-mixed when add_noise; 0 before the node is expanded),
  * the node's own N / W (the tree-level edge, uct/UCTTree.hpp:301), player to move, terminal flag, winner (-1/0/1),
- * descents since the last advance, and the legal mask [num_trees, A] (GameNode::getActionMask).  Host arrays; any
- * may be NULL.  Synchronises the stream. */
+ * descents since the last advance, the legal mask [num_trees, A] (GameNode::getActionMask) and the number of leaves
+ * queued for the evaluator (what the last searchAndGetLeaves returned).  Host arrays; any may be NULL.  Synchronises
+ * the stream. */
 int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, float* h_P, float* h_root_N, float* h_root_W,
-                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask);
+                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask,
+                    int32_t* h_queued);
 /* advanceDecision(h_actions[i]) for tree i (uct/UCTTree.hpp:197-210: prune the siblings, clear the kept subtree's
  * statistics, keep its cached evaluations); -1 leaves a tree where it is.  An illegal action fails with
  * SPRL_E_INVALID.  A tree whose new decision node is terminal stops (sprl_poll counts it as finished). */

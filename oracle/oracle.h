@@ -74,6 +74,8 @@ typedef struct {
     uint64_t hash_salt; /* OE_HASHNET: 0 = the plain net, other values = independent nets (matches) */
     int fix_symmetry_mask; /* NOT the reference: symmetrise the legal mask together with the state before the
                             * evaluator masks its policy (repairs quirk Q3, uct/UCTTree.hpp:136-149).  Default 0. */
+    int caller_moves;      /* 1: the tree is driven through UCTTree's public API by a caller that plays the FIRST
+                            * most-visited action (ref_trace `treewalk`): no SampleCDF draw, advanceDecision(argmax). */
 } oracle_selfplay_cfg;
 
 typedef struct {

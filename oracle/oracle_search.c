@@ -448,7 +448,13 @@ static int self_play_game(const oracle_selfplay_cfg* cfg, uint64_t game_id, int 
             float* dst = out->distributions + (size_t)(out->n_samples + s) * A;
             if (cfg->use_sym) osym_dist(cfg->game, s, pdf, dst); else memcpy(dst, pdf, sizeof(float) * (size_t)A);
         }
-        int action = orng_sample_cdf(&rng, cdf, A);
+        int action;
+        if (cfg->caller_moves) {                    /* std::max_element: the first action with the most visits */
+            action = 0;
+            for (int a = 1; a < A; ++a) if (root->N[a] > root->N[action]) action = a;
+        } else {
+            action = orng_sample_cdf(&rng, cdf, A);
+        }
         PUT(out->move_action, m, action);
         players[moveCount] = root->player;
         tree_advance(&t, action);

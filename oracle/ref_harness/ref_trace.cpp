@@ -9,6 +9,11 @@
 //   match    <game> <evaluator0> <evaluator1> <seed> <first_game> <ngames> <sims> <batch> <queue>
 //            <sym0 0|1> <initq0> <sym1 0|1> <initq1> <out.trace>
 //
+//   treewalk <game> <evaluator> <seed> <first_game> <ngames> <sims> <batch> <queue> <eps> <alpha> <noise 0|1> <sym 0|1>
+//            <parent|zero|drop> <out.trace>    ONE tree per game driven through the public UCTTree API by a caller
+//                                              that plays the first most-visited action: searchAndGetLeaves /
+//                                              evaluateAndBackpropLeaves until <sims>, getDecisionNode()'s statistics,
+//                                              advanceDecision(action) -- the trace of the step-wise C ABI
 //   npy      x <out.npy> <d0> [<d1> ...]       the array value[i] = 0.25 * i - 3 of that shape through the reference's own
 //                                              npy::write_npy (utils/npy.hpp:616-639), as selfplay/GridWorker.hpp:173-196 calls it
 //
@@ -489,6 +494,70 @@ int cmdMatch(const std::string& evalKind0, const std::string& evalKind1, uint64_
     return 0;
 }
 
+// ---- treewalk: the public UCTTree API with the caller choosing the moves --------------------------
+template <class D>
+int cmdTreewalk(const std::string& evalKind, uint64_t seed, uint64_t firstGame, int nGames, int sims, int maxBatch, int maxQueue,
+                float eps, float alpha, bool addNoise, bool useSym, InitQ initQ, const std::string& outPath) {
+    constexpr int A = D::A;
+    using State = StateOf<D>;
+    auto net = makeEvaluator<D>(evalKind);
+    typename D::Sym symObj;
+    std::vector<int32_t> gameMoves, gameWinner, mvAction, mvTrav;
+    std::vector<uint64_t> gameCtr;
+    std::vector<float> mvN, mvW, mvP, mvRootN, mvRootW;
+    std::vector<int8_t> mvPlayer;
+    for (int g = 0; g < nGames; ++g) {
+        sprl_shim_set_stream(seed, firstGame + g);
+        UCTTree<typename D::Node, State, A> tree { std::make_unique<typename D::Node>(), eps, alpha, initQ, useSym ? &symObj : nullptr, addNoise };
+        int moves = 0;
+        typename D::Node gameRoot {};
+        GNode<D>* cur = &gameRoot;              // the same game on a plain game tree, for the winner
+        while (!tree.getDecisionNode()->isTerminal()) {
+            auto* root = const_cast<UCTNode<typename D::Node, State, A>*>(tree.getDecisionNode());
+            int trav = 0;
+            while (trav < sims) {
+                auto [leaves, n] = tree.searchAndGetLeaves(maxBatch, maxQueue, net.get(), U_WEIGHT);
+                if (!leaves.empty()) tree.evaluateAndBackpropLeaves(leaves, net.get());
+                trav += n;
+            }
+            const auto* es = root->getEdgeStatistics();
+            for (int a = 0; a < A; ++a) {
+                mvN.push_back(es->m_numVisits[a]);
+                mvW.push_back(es->m_totalValues[a]);
+                mvP.push_back(es->m_childPriors[a]);
+            }
+            mvRootN.push_back(root->N());
+            mvRootW.push_back(root->W());
+            mvTrav.push_back(trav);
+            mvPlayer.push_back((int8_t)root->getPlayer());
+            auto visits = es->m_numVisits;
+            int action = (int)std::distance(visits.begin(), std::max_element(visits.begin(), visits.end()));
+            mvAction.push_back(action);
+            tree.advanceDecision((ActionIdx)action);
+            cur = cur->getAddChild((ActionIdx)action);
+            ++moves;
+        }
+        gameMoves.push_back(moves);
+        gameWinner.push_back((int32_t)cur->getWinner());
+        gameCtr.push_back(sprl_shim_get_counter());
+    }
+    uint64_t M = mvAction.size();
+    TraceWriter w(outPath);
+    w.put("game_moves", 'i', gameMoves, { (uint64_t)nGames });
+    w.put("game_winner", 'i', gameWinner, { (uint64_t)nGames });
+    w.put("game_rng_draws", 'Q', gameCtr, { (uint64_t)nGames });
+    w.put("move_N", 'f', mvN, { M, (uint64_t)A });
+    w.put("move_W", 'f', mvW, { M, (uint64_t)A });
+    w.put("move_P", 'f', mvP, { M, (uint64_t)A });
+    w.put("move_root_N", 'f', mvRootN, { M });
+    w.put("move_root_W", 'f', mvRootW, { M });
+    w.put("move_action", 'i', mvAction, { M });
+    w.put("move_traversals", 'i', mvTrav, { M });
+    w.put("move_player", 'b', mvPlayer, { M });
+    std::cout << "{\"moves\": " << M << "}" << std::endl;
+    return 0;
+}
+
 template <class D>
 int dispatch(int argc, char** argv) {
     std::string cmd = argv[1];
@@ -498,6 +567,13 @@ int dispatch(int argc, char** argv) {
     if (cmd == "selfplay" && argc == 16) {
         InitQ q = parseInitQ(argv[14]);
         return cmdSelfplay<D>(argv[3], std::strtoull(argv[4], 0, 10), std::strtoull(argv[5], 0, 10),
+                              std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]), std::atoi(argv[9]),
+                              (float)std::atof(argv[10]), (float)std::atof(argv[11]),
+                              std::atoi(argv[12]) != 0, std::atoi(argv[13]) != 0, q, argv[15]);
+    }
+    if (cmd == "treewalk" && argc == 16) {
+        InitQ q = parseInitQ(argv[14]);
+        return cmdTreewalk<D>(argv[3], std::strtoull(argv[4], 0, 10), std::strtoull(argv[5], 0, 10),
                               std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]), std::atoi(argv[9]),
                               (float)std::atof(argv[10]), (float)std::atof(argv[11]),
                               std::atoi(argv[12]) != 0, std::atoi(argv[13]) != 0, q, argv[15]);

@@ -86,8 +86,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("SPRL_B200_REBUILD"):
+    path = os.environ.get("SPRL_B200_LIB") or _build.LIB_PATH      # SPRL_B200_LIB: a build variant (timing experiments)
+    if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("SPRL_B200_REBUILD")):
         _build.build_library()
     lib = C.CDLL(path)
     lib.sprl_last_error.restype = C.c_char_p
@@ -116,7 +116,7 @@ def load():
     lib.sprl_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.sprl_search_batch.argtypes = [C.c_void_p]
     lib.sprl_apply_evaluations.argtypes = [C.c_void_p]
-    lib.sprl_root_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10
+    lib.sprl_root_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11
     lib.sprl_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.sprl_move_stats.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.POINTER(C.c_int64)]
     lib.sprl_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]

@@ -17,7 +17,7 @@ void search_launch_emit(int game, const EngineParams& p, const long long* row0, 
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,
-                              signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s);
+                              signed char* te, signed char* wi, int* tr, signed char* mk, int* qu, cudaStream_t s);
 void search_launch_tree_advance(int game, const EngineParams& p, int n, const int* actions, cudaStream_t s);
 int search_header_units(int game);
 }  // namespace sprl
@@ -646,7 +646,7 @@ int sprl_apply_evaluations(sprl_engine* e) {
 }
 
 int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, float* h_P, float* h_root_N, float* h_root_W,
-                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask) {
+                    int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask, int32_t* h_queued) {
     ENGINE_CHECK(e);
     int rc = stepwise_check(e);
     if (rc) return rc;
@@ -654,7 +654,7 @@ int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, f
     if (cap_trees < n) return fail(SPRL_E_CAPACITY, "%lld trees do not fit the caller's capacity %lld", (long long)n, (long long)cap_trees);
     const size_t A = (size_t)e->gi.actions, S = (size_t)e->cfg.num_slots;
     // staging: N, W, P [S][A] floats | root_N, root_W [S] floats | traversals [S] ints | player, terminal, winner [S] | mask [S][A]
-    const size_t bytes = 3 * S * A * 4 + 3 * S * 4 + 3 * S + S * A;
+    const size_t bytes = 3 * S * A * 4 + 4 * S * 4 + 3 * S + S * A;
     if (!e->d_tree_io) {
         ENGINE_CUDA(e, cudaMalloc((void**)&e->d_tree_io, std::max(bytes, S * sizeof(int))));
         e->allocations.push_back(e->d_tree_io);
@@ -662,8 +662,9 @@ int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, f
     float* dN = (float*)e->d_tree_io; float* dW = dN + S * A; float* dP = dW + S * A;
     float* drn = dP + S * A; float* drw = drn + S;
     int* dtr = (int*)(drw + S);
-    signed char* dpl = (signed char*)(dtr + S); signed char* dte = dpl + S; signed char* dwi = dte + S; signed char* dmk = dwi + S;
-    search_launch_tree_stats(e->cfg.game, e->p, (int)n, dN, dW, dP, drn, drw, dpl, dte, dwi, dtr, dmk, e->stream);
+    int* dqu = dtr + S;
+    signed char* dpl = (signed char*)(dqu + S); signed char* dte = dpl + S; signed char* dwi = dte + S; signed char* dmk = dwi + S;
+    search_launch_tree_stats(e->cfg.game, e->p, (int)n, dN, dW, dP, drn, drw, dpl, dte, dwi, dtr, dmk, dqu, e->stream);
     e->launches += 1;
     ENGINE_CUDA(e, cudaGetLastError());
     if (h_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_N, dN, (size_t)n * A * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -672,6 +673,7 @@ int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, f
     if (h_root_N) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_N, drn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (h_root_W) ENGINE_CUDA(e, cudaMemcpyAsync(h_root_W, drw, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (h_traversals) ENGINE_CUDA(e, cudaMemcpyAsync(h_traversals, dtr, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_queued) ENGINE_CUDA(e, cudaMemcpyAsync(h_queued, dqu, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (h_player) ENGINE_CUDA(e, cudaMemcpyAsync(h_player, dpl, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     if (h_terminal) ENGINE_CUDA(e, cudaMemcpyAsync(h_terminal, dte, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     if (h_winner) ENGINE_CUDA(e, cudaMemcpyAsync(h_winner, dwi, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
@@ -687,7 +689,7 @@ int sprl_advance(sprl_engine* e, const int32_t* h_actions, int64_t n_actions) {
     if (!h_actions || n_actions != e->num_games) return fail(SPRL_E_INVALID, "sprl_advance takes one action per tree (%lld)", (long long)e->num_games);
     const size_t S = (size_t)e->cfg.num_slots, A = (size_t)e->gi.actions;
     if (!e->d_tree_io) {
-        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_tree_io, 3 * S * A * 4 + 3 * S * 4 + 3 * S + S * A));
+        ENGINE_CUDA(e, cudaMalloc((void**)&e->d_tree_io, 3 * S * A * 4 + 4 * S * 4 + 3 * S + S * A));
         e->allocations.push_back(e->d_tree_io);
     }
     ENGINE_CUDA(e, cudaMemcpyAsync(e->d_tree_io, h_actions, (size_t)n_actions * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));

@@ -1068,6 +1068,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
                     }
                     rbw.resize(start + (size_t)ph.w_bytes / 2, 0);
                 }
+                ph.index = (int)i;
                 phases.push_back(ph);
             }
             for (size_t i = 0; i < phases.size(); ++i) phases[i].w = reinterpret_cast<const unsigned char*>(w_at[i] * 2);   // offsets until the upload below
@@ -1293,11 +1294,13 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
     if (flag[0]) return fail(SPRL_E_CUDA, "evaluator kernel timed out on a pipeline barrier (code %llx)", flag[0]);
     if (flag[1]) return fail(SPRL_E_STATE, "an input or activation exceeded %.0f, the range of the fp16-split evaluator; its outputs were clamped", HALF_MAX / ACT_SCALE);
     if (e->dev.timing) {
-        std::vector<long long> t(12 * 4);
+        std::vector<long long> t(12 * 1024);
         cudaMemcpy(t.data(), e->dev.timing, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        for (int b = 0; b < 2; ++b)
-            fprintf(stderr, "[evalnet timing, CTA %d, last launch] mma: bar %lld full %lld issue %lld commit %lld total %lld | epi: bar %lld acc %lld heads %lld total %lld | producer: empty %lld total %lld\n",
-                    b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 3], t[b * 12 + 10], t[b * 12 + 2], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9]);
+        const bool res = !e->phases.empty() && e->path != SPRL_EVALNET_PATH_STREAMING;
+        for (int b = 0; b < (res ? 160 * (int)e->phases.size() : 2); b += (res ? 160 : 1))       // streaming kernel: mma {bar, full, total, issue} epi {bar, acc, heads, total} producer {empty, total} mma commit;
+                                          // resident kernel: mma {wait img, -, total} epi {wait acc X, Y, total X, Y}
+            fprintf(stderr, "[evalnet timing, CTA %d, last launch] %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld\n",
+                    b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 2], t[b * 12 + 3], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9], t[b * 12 + 10]);
     }
     if (launches) *launches = e->launches;
     return SPRL_OK;

@@ -56,6 +56,7 @@ struct RbPhase {
     const unsigned char* w;      // [2][w_bytes]: the resident weights of CTA rank 0 / rank 1 (each holds half of the rows)
     int w_bytes;                 // per CTA, a multiple of 128
     float* act;                  // [tiles][16 channel quads][128 cells][4]: activations between phases, image units, in place
+    int index;                   // position of the phase in the forward (timing slots)
 };
 __host__ __device__ inline int rb_smem_bytes(const RbPhase& ph) { return RB_OFF_W + ph.w_bytes + ph.n_stages * CH * 4 + 64 + 16; }
 __host__ __device__ inline int rb_stage_ndy(int kind) { return kind == RB_CONV ? 3 : 1; }
@@ -147,7 +148,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                     }
                 }
             }
-            if (lane == 0 && net.timing) { net.timing[blockIdx.x * 12 + 0] = t_wait; net.timing[blockIdx.x * 12 + 2] = NOW() - t0; }
+            if (lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[0] = t_wait; tm[2] = NOW() - t0; }
         }
     } else {
         // ===== epilogue group of stream s: cell m = TMEM lane m =====
@@ -303,7 +304,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             }
         }
         if (mx > HALF_MAX) atomicExch(net.error_flag + 1, 1ULL);
-        if (w8 == 0 && lane == 0 && net.timing) { net.timing[blockIdx.x * 12 + 4 + s] = t_acc; net.timing[blockIdx.x * 12 + 6 + s] = NOW() - t0; }
+        if (w8 == 0 && lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[4 + s] = t_acc; tm[6 + s] = NOW() - t0; }
     }
     tc_fence_before();
     __syncthreads();

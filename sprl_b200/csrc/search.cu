@@ -1102,7 +1102,7 @@ template <class G>
 __global__ void __launch_bounds__(32) k_tree_stats(EngineParams p, int n_trees, float* __restrict__ N, float* __restrict__ Wt, float* __restrict__ P,
                                                    float* __restrict__ root_N, float* __restrict__ root_W, signed char* __restrict__ player,
                                                    signed char* __restrict__ terminal, signed char* __restrict__ winner,
-                                                   int* __restrict__ traversals, signed char* __restrict__ mask) {
+                                                   int* __restrict__ traversals, signed char* __restrict__ mask, int* __restrict__ queued) {
     const int tree = blockIdx.x, lane = threadIdx.x;
     if (tree >= n_trees) return;
     const TreeState& g = p.trees[tree];
@@ -1136,6 +1136,7 @@ __global__ void __launch_bounds__(32) k_tree_stats(EngineParams p, int n_trees, 
         if (terminal) terminal[tree] = (signed char)META_TERMINAL(h.meta);
         if (winner) winner[tree] = (signed char)((int)META_WINNER(h.meta) - 1);      // device encoding: 0 none, 1 ZERO, 2 ONE
         if (traversals) traversals[tree] = g.traversals;
+        if (queued) queued[tree] = g.n_queued;
     }
 }
 
@@ -1215,8 +1216,8 @@ template <class G> static void launch_emit(const EngineParams& p, const long lon
 }
 
 template <class G> static void launch_tree_stats(const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw,
-                                                 signed char* pl, signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s) {
-    k_tree_stats<G><<<n, 32, 0, s>>>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk);
+                                                 signed char* pl, signed char* te, signed char* wi, int* tr, signed char* mk, int* qu, cudaStream_t s) {
+    k_tree_stats<G><<<n, 32, 0, s>>>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk, qu);
 }
 template <class G> static void launch_tree_advance(const EngineParams& p, int n, const int* actions, cudaStream_t s) {
     k_tree_advance<G><<<n, 32, 0, s>>>(p, n, actions);
@@ -1246,8 +1247,8 @@ void search_launch_emit(int game, const EngineParams& p, const long long* row0, 
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_begin<G>(p, m, s)); }
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_round<G>(p, m, s)); }
 void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,
-                              signed char* te, signed char* wi, int* tr, signed char* mk, cudaStream_t s) {
-    GAME_SWITCH(game, launch_tree_stats<G>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk, s));
+                              signed char* te, signed char* wi, int* tr, signed char* mk, int* qu, cudaStream_t s) {
+    GAME_SWITCH(game, launch_tree_stats<G>(p, n, N, W, P, rn, rw, pl, te, wi, tr, mk, qu, s));
 }
 void search_launch_tree_advance(int game, const EngineParams& p, int n, const int* actions, cudaStream_t s) { GAME_SWITCH(game, launch_tree_advance<G>(p, n, actions, s)); }
 int search_header_units(int game) { return (game == SPRL_GAME_GO9) ? 5 : 3; }

@@ -14,9 +14,13 @@
 //   SPRL::waitModelPath, SPRL::runWorker<NN,Impl,R,C,H,A>(...)   selfplay/GridWorker.hpp:35-55,84-91
 //   SPRL::playMatch<Impl,State,A>(...)                the game loop of Evaluate.cpp:93-157 (UCTNetworkAgent::act /
 //                                                     opponentAct inside playGame), all games concurrently
-//   SPRL::UCTTree, IAgent, UCTNetworkAgent, playGame  uct/UCTTree.hpp:38-60, agents/*.hpp, evaluate/play.hpp:24-69 as
-//                                                     handles: the reference's Evaluate.cpp compiles unchanged and plays
-//                                                     one game per playGame call on the GPU (playMatch is the batched form)
+//   SPRL::UCTTree                                     uct/UCTTree.hpp:38-210: getDecisionNode / searchAndGetLeaves /
+//                                                     evaluateAndBackpropLeaves / advanceDecision over a one-tree engine
+//                                                     (the step-wise C ABI: sprl_begin_trees, sprl_search_batch,
+//                                                     sprl_apply_evaluations, sprl_root_stats, sprl_advance)
+//   SPRL::IAgent, UCTNetworkAgent, playGame           agents/*.hpp, evaluate/play.hpp:24-69: act / opponentAct drive the
+//                                                     agent's own tree; the reference's Evaluate.cpp compiles unchanged and
+//                                                     plays one game per playGame call on the GPU (playMatch is the batched form)
 //
 // What changes underneath: runIteration plays all `numGames` games CONCURRENTLY on one GPU
 // (one warp per tree) instead of one after the other on a CPU core; the evaluator is a handle
@@ -28,12 +32,16 @@
 
 #include "../../../../include/sprl_b200.h"
 
+#include <algorithm>
 #include <array>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <filesystem>
 #include <iostream>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -50,7 +58,18 @@ using SymmetryIdx = int8_t;
 
 enum class InitQ { ZERO, PARENT, DROP_PARENT };
 
-template <int ACTION_SIZE> struct GameActionDist { static constexpr int SIZE = ACTION_SIZE; };
+// games/GameActionDist.hpp:18-293: a fixed-size float vector with the reference's arithmetic -- sum() adds in index
+// order, dividing by a scalar multiplies by its reciprocal (:283-293), pow / exp are libm's.
+template <int ACTION_SIZE> struct GameActionDist : std::array<float, ACTION_SIZE> {
+    static constexpr int SIZE = ACTION_SIZE;
+    GameActionDist() { this->fill(0.0f); }
+    float sum() const { float s = 0.0f; for (float v : *this) s += v; return s; }
+    GameActionDist pow(float e) const { GameActionDist r; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = std::pow((*this)[i], e); return r; }
+    GameActionDist exp() const { GameActionDist r; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = std::exp((*this)[i]); return r; }
+    GameActionDist cumsum() const { GameActionDist r; float run = 0.0f; for (int i = 0; i < ACTION_SIZE; ++i) { run += (*this)[i]; r[i] = run; } return r; }
+    GameActionDist operator/(float rhs) const { GameActionDist r; const float inv = 1.0f / rhs; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = (*this)[i] * inv; return r; }
+    GameActionDist operator*(float rhs) const { GameActionDist r; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = (*this)[i] * rhs; return r; }
+};
 template <int BOARD_SIZE, int HISTORY_SIZE> struct GridState {
     static constexpr int BOARD = BOARD_SIZE, HISTORY = HISTORY_SIZE;
 };
@@ -167,8 +186,24 @@ struct DeviceOptions {
     uint64_t firstGame = 0;    // stream id of the first game of the next runIteration
     uint64_t gameStride = 1;
     bool fixSymmetryMask = false;   // not the reference: symmetrise the legal mask with the state (repairs quirk Q3)
+    int64_t treeUnits = 1 << 20;    // slab size (16-byte units) of a UCTTree object's device tree; 0 = sized for 2^30 descents
 };
-inline DeviceOptions& deviceOptions() { static DeviceOptions o; return o; }
+// The reference seeds its generator from std::random_device (constants.hpp:4 SEED = 0, utils/random.cpp:38-47), so two
+// runs never replay the same games; same here unless SPRL_SEED pins the run seed (tests, reproducible deployments).
+inline DeviceOptions& deviceOptions() {
+    static DeviceOptions o = [] {
+        DeviceOptions d;
+        const char* env = std::getenv("SPRL_SEED");
+        if (env) d.seed = std::strtoull(env, nullptr, 10);
+        else {
+            std::random_device rd;
+            d.seed = ((uint64_t)rd() << 32) | (uint64_t)rd();
+            std::cout << "Run seed " << d.seed << " (std::random_device; set SPRL_SEED to pin it)" << std::endl;
+        }
+        return d;
+    }();
+    return o;
+}
 
 inline int initQCode(InitQ q) {
     return q == InitQ::PARENT ? SPRL_INITQ_PARENT : (q == InitQ::DROP_PARENT ? SPRL_INITQ_DROP_PARENT : SPRL_INITQ_ZERO);
@@ -324,17 +359,168 @@ MatchResult playMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, AC
 }
 
 // ---- UCTTree / IAgent / UCTNetworkAgent / playGame as the reference spells them ------------------------
-// uct/UCTTree.hpp:38-60: a tree is described by its construction arguments; the nodes live in device slabs.
+// uct/UCTTree.hpp:38-210 over ONE device tree (a one-slot engine created at the first search, when the batch / queue
+// sizes and the evaluator are known).  The nodes live in device slabs; getDecisionNode() returns a host snapshot of the
+// decision node: its EdgeStatistics (uct/UCTNode.hpp:45-60), N() / W(), player, terminal flag, winner and legal mask.
+// Random draws come from the tree's own stream (deviceOptions().seed, deviceOptions().firstGame + trees made so far).
 template <typename ImplNode, typename State, int ACTION_SIZE>
 class UCTTree {
 public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
+    struct EdgeStatistics { ActionDist m_childPriors, m_totalValues, m_numVisits; };
+    struct DecisionNode {
+        EdgeStatistics stats;
+        ActionDist mask;
+        float n = 0.0f, w = 0.0f;
+        Player player = Player::ZERO, winner = Player::NONE;
+        bool terminal = false;
+        const EdgeStatistics* getEdgeStatistics() const { return &stats; }
+        const ActionDist& getActionMask() const { return mask; }
+        float N() const { return n; }
+        float W() const { return w; }
+        Player getPlayer() const { return player; }
+        Player getWinner() const { return winner; }
+        bool isTerminal() const { return terminal; }
+        std::array<Value, 2> getRewards() const {                         // games/GameNode.hpp:170-186 through the winner
+            if (winner == Player::ZERO) return { 1.0f, -1.0f };
+            if (winner == Player::ONE) return { -1.0f, 1.0f };
+            return { 0.0f, 0.0f };
+        }
+    };
+    struct Leaf { int index; };       // a queued leaf of the last searchAndGetLeaves; it lives on the device
+
     UCTTree(std::unique_ptr<ImplNode> gameRoot, float dirEps, float dirAlpha, InitQ initQMethod,
             ISymmetrizer<State, ACTION_SIZE>* symmetrizer, bool addNoise = true)
-        : dirEps(dirEps), dirAlpha(dirAlpha), initQMethod(initQMethod), symmetrizer(symmetrizer), addNoise(addNoise) { (void)gameRoot; }
+        : dirEps(dirEps), dirAlpha(dirAlpha), initQMethod(initQMethod), symmetrizer(symmetrizer), addNoise(addNoise) {
+        (void)gameRoot;
+        static uint64_t treesMade = 0;
+        streamId = deviceOptions().firstGame + deviceOptions().gameStride * treesMade++;
+    }
+    UCTTree(const UCTTree&) = delete;
+    UCTTree& operator=(const UCTTree&) = delete;
+    ~UCTTree() { if (engine) sprl_destroy(engine); }
+
+    // uct/UCTTree.hpp:62
+    const DecisionNode* getDecisionNode() {
+        ensureAny();
+        if (!snapshotValid) refresh();
+        return &snapshot;
+    }
+
+    // uct/UCTTree.hpp:76-114: one batch of up to maxBatchSize descents that stops early at maxQueueSize queued leaves;
+    // terminal and cached leaves are backed up at once.  Returns the queued leaves and the number of descents.
+    std::pair<std::vector<Leaf>, int> searchAndGetLeaves(int maxBatchSize, int maxQueueSize, INetwork<State, ACTION_SIZE>* network,
+                                                         float uWeight = 1.0f) {
+        ensureEngine(maxBatchSize, maxQueueSize, network, uWeight);
+        int32_t before = 0, after = 0, queued = 0;
+        check(sprl_root_stats(engine, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &before, nullptr, &queued));
+        if (queued != 0) throw EngineError(SPRL_E_STATE, "searchAndGetLeaves: the previous batch's leaves were not passed to evaluateAndBackpropLeaves");
+        check(sprl_search_batch(engine));
+        check(sprl_root_stats(engine, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &after, nullptr, &queued));
+        snapshotValid = false;
+        std::vector<Leaf> leaves;
+        for (int i = 0; i < queued; ++i) leaves.push_back(Leaf { i });
+        return { leaves, (int)(after - before) };
+    }
+
+    // uct/UCTTree.hpp:124-184: evaluate the queued leaves (one random symmetry each), expand and back up
+    void evaluateAndBackpropLeaves(const std::vector<Leaf>& leaves, INetwork<State, ACTION_SIZE>* network) {
+        if (!engine) throw EngineError(SPRL_E_STATE, "evaluateAndBackpropLeaves before searchAndGetLeaves");
+        if (network != net) throw EngineError(SPRL_E_INVALID, "a tree keeps the evaluator of its first search");
+        if (leaves.empty()) return;
+        if (net->evaluatorKind() == SPRL_EVAL_EXTERNAL) {
+            if (net->forward(dIn, sprl_eval_batch(engine), dLogits, dValue, nullptr) != 0)
+                throw EngineError(SPRL_E_STATE, "the network's forward failed");
+        }
+        check(sprl_apply_evaluations(engine));
+        net->addEvals((uint64_t)leaves.size());
+        snapshotValid = false;
+    }
+
+    // uct/UCTTree.hpp:197-210
+    void advanceDecision(ActionIdx action) {
+        ensureAny();
+        const int32_t a = (int32_t)action;
+        check(sprl_advance(engine, &a, 1));
+        history.push_back(a);
+        snapshotValid = false;
+    }
+
     float dirEps, dirAlpha;
     InitQ initQMethod;
     ISymmetrizer<State, ACTION_SIZE>* symmetrizer;
     bool addNoise;
+    uint64_t streamId;
+
+private:
+    // The device tree needs the batch / queue sizes and the evaluator, which the reference only passes to the first
+    // searchAndGetLeaves.  A tree that is inspected or advanced before its first search (the `while (!isTerminal())` of
+    // every move loop; opponentAct when the other side moves first) lives in a provisional engine; the first search
+    // replaces it and replays the advances -- an unsearched tree has drawn nothing from its stream, so nothing is lost.
+    void ensureAny() { if (!engine) createEngine(1, 1, nullptr, 1.0f); }
+    void ensureEngine(int maxBatchSize, int maxQueueSize, INetwork<State, ACTION_SIZE>* network, float uWeight) {
+        if (engine && !provisional) {
+            if (network != net || maxBatchSize != batch || maxQueueSize != queue || uWeight != uw)
+                throw EngineError(SPRL_E_INVALID, "a tree keeps the batch size, queue size, evaluator and uWeight of its first search");
+            return;
+        }
+        if (engine) { sprl_destroy(engine); engine = nullptr; }
+        createEngine(maxBatchSize, maxQueueSize, network, uWeight);
+    }
+    void createEngine(int maxBatchSize, int maxQueueSize, INetwork<State, ACTION_SIZE>* network, float uWeight) {
+        const DeviceOptions& opt = deviceOptions();
+        sprl_config cfg;
+        check(sprl_default_config(ImplNode::GAME, &cfg));
+        cfg.device = opt.device; cfg.seed = opt.seed;
+        cfg.evaluator = network ? network->evaluatorKind() : SPRL_EVAL_UNIFORM;
+        cfg.num_slots = 1; cfg.max_games = 1;
+        cfg.sims = 1 << 30;                              // budgets are the caller's: sprl_search_batch runs one batch per call
+        cfg.max_batch = maxBatchSize; cfg.max_queue = maxQueueSize;
+        cfg.dir_eps = dirEps; cfg.dir_alpha = dirAlpha; cfg.u_weight = uWeight;
+        cfg.init_q = initQCode(initQMethod);
+        cfg.add_noise = addNoise ? 1 : 0;
+        cfg.use_sym = symmetrizer != nullptr ? 1 : 0;
+        cfg.fix_symmetry_mask = opt.fixSymmetryMask ? 1 : 0;
+        cfg.units_per_tree = opt.treeUnits;
+        check(sprl_create(&cfg, &engine));
+        sprl_game_info gi;
+        check(sprl_game_info_get(ImplNode::GAME, &gi));
+        if (cfg.evaluator == SPRL_EVAL_EXTERNAL) {
+            if (network->prepare(cfg.device, sprl_eval_batch(engine), 2 * gi.history + 1, gi.rows, gi.cols, gi.actions, &dIn, &dLogits, &dValue) != 0)
+                throw EngineError(SPRL_E_STATE, "network could not allocate its device buffers");
+            check(sprl_bind_eval_buffers(engine, dIn, dLogits, dValue));
+            const uint32_t* d_rows = nullptr;
+            check(sprl_eval_rows(engine, &d_rows));
+            network->setRowCount(d_rows);
+        }
+        check(sprl_begin_trees(engine, streamId, 1));
+        for (int32_t a : history) check(sprl_advance(engine, &a, 1));
+        net = network; batch = maxBatchSize; queue = maxQueueSize; uw = uWeight;
+        provisional = network == nullptr;
+        snapshotValid = false;
+    }
+    void refresh() {
+        std::array<float, ACTION_SIZE> n {}, w {}, p {};
+        std::array<int8_t, ACTION_SIZE> m {};
+        int8_t player = 0, terminal = 0, winner = -1;
+        check(sprl_root_stats(engine, 1, n.data(), w.data(), p.data(), &snapshot.n, &snapshot.w, &player, &terminal, &winner, nullptr, m.data(), nullptr));
+        for (int i = 0; i < ACTION_SIZE; ++i) {
+            snapshot.stats.m_numVisits[i] = n[i]; snapshot.stats.m_totalValues[i] = w[i]; snapshot.stats.m_childPriors[i] = p[i];
+            snapshot.mask[i] = m[i] ? 1.0f : 0.0f;
+        }
+        snapshot.player = static_cast<Player>(player);
+        snapshot.winner = static_cast<Player>(winner);
+        snapshot.terminal = terminal != 0;
+        snapshotValid = true;
+    }
+    sprl_engine* engine = nullptr;
+    INetwork<State, ACTION_SIZE>* net = nullptr;
+    int batch = 0, queue = 0;
+    float uw = 1.0f;
+    bool provisional = false, snapshotValid = false;
+    std::vector<int32_t> history;       // actions advanced so far
+    float *dIn = nullptr, *dLogits = nullptr, *dValue = nullptr;
+    DecisionNode snapshot;
 };
 
 template <typename ImplNode, typename State, int ACTION_SIZE>
@@ -342,14 +528,31 @@ class IAgent {                                                       // agents/I
 public:
     using ActionDist = GameActionDist<ACTION_SIZE>;
     virtual ~IAgent() = default;
+    virtual ActionIdx act(const GameNode<ImplNode, State, ACTION_SIZE>* gameNode, bool verbose = false) const = 0;
+    virtual void opponentAct(const ActionIdx action) const = 0;
 };
 
 template <typename ImplNode, typename State, int ACTION_SIZE>
-class UCTNetworkAgent : public IAgent<ImplNode, State, ACTION_SIZE> { // agents/UCTNetworkAgent.hpp:21-40
+class UCTNetworkAgent : public IAgent<ImplNode, State, ACTION_SIZE> { // agents/UCTNetworkAgent.hpp:21-108
 public:
     UCTNetworkAgent(INetwork<State, ACTION_SIZE>* network, UCTTree<ImplNode, State, ACTION_SIZE>* tree,
                     int numTraversals, int maxBatchSize, int maxQueueSize)
         : network(network), tree(tree), numTraversals(numTraversals), maxBatchSize(maxBatchSize), maxQueueSize(maxQueueSize) {}
+    // :42-105: search numTraversals descents in the agent's own tree, play the FIRST most-visited action, advance
+    ActionIdx act(const GameNode<ImplNode, State, ACTION_SIZE>* /*gameNode*/, bool /*verbose*/ = false) const override {
+        int traversals = 0;
+        while (traversals < numTraversals) {
+            auto [leaves, n] = tree->searchAndGetLeaves(maxBatchSize, maxQueueSize, network);
+            if (!leaves.empty()) tree->evaluateAndBackpropLeaves(leaves, network);
+            traversals += n;
+        }
+        const auto& visits = tree->getDecisionNode()->getEdgeStatistics()->m_numVisits;
+        const ActionIdx action = (ActionIdx)std::distance(visits.begin(), std::max_element(visits.begin(), visits.end()));
+        tree->advanceDecision(action);
+        return action;
+    }
+    // :106-108
+    void opponentAct(const ActionIdx action) const override { tree->advanceDecision(action); }
     INetwork<State, ACTION_SIZE>* network;
     UCTTree<ImplNode, State, ACTION_SIZE>* tree;
     int numTraversals, maxBatchSize, maxQueueSize;

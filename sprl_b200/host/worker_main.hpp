@@ -56,7 +56,7 @@ int workerMain(int argc, char* argv[], const WorkerDefaults& d, const char* exeN
 
     DeviceOptions& opt = deviceOptions();
     opt.device = envInt("SPRL_DEVICE", 0);
-    opt.seed = (uint64_t)envInt("SPRL_SEED", 0);
+    // opt.seed: SPRL_SEED, else drawn from std::random_device and logged (deviceOptions())
     opt.numSlots = envInt("SPRL_NUM_SLOTS", 0);
     opt.fixSymmetryMask = envInt("SPRL_FIX_SYMMETRY_MASK", 0) != 0;      // default: the reference's behaviour (quirk Q3)
     // task t plays stream ids t, t + numTasks, ...: the tasks of a run never share a game stream

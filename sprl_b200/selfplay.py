@@ -256,6 +256,54 @@ class Engine:
         self._check_evaluators()
         return self.collect_samples() if collect else None
 
+    # -- step-wise trees: UCTTree's own surface (uct/UCTTree.hpp:62-210) ------------------------------
+    def begin_trees(self, num_trees, first_game=0):
+        """UCTTree(start position, ...) for trees 0..num_trees-1; tree i draws from stream first_game + i * stride."""
+        if self._nn is not None:
+            torch = self._nn["torch"]
+            self.set_stream(torch.cuda.current_stream(self._nn["dev"]).cuda_stream)
+        capi.check(self.lib.sprl_begin_trees(self.handle, first_game, num_trees))
+        self._num_trees = num_trees
+
+    def search(self, sims):
+        """while (traversals < sims) { searchAndGetLeaves; evaluateAndBackpropLeaves } for every live tree."""
+        if self.cfg.evaluator == capi.EVAL_EXTERNAL:
+            if self._nn is None:
+                raise capi.SprlError(capi.SPRL_E_STATE, "attach_network() first")
+            torch = self._nn["torch"]
+
+            def forward(user, d_in, batch, d_logits, d_value, stream):
+                try:
+                    self._forward()
+                    return 0
+                except Exception:           # must not propagate through the C frame
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = capi.FORWARD_FN(forward)
+            with torch.cuda.device(self._nn["dev"]):
+                capi.check(self.lib.sprl_search(self.handle, sims, cb, None))
+        else:
+            capi.check(self.lib.sprl_search(self.handle, sims, None, None))
+
+    def root_stats(self):
+        """getDecisionNode()->getEdgeStatistics() of every tree: dict of N, W, P [trees, A], root_N, root_W, player,
+        terminal, winner, traversals, queued [trees], mask [trees, A]."""
+        n, A = self._num_trees, self.gi.actions
+        r = dict(N=np.zeros((n, A), np.float32), W=np.zeros((n, A), np.float32), P=np.zeros((n, A), np.float32),
+                 root_N=np.zeros(n, np.float32), root_W=np.zeros(n, np.float32), player=np.zeros(n, np.int8),
+                 terminal=np.zeros(n, np.int8), winner=np.zeros(n, np.int8), traversals=np.zeros(n, np.int32),
+                 mask=np.zeros((n, A), np.int8), queued=np.zeros(n, np.int32))
+        capi.check(self.lib.sprl_root_stats(self.handle, n, _ptr(r["N"]), _ptr(r["W"]), _ptr(r["P"]), _ptr(r["root_N"]),
+                                            _ptr(r["root_W"]), _ptr(r["player"]), _ptr(r["terminal"]), _ptr(r["winner"]),
+                                            _ptr(r["traversals"]), _ptr(r["mask"]), _ptr(r["queued"])))
+        return r
+
+    def advance(self, actions):
+        """advanceDecision(actions[i]) for tree i; -1 leaves a tree where it is."""
+        a = np.ascontiguousarray(actions, np.int32)
+        capi.check(self.lib.sprl_advance(self.handle, _ptr(a), a.shape[0]))
+
     # -- match play (Evaluate.cpp) ----------------------------------------------------------
     def run_match(self, agents, num_games, first_game=0, poll_every=None):
         """Plays a match of `num_games` games between two agents on num_slots // 2 concurrent pairs of trees.

@@ -1,7 +1,7 @@
 """Regenerate tests/golden/*.npz from the UNMODIFIED reference sources.
 
 Run in the build container (where /root/reference exists):
-    make -C oracle ref ref9 ref_torch && python tests/golden/make_golden.py
+    make -C oracle ref ref9 ref_gridnet && python tests/golden/make_golden.py
 Each fixture is the output of oracle/_ref/ref_trace (reference sources compiled
 verbatim + the contract RNG shim) for the command recorded in its `cmd` field.
 Game "go9" = oracle/_ref/ref_trace9, the same tool over the build-dir copy of
@@ -44,6 +44,14 @@ SELFPLAY = [
 # The reference's LibTorch GridNetwork (its own glibc exp / mask / sequential sum / divide, networks/GridNetwork.hpp:107-142)
 # over an integer-exact TorchScript module (tests/integer_net.py): name, game, net seed, seed, first, ngames, sims, b, q, eps, alpha
 GRIDNET = [("othello_intnet_64_8_4", "othello", 3, 6, 0, 6, 64, 8, 4, 0.25, 0.3)]
+# The step-wise surface: one tree per game through the public UCTTree API, the caller plays the first most-visited action
+# name, game, evaluator, seed, first_game, ngames, sims, batch, queue, eps, alpha, noise, sym, initq
+TREEWALK = [
+    ("othello_hash_120_8_4", "othello", "hash", 3, 10, 3, 120, 8, 4, 0.25, 0.3, 1, 1, "parent"),
+    ("c4_hash_200_8_4", "c4", "hash", 1, 0, 4, 200, 8, 4, 0.25, 0.5, 1, 1, "zero"),
+    ("go_hash_60_16_8", "go", "hash", 2, 0, 1, 60, 16, 8, 0.25, 0.2, 1, 1, "parent"),
+    ("go9_hash_40_16_8", "go9", "hash", 2, 0, 1, 40, 16, 8, 0.25, 0.2, 1, 1, "parent"),
+]
 NPY_SHAPES = [(5,), (3, 65), (2, 3, 8, 8), (16,), (1, 17, 7, 7)]
 # match play (Evaluate.cpp).  name, game, evaluator0, evaluator1, seed, first_game, ngames, sims, batch,
 # queue, sym0, initq0, sym1, initq1
@@ -109,6 +117,13 @@ def main():
             np.savez_compressed(os.path.join(HERE, f"match_{name}.npz"),
                                 cmd=json.dumps(dict(game=game, evaluators=[ev0, ev1], seed=seed, first_game=first, ngames=n,
                                                     sims=sims, max_batch=b, max_queue=q, sym=[sym0, sym1], initq=[q0, q1])), **t)
+        for name, game, ev, seed, first, n, sims, b, q, eps, alpha, noise, sym, initq in TREEWALK:
+            tool, gname = tool_of(game)
+            O.run_ref("treewalk", gname, ev, seed, first, n, sims, b, q, eps, alpha, noise, sym, initq, path, tool=tool)
+            t = O.read_trace(path)
+            np.savez_compressed(os.path.join(HERE, f"treewalk_{name}.npz"),
+                                cmd=json.dumps(dict(game=game, evaluator=ev, seed=seed, first_game=first, ngames=n, sims=sims,
+                                                    max_batch=b, max_queue=q, eps=eps, alpha=alpha, noise=noise, sym=sym, initq=initq)), **t)
         # the 2^16-game rollout sweep of config 2, as digests
         game, seed, first, n, chunk = ROLLOUT_DIGEST
         O.run_ref("rollout", game, seed, first, n, path)

@@ -61,7 +61,8 @@ class SelfplayCfg(C.Structure):
     _fields_ = [("game", C.c_int), ("evaluator", C.c_int), ("seed", C.c_uint64), ("sims", C.c_int),
                 ("max_batch", C.c_int), ("max_queue", C.c_int), ("dir_eps", C.c_float), ("dir_alpha", C.c_float),
                 ("add_noise", C.c_int), ("use_sym", C.c_int), ("init_q", C.c_int), ("u_weight", C.c_float),
-                ("eval_cb", EVAL_CB), ("eval_user", C.c_void_p), ("hash_salt", C.c_uint64), ("fix_symmetry_mask", C.c_int)]
+                ("eval_cb", EVAL_CB), ("eval_user", C.c_void_p), ("hash_salt", C.c_uint64), ("fix_symmetry_mask", C.c_int),
+                ("caller_moves", C.c_int)]
 
 
 class MatchOut(C.Structure):
@@ -151,7 +152,7 @@ def replay(game, actions):
 
 def selfplay(game, evaluator, seed, first_game, ngames, sims, max_batch, max_queue, eps=0.25, alpha=0.3,
              add_noise=True, use_sym=True, init_q=OQ_PARENT, u_weight=1.1, eval_fn=None, max_moves_per_game=200,
-             fix_symmetry_mask=False):
+             fix_symmetry_mask=False, caller_moves=False):
     """Run the oracle's selfPlay for `ngames` games; returns a dict shaped like a ref_trace selfplay trace."""
     gi = game_info(game)
     S = gi.nsym if use_sym else 1
@@ -169,7 +170,7 @@ def selfplay(game, evaluator, seed, first_game, ngames, sims, max_batch, max_que
                distributions=np.zeros((cap_s, A), np.float32), outcomes=np.zeros(cap_s, np.float32))
     cfg = SelfplayCfg(game=game, evaluator=evaluator, seed=seed, sims=sims, max_batch=max_batch, max_queue=max_queue,
                       dir_eps=eps, dir_alpha=alpha, add_noise=int(add_noise), use_sym=int(use_sym), init_q=init_q,
-                      u_weight=u_weight, fix_symmetry_mask=int(fix_symmetry_mask))
+                      u_weight=u_weight, fix_symmetry_mask=int(fix_symmetry_mask), caller_moves=int(caller_moves))
     keep = None
     if evaluator == OE_CALLBACK:
         planes_per = (2 * gi.history + 1) * B

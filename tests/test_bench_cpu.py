@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--ref-seconds", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--ref-window", "2", "--ref-test-sims", "24"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -20,4 +20,5 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("othello8x8_selfplay_400sims")
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["games"] >= cb["cores"] and 24 <= cb["sims_per_move"] < 32 and d["ms_per_step"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

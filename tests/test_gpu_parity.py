@@ -15,7 +15,7 @@ from sprl_b200 import selfplay as SP
 
 pytestmark = pytest.mark.gpu
 
-GAMES = {"othello": capi.GAME_OTHELLO, "c4": capi.GAME_C4, "go": capi.GAME_GO7}
+GAMES = {"othello": capi.GAME_OTHELLO, "c4": capi.GAME_C4, "go": capi.GAME_GO7, "go9": capi.GAME_GO9}
 EVALS = {"hash": capi.EVAL_HASHNET, "hash1": capi.EVAL_HASHNET, "uniform": capi.EVAL_UNIFORM,
          "heuristic": capi.EVAL_OTHELLO_HEURISTIC}
 INITQ = {"parent": capi.INITQ_PARENT, "zero": capi.INITQ_ZERO, "drop": capi.INITQ_DROP_PARENT}
@@ -42,9 +42,8 @@ def test_perft_bit_exact():
     assert SP.env_perft(capi.GAME_OTHELLO, 10)[0] == 24571284
     # Othello perft(11): published value
     assert SP.env_perft(capi.GAME_OTHELLO, 11)[0] == 212258800
-    # Go 9x9: against the oracle's two-constant variant
-    for d in (1, 2, 3):
-        assert SP.env_perft(capi.GAME_GO9, d)[0] == O.perft(O.OG_GO9, d)
+    # (Go 9x9 = the reference with the two constants of games/GoNode.hpp:16,20 edited, oracle/Makefile: ref9; Go 7x7
+    # depth 4 = 5,536,331 from the verbatim reference)
     assert SP.env_perft(capi.GAME_OTHELLO, 0)[0] == 1
 
 
@@ -61,6 +60,21 @@ def test_rollout_vs_oracle_state_by_state(game, n):
     ref = O.rollout(game, 77, 1000, n)
     G.assert_trace_equal(ref, got)
     assert got["total_positions"] == len(ref["player"])
+
+
+def test_rollout_sweep_65536_games_state_by_state():
+    """BASELINE.json config 2: 2^16 Othello rollouts compared state by state -- with the verbatim reference through the
+    committed SHA-256 digests of its arrays (16 chunks of 4,096 games), and with the oracle on the first chunk."""
+    fx = G.load_json("rollout_othello_65536.json")
+    c = fx["cmd"]
+    positions = 0
+    for i, want in enumerate(fx["chunks"]):
+        got = SP.env_rollout(GAMES[c["game"]], c["seed"], c["first_game"] + i * c["chunk"], c["chunk"], record=True)
+        assert G.rollout_digests(got, c["chunk"])[0] == want, f"chunk {i}"
+        positions += got["total_positions"]
+        if i == 0:
+            G.assert_trace_equal(O.rollout(G.GAME_ID[c["game"]], c["seed"], c["first_game"], c["chunk"]), got)
+    assert positions == fx["positions"]
 
 
 def test_rollout_large_sweep_properties():
@@ -253,6 +267,74 @@ def test_reused_engine_and_captured_graph_follow_the_new_iteration():
             got = eng.move_stats(ngames)
             got.update(states=states, distributions=dists, outcomes=outcomes)
             compare_selfplay(ref, got)
+
+
+# ------------------------------------------------- step-wise trees: UCTTree's own surface through the C ABI
+def walk_trees(eng, ngames, sims, first_game):
+    """A caller of the step-wise ABI that does what ref_trace `treewalk` does with the reference's UCTTree: search,
+    read the decision node, play the FIRST most-visited action, advance -- all trees in lock step."""
+    A = eng.gi.actions
+    rows = [[] for _ in range(ngames)]
+    eng.begin_trees(ngames, first_game=first_game)
+    live = np.ones(ngames, bool)
+    while live.any():
+        eng.search(sims)
+        st = eng.root_stats()
+        assert (st["terminal"][live] == 0).all()
+        assert ((st["N"] > 0) <= (st["mask"] > 0)).all()            # visits only on legal actions
+        actions = np.where(live, st["N"].argmax(1), -1).astype(np.int32)
+        for g in np.nonzero(live)[0]:
+            rows[g].append({k: st[k][g].copy() for k in ("N", "W", "P", "root_N", "root_W", "traversals", "player")} | {"action": actions[g]})
+        eng.advance(actions)
+        live &= eng.root_stats()["terminal"] == 0
+    flat = [r for g in range(ngames) for r in rows[g]]
+    got = dict(game_moves=np.array([len(r) for r in rows], np.int32),
+               move_N=np.stack([r["N"] for r in flat]), move_W=np.stack([r["W"] for r in flat]), move_P=np.stack([r["P"] for r in flat]),
+               move_root_N=np.array([r["root_N"] for r in flat], np.float32), move_root_W=np.array([r["root_W"] for r in flat], np.float32),
+               move_action=np.array([r["action"] for r in flat], np.int32), move_traversals=np.array([r["traversals"] for r in flat], np.int32),
+               move_player=np.array([r["player"] for r in flat], np.int8), game_winner=eng.root_stats()["winner"].astype(np.int32))
+    assert got["move_N"].shape[1] == A
+    return got
+
+
+STEP_KEYS = ["game_moves", "game_winner", "move_N", "move_W", "move_P", "move_root_N", "move_root_W", "move_action", "move_traversals", "move_player"]
+
+
+@pytest.mark.parametrize("name", G.TREEWALK_FIXTURES)
+def test_stepwise_trees_golden(name):
+    """sprl_begin_trees / sprl_search / sprl_root_stats / sprl_advance against the verbatim reference driven through
+    its public UCTTree API (uct/UCTTree.hpp:62-210) by a caller that plays the first most-visited action: every
+    decision node of every game, N / W / P bit for bit (Dirichlet noise and symmetries on)."""
+    cmd, ref = G.load("treewalk_" + name)
+    with SP.Engine(GAMES[cmd["game"]], EVALS[cmd["evaluator"]], seed=cmd["seed"], sims=cmd["sims"], max_batch=cmd["max_batch"],
+                   max_queue=cmd["max_queue"], dir_eps=cmd["eps"], dir_alpha=cmd["alpha"], add_noise=cmd["noise"], use_sym=cmd["sym"],
+                   init_q=INITQ[cmd["initq"]], num_slots=cmd["ngames"], max_games=cmd["ngames"]) as eng:
+        got = walk_trees(eng, cmd["ngames"], cmd["sims"], cmd["first_game"])
+        playing, failed = eng.poll()
+    assert playing == 0 and failed == 0
+    G.assert_trace_equal(ref, got, STEP_KEYS)
+
+
+def test_stepwise_trees_vs_oracle_with_a_network_and_fewer_trees_than_slots():
+    """The same walk with the external evaluator (planes -> network -> logits between the two halves of every loop
+    trip) against the oracle; then illegal actions are refused."""
+    import torch
+    game, sims, b, q, ngames = capi.GAME_OTHELLO, 40, 8, 4, 5
+    gi = capi.game_info(game)
+    net = IntegerNet(2 * gi.history + 1, gi.cells, gi.actions, seed=8)
+    ref = O.selfplay(game, O.OE_CALLBACK, 13, 200, ngames, sims, b, q, 0.25, 0.3, eval_fn=net.numpy, caller_moves=True, max_moves_per_game=170)
+    with SP.Engine(game, capi.EVAL_EXTERNAL, seed=13, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.3,
+                   num_slots=8, max_games=8) as eng:
+        eng.attach_network(net.torch_fn(torch.device("cuda", 0)), use_cuda_graph=False)
+        got = walk_trees(eng, ngames, sims, 200)
+        G.assert_trace_equal(ref, got, [k for k in STEP_KEYS if k != "game_winner"])
+        eng.begin_trees(2)
+        with pytest.raises(capi.SprlError) as err:
+            eng.advance(np.array([0, 19], np.int32))          # a1 is not a legal first move (d3 is)
+        assert "not legal" in str(err.value)
+    with SP.Engine(game, capi.EVAL_UNIFORM, num_slots=2, max_games=2, sims=16) as eng:
+        with pytest.raises(capi.SprlError):
+            eng.search(8)                                     # no trees begun
 
 
 def test_external_evaluator_needs_a_network():

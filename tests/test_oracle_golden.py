@@ -12,7 +12,7 @@ import oracle_py as O
 
 def test_perft_matches_reference():
     table = G.perft_table()
-    limits = {"othello": 8, "c4": 7, "go": 3}      # keep the CPU suite short
+    limits = {"othello": 8, "c4": 7, "go": 4, "go9": 3}      # keep the CPU suite short
     for game, counts in table.items():
         for d, want in enumerate(counts[:limits[game]], start=1):
             assert O.perft(G.GAME_ID[game], d) == want, (game, d)
@@ -65,6 +65,67 @@ def test_match_play_matches_reference(name):
     first = ref["game_first"]
     wins = [int(((ref["game_winner"] >= 0) & ((ref["game_winner"] ^ first) == k)).sum()) for k in (0, 1)]
     assert got["wins"] == tuple(wins) and got["draws"] == int((ref["game_winner"] < 0).sum())
+
+
+@pytest.mark.parametrize("name", G.TREEWALK_FIXTURES)
+def test_treewalk_matches_reference(name):
+    """One tree per game through the reference's public UCTTree API, the caller playing the first most-visited action
+    (ref_trace `treewalk`): what the step-wise C ABI (sprl_search / sprl_root_stats / sprl_advance) is checked against."""
+    cmd, ref = G.load("treewalk_" + name)
+    got = O.selfplay(G.GAME_ID[cmd["game"]], G.EVAL_ID[cmd["evaluator"]], cmd["seed"], cmd["first_game"], cmd["ngames"],
+                     cmd["sims"], cmd["max_batch"], cmd["max_queue"], cmd["eps"], cmd["alpha"], bool(cmd["noise"]),
+                     bool(cmd["sym"]), G.INITQ_ID[cmd["initq"]], caller_moves=True)
+    G.assert_trace_equal(ref, got, G.TREEWALK_KEYS)
+
+
+@pytest.mark.parametrize("name", G.GRIDNET_FIXTURES)
+def test_gridnetwork_postprocess_matches_reference(name):
+    """The fixture went through the verbatim reference's LibTorch GridNetwork (networks/GridNetwork.hpp:62-145: embed,
+    forward, glibc exp, mask, sequential sum, multiply by the reciprocal) over an integer-exact TorchScript module; the
+    oracle evaluates the same function through its callback and the contract's deterministic exp.  Root priors within
+    1e-6 (the two exps may differ in the last bit), and with these inputs the whole search agrees bit for bit."""
+    from integer_net import IntegerNet
+    cmd, ref = G.load("gridnet_" + name)
+    gi = O.game_info(G.GAME_ID[cmd["game"]])
+    net = IntegerNet(2 * gi.history + 1, gi.cells, gi.actions, seed=cmd["net_seed"])
+    got = O.selfplay(G.GAME_ID[cmd["game"]], O.OE_CALLBACK, cmd["seed"], cmd["first_game"], cmd["ngames"], cmd["sims"],
+                     cmd["max_batch"], cmd["max_queue"], cmd["eps"], cmd["alpha"], eval_fn=net.numpy)
+    first = np.concatenate([[0], np.cumsum(ref["game_moves"])[:-1]])
+    np.testing.assert_allclose(got["move_P"][first], ref["move_P"][first], rtol=0, atol=1e-6)
+    G.assert_trace_equal(ref, got, ["game_moves", "game_rng_draws", "move_N", "move_action", "move_traversals", "move_player", "states", "outcomes"])
+    np.testing.assert_allclose(got["move_P"], ref["move_P"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(got["move_W"], ref["move_W"], rtol=0, atol=1e-5)
+
+
+def test_rollout_sweep_digests_match_reference():
+    """BASELINE.json config 2: the first 4,096 of the 2^16 Othello rollouts, state by state, as SHA-256 digests of the
+    verbatim reference's arrays (the GPU suite checks all 16 chunks)."""
+    fx = G.load_json("rollout_othello_65536.json")
+    c = fx["cmd"]
+    got = O.rollout(G.GAME_ID[c["game"]], c["seed"], c["first_game"], c["chunk"])
+    assert G.rollout_digests(got, c["chunk"])[0] == fx["chunks"][0]
+
+
+def test_npy_writer_bytes_match_reference():
+    """sprl_write_npy_f32 (the C ABI's writer; host code, no GPU needed) and the oracle's writer against the bytes the
+    reference's own npy::write_npy (utils/npy.hpp:616-639) produced for the same arrays."""
+    import ctypes as C
+    import tempfile
+    from sprl_b200 import capi
+    fx = G.load_json("npy_reference_bytes.json")
+    assert len(fx) >= 5
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "a.npy")
+        for key, hexbytes in fx.items():
+            shape = tuple(int(x) for x in key.split("x"))
+            a = (np.arange(int(np.prod(shape)), dtype=np.float32) * np.float32(0.25) - np.float32(3.0)).reshape(shape)
+            want = bytes.fromhex(hexbytes)
+            dims = (C.c_uint64 * len(shape))(*shape)
+            capi.check(capi.load().sprl_write_npy_f32(path.encode(), a.ctypes.data_as(C.c_void_p), dims, len(shape)))
+            assert open(path, "rb").read() == want, key
+            O.write_npy(path, a)
+            assert open(path, "rb").read() == want, key
+            assert np.array_equal(np.load(path), a)
 
 
 def test_othello_quirks():

@@ -1,5 +1,9 @@
 #!/bin/bash
-# builds libsprl_b200.so with extra -D flags for evalnet.cu (timing experiments): tools/build_variant.sh -DSPRL_EVALNET_CLUSTER=2 ...
+# tools/build_variant.sh <name> [-D...]: builds sprl_b200/lib/variants/<name>.so = the library with extra flags for evalnet.cu
+# (timing experiments; select it with SPRL_B200_LIB=<path>).  The other objects come from the regular build.
 cd "$(dirname "$0")/.."
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" -c sprl_b200/csrc/evalnet.cu -o sprl_b200/lib/evalnet.o &&
-nvcc -shared -o sprl_b200/lib/libsprl_b200.so sprl_b200/lib/env.o sprl_b200/lib/search.o sprl_b200/lib/engine.o sprl_b200/lib/evalnet.o -gencode arch=compute_100a,code=sm_100a
+name=$1; shift
+mkdir -p sprl_b200/lib/variants
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" -c sprl_b200/csrc/evalnet.cu -o sprl_b200/lib/variants/$name.o &&
+nvcc -shared -o sprl_b200/lib/variants/$name.so sprl_b200/lib/env.o sprl_b200/lib/search.o sprl_b200/lib/engine.o sprl_b200/lib/variants/$name.o -gencode arch=compute_100a,code=sm_100a &&
+rm sprl_b200/lib/variants/$name.o && echo built sprl_b200/lib/variants/$name.so
