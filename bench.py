@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=16384, help="concurrent games per GPU")
     ap.add_argument("--rounds", type=int, default=256, help="search rounds per step")
-    ap.add_argument("--e2e-games", type=int, default=8192, help="games per e2e step per GPU (one slot per game)")
+    ap.add_argument("--e2e-games", type=int, default=16384, help="games per e2e step per GPU")
+    ap.add_argument("--e2e-slots", type=int, default=8192, help="concurrent games of the e2e engine (fewer than games: slots refill, finished games stream out)")
+    ap.add_argument("--e2e-no-stream", action="store_true", help="collect the samples at the end into pageable memory (round-1 behaviour)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,12 +241,12 @@ def run_ours(args):
     eng.close()
 
     # totals over ranks
-    tot = torch.tensor([st["sims"], st["moves"], st["evals"], st["games"]], dtype=torch.float64, device=dev)
+    tot = torch.tensor([st["sims"], st["moves"], st["evals"], st["games"], st["leaves_duplicate"]], dtype=torch.float64, device=dev)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    sims, moves, evals, games = [float(x) for x in tot.tolist()]
+    sims, moves, evals, games, dups = [float(x) for x in tot.tolist()]
     ms = float(tmax.item())
     value = sims / (ms / 1e3)
 
@@ -282,9 +284,9 @@ def run_ours(args):
     if evalnet is not None:
         # dominant kernel of the step: the evaluator's forward over the rows in use (the leaves the launch queued)
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        batch_rows = pst["evals"] / n_probe
+        batch_rows = (pst["evals"] - pst["leaves_duplicate"]) / n_probe     # a leaf queued twice in a batch (quirk Q4) takes one row
         tf = batch_rows * NET_FLOP_PER_LEAF / (nn_ms / 1e3) / 1e12
-        roofline = {"kernel": "k_evalnet", "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
+        roofline = {"kernel": "k_evalnet_resident" if evalnet.phases else "k_evalnet", "launches_per_forward": max(1, evalnet.phases), "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
                     "frac": round(tf / tpeak, 5), "traffic": traffic_of("k_evalnet"), "peak_source": peak_src + " bf16 sustained",
                     "launch_ms": round(nn_ms, 4), "leaves_per_launch": round(batch_rows, 1), "leaf_batch_capacity": args.slots * MAX_QUEUE, "flop_per_leaf": NET_FLOP_PER_LEAF,
                     "note": "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
@@ -308,7 +310,10 @@ def run_ours(args):
                    "evaluator_max_abs_logit_err_vs_fp64": eval_err},
         "moves_per_sec": round(moves / (ms / 1e3), 1), "evals_per_sec": round(evals / (ms / 1e3), 1),
         "samples_per_sec": round(8 * moves / (ms / 1e3), 1), "games_finished": int(games),
-        "gpu_launches": int(args.steps * args.rounds * world * (4 if evalnet is not None else 2)),
+        "evals_per_sim": round(evals / max(1.0, sims), 4), "eval_rows_per_sim": round((evals - dups) / max(1.0, sims), 4),
+        "duplicate_leaf_fraction": round(dups / max(1.0, evals), 4),
+        # per round: k_round, k_flip, the conv tower (one k_evalnet_resident launch per residual block, or one k_evalnet), k_heads
+        "gpu_launches": int(args.steps * args.rounds * world * ((2 + max(1, evalnet.phases) + 1) if evalnet is not None else 2)),
         "roofline": roofline, "roofline_search": roofline_search, "clocks": clocks,
     }
 
@@ -343,7 +348,11 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
     host_weights = [t.detach().cpu().pin_memory() for t in flat_params]
     G = args.e2e_games
     with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=1, sims=SIMS, max_batch=MAX_BATCH,
-                   max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=G, max_games=G) as eng:
+                   max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=min(G, args.e2e_slots), max_games=G) as eng:
+        if not args.e2e_no_stream:
+            # page-locked sample arrays, registered once (as a worker would keep them across iterations): finished games
+            # are embedded and copied while the others play; an Othello game has at most 60 placements + passes
+            eng.stream_samples(G * 8 * 66)
         if evalnet is not None:
             eng.attach_evalnet(evalnet, use_cuda_graph=not args.no_graph)
             host_state = {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
@@ -374,11 +383,14 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
         barrier()
         ms = e0.elapsed_time(e1)
         st = eng.stats()
+        eng_info = eng.stream_info()
     return {"value": None, "unit": "sims/s", "h2d_bytes_per_step": int(weight_bytes),
             "d2h_bytes_per_step": int(d2h / args.e2e_steps), "moves_per_sec": None,
-            "games_per_step_per_gpu": G, "steps": args.e2e_steps, "ms_per_step": None,
-            "note": "public API with host buffers: weights H2D from pinned memory, full games start to finish "
-                    "(incl. the tail where few games are left), samples D2H",
+            "games_per_step_per_gpu": G, "slots_per_gpu": min(G, args.e2e_slots), "steps": args.e2e_steps, "ms_per_step": None,
+            "streamed_chunks_while_playing": None if args.e2e_no_stream else eng_info["chunks_while_playing"],
+            "note": "public API (Engine.run_iteration) with host buffers: weights from host memory (fold + pack + H2D), full games "
+                    "start to finish incl. the tail where few games are left, every sample row D2H into page-locked host arrays "
+                    "(finished games stream out while the others play)",
             "_sims": float(st["sims"]), "_moves": float(st["moves"]), "_ms": float(ms)}
 
 

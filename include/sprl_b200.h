@@ -173,6 +173,16 @@ int sprl_iteration_counts(sprl_engine* e, int64_t* n_moves, int64_t* n_samples);
  * to HOST arrays: states [n, 2H+1, R, C], distributions [n, A], outcomes [n]. */
 int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions,
                          float* h_outcomes, int64_t* n_samples);
+/* Streamed output: registers the HOST arrays the next iterations' samples go to (same layout and order as
+ * sprl_collect_samples; capacity cap_samples rows).  From then on every sprl_poll embeds the games that have finished
+ * -- in game order, a game's rows follow those of all earlier games -- and copies them on a side stream while the other
+ * games keep playing, and sprl_collect_samples called with the SAME three pointers only waits for the rest.  pin != 0
+ * page-locks the arrays (cudaHostRegister) for the lifetime of the registration: asynchronous, full-speed copies.
+ * Three NULL pointers turn streaming off.  The arrays must stay valid until then or until sprl_destroy. */
+int sprl_stream_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions, float* h_outcomes, int pin);
+/* Progress of the streamed output: games and sample rows copied so far in the open iteration, and (since the
+ * registration) how many chunks left while games were still being played. */
+int sprl_stream_info(sprl_engine* e, int64_t* games_done, int64_t* samples_done, uint64_t* chunks_while_playing);
 /* Same, left on the device (engine-owned, valid until the next begin/collect). */
 int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_distributions, float** d_outcomes,
                                 int64_t* n_samples);
@@ -256,6 +266,9 @@ typedef struct {
     uint64_t units_per_tree;
     uint64_t launches;              /* kernels this engine launched since creation */
     uint64_t device_bytes;          /* HBM held by the engine */
+    uint64_t leaves_duplicate;      /* queued leaves that were already queued in the same batch (uct/UCTTree.hpp:166-182:
+                                     * evaluated again by the reference, result dropped): counted in `evals` like the
+                                     * reference's getNumEvals, but they take no evaluator row -- rows = evals - this */
 } sprl_stats;
 
 /* Counters accumulated since sprl_create (or the last sprl_reset_stats). */

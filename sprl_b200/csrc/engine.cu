@@ -12,8 +12,8 @@
 namespace sprl {
 void search_launch_begin(int game, const EngineParams& p, cudaStream_t s);
 void search_launch_round(int game, const EngineParams& p, cudaStream_t s);
-void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
-                        cudaStream_t s);
+void search_launch_emit(int game, const EngineParams& p, long long g0, long long n_games, const long long* row0, int S, float* st, float* di,
+                        float* ou, cudaStream_t s);
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s);
 void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,
@@ -38,7 +38,23 @@ struct sprl_engine {
     IterParams* d_iter = nullptr;   // device copy of the per-iteration values (search.cuh)
     bool stepwise = false;          // the open iteration is a set of step-wise trees (sprl_begin_trees)
     int step_sims = 0;
+    bool step_single = false;
     unsigned char* d_tree_io = nullptr;     // staging of sprl_root_stats / sprl_advance, sized for num_slots trees
+    // Streamed sample output (sprl_stream_samples): finished games are embedded and copied to the caller's (pinned) host
+    // arrays while the others still play.  Two copy streams, each with its own staging buffers of `rows` sample rows.
+    struct StreamOut {
+        bool active = false, registered = false;
+        float *h_states = nullptr, *h_dists = nullptr, *h_outcomes = nullptr;
+        int64_t cap = 0;                    // sample rows the host arrays hold
+        int64_t games_done = 0, rows_done = 0;
+        int64_t rows = 0;                   // staging capacity
+        cudaStream_t stream[2] = { nullptr, nullptr };
+        float* d_states[2] = { nullptr, nullptr }; float* d_dists[2] = { nullptr, nullptr }; float* d_outcomes[2] = { nullptr, nullptr };
+        long long* d_row0 = nullptr;        // [max_games]
+        int which = 0;
+        bool overflow = false;
+        uint64_t chunks = 0;                // chunks copied while games were still playing (reported by sprl_stream_info)
+    } so;
     bool failed = false;            // sticky CUDA error
     uint64_t launches = 0;
     uint64_t device_bytes = 0;
@@ -73,6 +89,22 @@ struct sprl_engine {
         if (d_outcomes) cudaFree(d_outcomes);
         if (d_row0) cudaFree(d_row0);
         d_states = d_dists = d_outcomes = nullptr; d_row0 = nullptr;
+        stream_out_release();
+    }
+    void stream_out_unregister() {
+        if (so.registered) { cudaHostUnregister(so.h_states); cudaHostUnregister(so.h_dists); cudaHostUnregister(so.h_outcomes); }
+        so.registered = false;
+    }
+    void stream_out_release() {
+        stream_out_unregister();
+        for (int k = 0; k < 2; ++k) {
+            if (so.stream[k]) cudaStreamDestroy(so.stream[k]);
+            if (so.d_states[k]) cudaFree(so.d_states[k]);
+            if (so.d_dists[k]) cudaFree(so.d_dists[k]);
+            if (so.d_outcomes[k]) cudaFree(so.d_outcomes[k]);
+        }
+        if (so.d_row0) cudaFree(so.d_row0);
+        so = StreamOut();
     }
 };
 
@@ -102,6 +134,7 @@ static int sum_tree_stats(sprl_engine* e, sprl_stats* out) {
         out->sims += t.sims; out->evals += t.evals; out->moves += t.moves; out->games += t.games;
         out->depth_sum += t.depth_sum; out->legal_sum += t.legal_sum; out->nodes_visited += t.nodes_visited;
         out->leaves_terminal += t.leaves_terminal; out->leaves_gray += t.leaves_gray; out->leaves_empty += t.leaves_empty;
+        out->leaves_duplicate += t.leaves_duplicate;
         out->units_high_water = std::max<uint64_t>(out->units_high_water, t.high_water);
     }
     out->units_per_tree = e->p.cap_units;
@@ -115,7 +148,7 @@ static int push_iter_params(sprl_engine* e) {
     IterParams it;
     memset(&it, 0, sizeof(it));
     it.num_games = e->p.num_games; it.first_game = e->p.first_game; it.game_stride = e->p.game_stride; it.q_half = e->p.q_half;
-    it.stepwise = e->stepwise ? 1 : 0; it.step_sims = e->step_sims;
+    it.stepwise = e->stepwise ? 1 : 0; it.step_sims = e->step_sims; it.step_single = e->step_single ? 1 : 0;
     it.agent[0] = e->match.agent[0]; it.agent[1] = e->match.agent[1];
     cudaError_t err = cudaMemcpyAsync(e->d_iter, &it, sizeof(it), cudaMemcpyHostToDevice, e->stream);   // pageable source: staged before the call returns
     if (err != cudaSuccess) { e->failed = true; return fail(SPRL_E_CUDA, "cudaMemcpyAsync of the iteration parameters failed: %s", cudaGetErrorString(err)); }
@@ -159,6 +192,7 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (rc) return rc;
     if (cfg->num_slots <= 0 || cfg->sims <= 0 || cfg->max_batch <= 0 || cfg->max_queue <= 0)
         return fail(SPRL_E_INVALID, "num_slots, sims, max_batch and max_queue must be positive");
+    if (cfg->max_queue > 255) return fail(SPRL_E_INVALID, "max_queue is limited to 255 leaves per tree and batch");
     rc = check_tree_options(cfg->game, cfg->evaluator, cfg->init_q);
     if (rc) return rc;
     if (!(cfg->dir_alpha > 0.0f) && cfg->add_noise) return fail(SPRL_E_INVALID, "dir_alpha must be positive");
@@ -209,6 +243,7 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
     if (!rc) rc = e->alloc(&p.q_count, 2, true);
     if (!rc) rc = e->alloc(&p.q_rows, 2, true);
     if (!rc) rc = e->alloc(&p.q_base, S, true);
+    if (!rc) rc = e->alloc(&p.q_rowoff, S * cfg->max_queue, true);
     if (!rc) rc = e->alloc(&p.root_p, S * A, true);
     if (!rc) rc = e->alloc(&p.rec_board, MG * MM * 2 * e->words, true);
     if (!rc) rc = e->alloc(&p.rec_player, MG * MM, true);
@@ -287,6 +322,7 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
     e->active_slots = std::min<int64_t>(num_games, e->cfg.num_slots);
     e->p.q_half = 0;
     e->stepwise = false;
+    e->so.games_done = e->so.rows_done = 0; e->so.overflow = false; e->so.which = 0;
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_count, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.q_rows, 0, 2 * sizeof(u32), e->stream));
     ENGINE_CUDA(e, cudaMemsetAsync(e->p.counters, 0, 4 * sizeof(unsigned long long), e->stream));
@@ -383,6 +419,96 @@ int sprl_match_results(sprl_engine* e, int64_t cap_games, int8_t* h_winner, int3
     return SPRL_OK;
 }
 
+// Streamed output: embeds the samples of the games that have finished since the last call -- the contiguous prefix of the
+// iteration's games, because a game's rows follow those of all earlier games -- and copies them to the host arrays, on the
+// copy streams.  The caller has synchronised the engine's stream (the records of finished games are final).
+static int stream_out_advance(sprl_engine* e) {
+    sprl_engine::StreamOut& so = e->so;
+    if (so.overflow) return SPRL_OK;
+    int64_t total = 0;
+    int rc = load_game_moves(e, &total);                // rec_moves[g] > 0 <=> game g is over
+    if (rc) return rc;
+    const int S = e->cfg.use_sym ? e->gi.nsym : 1;
+    const size_t row = (size_t)(2 * e->gi.history + 1) * e->gi.cells, A = (size_t)e->gi.actions;
+    int64_t g = so.games_done;
+    while (g < e->num_games) {
+        // the next chunk: finished games from g on, as many as the staging buffers hold
+        int64_t g1 = g, rows = 0;
+        std::vector<long long> row0;
+        while (g1 < e->num_games && e->h_moves[g1] > 0 && rows + (int64_t)e->h_moves[g1] * S <= so.rows) {
+            row0.push_back(rows);
+            rows += (int64_t)e->h_moves[g1] * S;
+            ++g1;
+        }
+        if (g1 == g) {
+            if (g < e->num_games && e->h_moves[g] > 0) return fail(SPRL_E_CAPACITY, "a single game's samples exceed the staging buffer");
+            break;                                      // game g is still being played
+        }
+        if (so.rows_done + rows > so.cap) { so.overflow = true; break; }     // reported by sprl_collect_samples
+        const int w = so.which;
+        so.which ^= 1;
+        cudaStream_t cs = so.stream[w];
+        ENGINE_CUDA(e, cudaMemcpyAsync(so.d_row0 + g, row0.data(), row0.size() * sizeof(long long), cudaMemcpyHostToDevice, cs));   // pageable: staged at once
+        search_launch_emit(e->cfg.game, e->p, g, g1 - g, so.d_row0, S, so.d_states[w], so.d_dists[w], so.d_outcomes[w], cs);
+        e->launches += 1;
+        ENGINE_CUDA(e, cudaGetLastError());
+        ENGINE_CUDA(e, cudaMemcpyAsync(so.h_states + (size_t)so.rows_done * row, so.d_states[w], (size_t)rows * row * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        ENGINE_CUDA(e, cudaMemcpyAsync(so.h_dists + (size_t)so.rows_done * A, so.d_dists[w], (size_t)rows * A * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        ENGINE_CUDA(e, cudaMemcpyAsync(so.h_outcomes + (size_t)so.rows_done, so.d_outcomes[w], (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        so.rows_done += rows;
+        g = g1;
+    }
+    so.games_done = g;
+    return SPRL_OK;
+}
+
+int sprl_stream_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions, float* h_outcomes, int pin) {
+    ENGINE_CHECK(e);
+    sprl_engine::StreamOut& so = e->so;
+    if (e->iteration_open && so.active && so.games_done > 0) ENGINE_CUDA(e, cudaDeviceSynchronize());
+    e->stream_out_unregister();
+    so.active = false;
+    if (!h_states && !h_distributions && !h_outcomes) return SPRL_OK;          // streaming off
+    if (!h_states || !h_distributions || !h_outcomes || cap_samples <= 0) return fail(SPRL_E_INVALID, "sprl_stream_samples needs the three host arrays and their capacity");
+    const int S = e->cfg.use_sym ? e->gi.nsym : 1;
+    const size_t row = (size_t)(2 * e->gi.history + 1) * e->gi.cells, A = (size_t)e->gi.actions;
+    if (!so.stream[0]) {
+        so.rows = std::max<int64_t>(1 << 16, (int64_t)e->p.max_moves * S);      // >= one game of maximal length
+        for (int k = 0; k < 2; ++k) {
+            ENGINE_CUDA(e, cudaStreamCreateWithFlags(&so.stream[k], cudaStreamNonBlocking));
+            ENGINE_CUDA(e, cudaMalloc((void**)&so.d_states[k], (size_t)so.rows * row * sizeof(float)));
+            ENGINE_CUDA(e, cudaMalloc((void**)&so.d_dists[k], (size_t)so.rows * A * sizeof(float)));
+            ENGINE_CUDA(e, cudaMalloc((void**)&so.d_outcomes[k], (size_t)so.rows * sizeof(float)));
+        }
+        ENGINE_CUDA(e, cudaMalloc((void**)&so.d_row0, (size_t)e->cfg.max_games * sizeof(long long)));
+    }
+    if (pin) {
+        // page-lock the caller's arrays so that the copies run at full speed and asynchronously
+        cudaError_t err = cudaHostRegister(h_states, (size_t)cap_samples * row * sizeof(float), cudaHostRegisterDefault);
+        if (err == cudaSuccess) err = cudaHostRegister(h_distributions, (size_t)cap_samples * A * sizeof(float), cudaHostRegisterDefault);
+        if (err == cudaSuccess) err = cudaHostRegister(h_outcomes, (size_t)cap_samples * sizeof(float), cudaHostRegisterDefault);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            cudaHostUnregister(h_states); cudaHostUnregister(h_distributions);
+            cudaGetLastError();
+            return fail(SPRL_E_CAPACITY, "cudaHostRegister of the sample arrays failed: %s", cudaGetErrorString(err));
+        }
+        so.registered = true;
+    }
+    so.h_states = h_states; so.h_dists = h_distributions; so.h_outcomes = h_outcomes; so.cap = cap_samples;
+    so.games_done = so.rows_done = 0; so.overflow = false; so.which = 0;
+    so.active = true;
+    return SPRL_OK;
+}
+
+int sprl_stream_info(sprl_engine* e, int64_t* games_done, int64_t* samples_done, uint64_t* chunks_while_playing) {
+    ENGINE_CHECK(e);
+    if (games_done) *games_done = e->so.games_done;
+    if (samples_done) *samples_done = e->so.rows_done;
+    if (chunks_while_playing) *chunks_while_playing = e->so.chunks;
+    return SPRL_OK;
+}
+
 int sprl_round(sprl_engine* e) {
     ENGINE_CHECK(e);
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration in progress");
@@ -406,6 +532,12 @@ int sprl_poll(sprl_engine* e, int64_t* slots_playing, int64_t* slots_failed) {
     ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
     if (slots_playing) *slots_playing = e->active_slots - (int64_t)c[0] - (int64_t)c[1];
     if (slots_failed) *slots_failed = (int64_t)c[1];
+    if (e->so.active && e->iteration_open && !e->match_open && !e->stepwise && c[1] == 0) {
+        const uint64_t before = e->so.games_done;
+        int rc = stream_out_advance(e);
+        if (rc) return rc;
+        if ((uint64_t)e->so.games_done > before && (int64_t)c[0] + (int64_t)c[1] < e->active_slots) e->so.chunks += 1;
+    }
     return SPRL_OK;
 }
 
@@ -514,7 +646,7 @@ int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_dist
     ENGINE_CUDA(e, cudaMemcpyAsync(e->d_row0, row0.data(), row0.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
     ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));      // row0 is a stack-lifetime host buffer
     if (n > 0) {
-        search_launch_emit(e->cfg.game, e->p, e->d_row0, S, e->d_states, e->d_dists, e->d_outcomes, e->stream);
+        search_launch_emit(e->cfg.game, e->p, 0, e->num_games, e->d_row0, S, e->d_states, e->d_dists, e->d_outcomes, e->stream);
         e->launches += 1;
         ENGINE_CUDA(e, cudaGetLastError());
     }
@@ -527,6 +659,22 @@ int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_dist
 
 int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions, float* h_outcomes,
                          int64_t* n_samples) {
+    if (e && e->so.active && h_states == e->so.h_states && h_distributions == e->so.h_dists && h_outcomes == e->so.h_outcomes) {
+        // streamed output: most rows are on the host already; embed and copy the games that finished last
+        ENGINE_CHECK(e);
+        if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
+        ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
+        int rc = stream_out_advance(e);
+        if (rc) return rc;
+        for (int k = 0; k < 2; ++k) ENGINE_CUDA(e, cudaStreamSynchronize(e->so.stream[k]));
+        int64_t moves = 0;
+        for (int m : e->h_moves) moves += m;
+        const int64_t total = moves * (e->cfg.use_sym ? e->gi.nsym : 1);
+        if (n_samples) *n_samples = total;
+        if (e->so.overflow || total > cap_samples || e->so.rows_done != total)
+            return fail(SPRL_E_CAPACITY, "%lld samples do not fit the caller's capacity %lld", (long long)total, (long long)std::min(cap_samples, e->so.cap));
+        return SPRL_OK;
+    }
     int64_t n = 0;
     float *ds, *dd, *dout;
     int rc = sprl_collect_samples_device(e, &ds, &dd, &dout, &n);
@@ -583,6 +731,7 @@ int sprl_begin_trees(sprl_engine* e, uint64_t first_game, int64_t num_trees) {
     if (rc) return rc;
     e->stepwise = true;
     e->step_sims = 0;
+    e->step_single = false;
     return push_iter_params(e);
 }
 
@@ -622,6 +771,7 @@ int sprl_search(sprl_engine* e, int sims, sprl_forward_fn forward, void* user) {
     if (rc) return rc;
     if (sims < 0) return fail(SPRL_E_INVALID, "sims must not be negative");
     e->step_sims = sims;
+    e->step_single = false;
     return stepwise_rounds(e, forward, user, 0);
 }
 
@@ -630,6 +780,7 @@ int sprl_search_batch(sprl_engine* e) {
     int rc = stepwise_check(e);
     if (rc) return rc;
     e->step_sims = 0x7fffffff;
+    e->step_single = true;
     rc = push_iter_params(e);
     if (!rc) rc = sprl_round(e);
     return rc;
@@ -640,6 +791,7 @@ int sprl_apply_evaluations(sprl_engine* e) {
     int rc = stepwise_check(e);
     if (rc) return rc;
     e->step_sims = 0;               // every tree only applies what is queued, then waits
+    e->step_single = true;
     rc = push_iter_params(e);
     if (!rc) rc = sprl_round(e);
     return rc;
@@ -713,6 +865,7 @@ int sprl_get_stats(sprl_engine* e, sprl_stats* out) {
     out->sims -= e->base.sims; out->evals -= e->base.evals; out->moves -= e->base.moves; out->games -= e->base.games;
     out->depth_sum -= e->base.depth_sum; out->legal_sum -= e->base.legal_sum; out->nodes_visited -= e->base.nodes_visited;
     out->leaves_terminal -= e->base.leaves_terminal; out->leaves_gray -= e->base.leaves_gray; out->leaves_empty -= e->base.leaves_empty;
+    out->leaves_duplicate -= e->base.leaves_duplicate;
     out->launches -= e->base.launches;
     return SPRL_OK;
 }

@@ -145,7 +145,7 @@ struct TreeWarp {
         int traversals, move_count, status, n_queued;
         long long game_index;
     };
-    struct Acc { u32 sims, evals, moves, games, depth_sum, legal_sum, nodes_visited, leaves_terminal, leaves_gray, leaves_empty; };
+    struct Acc { u32 sims, evals, moves, games, depth_sum, legal_sum, nodes_visited, leaves_terminal, leaves_gray, leaves_empty, leaves_duplicate; };
 
     const EngineParams& p;
     const int tree, lane;
@@ -171,7 +171,7 @@ struct TreeWarp {
         st.game_id = g.game_id; st.n_units = g.n_units; st.slab = g.slab; st.high_water = g.high_water;
         st.traversals = g.traversals; st.move_count = g.move_count; st.status = g.status; st.n_queued = g.n_queued;
         st.game_index = g.game_index;
-        acc = Acc{ 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        acc = Acc{ 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         rng.seed = p.seed; rng.game = st.game_id; rng.ctr = g.rng_ctr;
         slab = slab_ptr(st.slab);
     }
@@ -186,6 +186,7 @@ struct TreeWarp {
             g.sims += acc.sims; g.evals += acc.evals; g.moves += acc.moves; g.games += acc.games;
             g.depth_sum += acc.depth_sum; g.legal_sum += acc.legal_sum; g.nodes_visited += acc.nodes_visited;
             g.leaves_terminal += acc.leaves_terminal; g.leaves_gray += acc.leaves_gray; g.leaves_empty += acc.leaves_empty;
+            g.leaves_duplicate += acc.leaves_duplicate;
         }
     }
     __device__ size_t rec_index() const { return (size_t)st.game_index * p.max_moves + st.move_count; }
@@ -462,6 +463,7 @@ struct TreeWarp {
     // ---- UCTTree::searchAndGetLeaves (uct/UCTTree.hpp:76-114) + the symmetry draws of :141-149 ----
     __device__ void search_batch() {
         int trav = 0, nq = 0;
+        u32 my_leaf = 0;                                // lane q < 32 remembers queue entry q
         while (trav < p.max_batch) {
             ++trav;
             H h;
@@ -483,6 +485,7 @@ struct TreeWarp {
                 const size_t qs = (size_t)tree * p.max_queue + nq;
                 if (lane == 0) { p.q_leaf[qs] = leaf; p.q_plen[qs] = (unsigned char)sel_edges; }
                 if (lane < sel_edges) p.q_path[qs * DESCENT_MAX + lane] = sm.path[lane];      // for the backup in the next launch
+                if (lane == nq) my_leaf = leaf;
                 ++nq;
                 acc.leaves_empty += 1;
             }
@@ -492,17 +495,31 @@ struct TreeWarp {
         acc.sims += trav;
         st.n_queued = nq;
         __syncwarp();
+        // Quirk Q4 (uct/UCTTree.hpp:166-182): a node can be queued several times in one batch; every copy gets a symmetry
+        // draw and is backed up, but only the FIRST evaluation is kept -- so only the first copy gets an evaluator row.
+        // (Entries beyond the 32nd of a very wide queue are not compared: each keeps its own row.)
+        const int n32 = min(nq, 32);
+        bool dup = false;
+        for (int k = 0; k + 1 < n32; ++k) {
+            const u32 v = __shfl_sync(FULL, my_leaf, k);
+            dup = dup || (lane > k && lane < n32 && my_leaf == v);
+        }
+        const u32 first_mask = __ballot_sync(FULL, lane < n32 && !dup);
+        const int n_rows = __popc(first_mask) + (nq - n32);
+        acc.leaves_duplicate += (u32)(nq - n_rows);
         u32 row0 = 0;                                   // rows of the evaluator batch for this tree's leaves
         if (cfg_evaluator() == SPRL_EVAL_EXTERNAL && nq > 0) {
             const int side = MATCH ? agent.pad : 0;
-            if (lane == 0) row0 = atomicAdd(&p.q_count[side], (u32)nq) + (side ? p.iter->q_half : 0u);
+            if (lane == 0) row0 = atomicAdd(&p.q_count[side], (u32)n_rows) + (side ? p.iter->q_half : 0u);
             row0 = __shfl_sync(FULL, row0, 0);
             if (lane == 0) p.q_base[tree] = row0;
         }
         for (int q = 0; q < nq; ++q) {
             int s = cfg_use_sym() ? rng_uniform_int(rng, 0, G::NSYM - 1) : 0;
-            if (lane == 0) p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s;
-            if (cfg_evaluator() == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)row0 + q);
+            const bool first = q >= 32 || ((first_mask >> q) & 1u);
+            const u32 off = q >= 32 ? (u32)(__popc(first_mask) + q - 32) : (u32)__popc(first_mask & ((1u << q) - 1u));
+            if (lane == 0) { p.q_sym[(size_t)tree * p.max_queue + q] = (unsigned char)s; p.q_rowoff[(size_t)tree * p.max_queue + q] = (unsigned char)off; }
+            if (first && cfg_evaluator() == SPRL_EVAL_EXTERNAL) encode_leaf(p.q_leaf[(size_t)tree * p.max_queue + q], s, (size_t)row0 + off);
         }
         acc.evals += nq;
         __syncwarp();
@@ -648,7 +665,7 @@ struct TreeWarp {
             int s = p.q_sym[slot];
             H h;
             HL<W>::load(slab + leaf, h);
-            if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, row0 + q);
+            if (!(h.meta & META_EVALUATED)) evaluate_leaf(leaf, h, s, row0 + p.q_rowoff[slot]);
             if (!(h.meta & META_EXPANDED)) expand(leaf, h.meta);
             const int n_path = p.q_plen[slot];
             if (n_path) backup_path(p.q_path + slot * DESCENT_MAX, n_path, META_PLAYER(h.meta), h.net_value);
@@ -1022,7 +1039,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) k_rou
         if (t.st.status != ST_PLAYING) break;
         t.search_batch();
         if (t.st.status != ST_PLAYING) break;
-        if (p.evaluator == SPRL_EVAL_EXTERNAL) break;
+        if (p.evaluator == SPRL_EVAL_EXTERNAL || (stepwise && p.iter->step_single)) break;
     }
     if (t.st.status != ST_PLAYING && lane == 0) atomicAdd(&p.counters[t.st.status == ST_DONE ? 0 : 1], 1ULL);
     if (stepwise && !waiting && t.st.status == ST_PLAYING && lane == 0) atomicAdd(&p.counters[2], 1ULL);
@@ -1157,10 +1174,10 @@ __global__ void __launch_bounds__(32) k_tree_advance(EngineParams p, int n_trees
 //      148-189) embedded as in runWorker (selfplay/GridWorker.hpp:146-196) ----
 // One block per (game, move slot); writes S consecutive rows of states / distributions / outcomes.
 template <class G>
-__global__ void k_emit(EngineParams p, const long long* __restrict__ game_row0, int S,
+__global__ void k_emit(EngineParams p, long long g0, const long long* __restrict__ game_row0, int S,
                        float* __restrict__ states, float* __restrict__ dists, float* __restrict__ outcomes) {
     constexpr int W = G::W, PLANES = 2 * G::HISTORY + 1, ROW = PLANES * G::CELLS;
-    const long long g = blockIdx.x;         // grid = (games, max_moves)
+    const long long g = g0 + blockIdx.x;    // grid = (games of the range, max_moves)
     const int m = (int)blockIdx.y;
     if (m >= p.rec_moves[g]) return;
     const size_t ri = (size_t)g * p.max_moves + m;
@@ -1210,9 +1227,9 @@ template <class G> static void launch_round(const EngineParams& p, cudaStream_t 
     k_round<G><<<ceil_div(p.n_slots, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(p);
     k_flip<<<1, 1, 0, s>>>(p);
 }
-template <class G> static void launch_emit(const EngineParams& p, const long long* row0, int S, float* st, float* di,
-                                           float* ou, cudaStream_t s) {
-    k_emit<G><<<dim3((unsigned)p.num_games, (unsigned)p.max_moves), 256, 0, s>>>(p, row0, S, st, di, ou);
+template <class G> static void launch_emit(const EngineParams& p, long long g0, long long n_games, const long long* row0, int S, float* st,
+                                           float* di, float* ou, cudaStream_t s) {
+    k_emit<G><<<dim3((unsigned)n_games, (unsigned)p.max_moves), 256, 0, s>>>(p, g0, row0, S, st, di, ou);
 }
 
 template <class G> static void launch_tree_stats(const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw,
@@ -1242,8 +1259,8 @@ template <class G> static void launch_match_round(const EngineParams& p, const M
 
 void search_launch_begin(int game, const EngineParams& p, cudaStream_t s) { GAME_SWITCH(game, launch_begin<G>(p, s)); }
 void search_launch_round(int game, const EngineParams& p, cudaStream_t s) { GAME_SWITCH(game, launch_round<G>(p, s)); }
-void search_launch_emit(int game, const EngineParams& p, const long long* row0, int S, float* st, float* di, float* ou,
-                        cudaStream_t s) { GAME_SWITCH(game, launch_emit<G>(p, row0, S, st, di, ou, s)); }
+void search_launch_emit(int game, const EngineParams& p, long long g0, long long n_games, const long long* row0, int S, float* st, float* di,
+                        float* ou, cudaStream_t s) { GAME_SWITCH(game, launch_emit<G>(p, g0, n_games, row0, S, st, di, ou, s)); }
 void search_launch_match_begin(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_begin<G>(p, m, s)); }
 void search_launch_match_round(int game, const EngineParams& p, const MatchParams& m, cudaStream_t s) { GAME_SWITCH(game, launch_match_round<G>(p, m, s)); }
 void search_launch_tree_stats(int game, const EngineParams& p, int n, float* N, float* W, float* P, float* rn, float* rw, signed char* pl,

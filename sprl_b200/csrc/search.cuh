@@ -64,6 +64,7 @@ struct TreeState {
     unsigned long long sims, evals, moves, games;
     unsigned long long depth_sum, legal_sum, nodes_visited;
     unsigned long long leaves_terminal, leaves_gray, leaves_empty;
+    unsigned long long leaves_duplicate;   // queued leaves that were already in the same batch's queue (quirk Q4): no evaluator row
 };
 
 struct AgentCfg {
@@ -83,7 +84,7 @@ struct IterParams {
     // a tree only while it has fewer than step_sims descents for the current move
     int stepwise;
     int step_sims;
-    int pad;
+    int step_single;                 // one searchAndGetLeaves batch per launch, whatever the evaluator (sprl_search_batch)
     AgentCfg agent[2];               // match play: the two sides
 };
 
@@ -107,6 +108,8 @@ struct EngineParams {
     u32* q_count;                   // [2] rows handed out by the running launch
     u32* q_rows;                    // [2] rows of the previous launch: what the evaluator has to compute (set by k_flip)
     u32* q_base;                    // [n_slots] first row of a tree's queued leaves
+    unsigned char* q_rowoff;        // [n_slots][max_queue] row of a queued leaf relative to q_base: a leaf queued twice in a batch
+                                    //   (quirk Q4, uct/UCTTree.hpp:166-182: only its first evaluation is kept) gets ONE row
     u32 q_half;                     // first row of agent 1 (match play)            } host copies of the IterParams
     // per-game records, game-major: [num_games][max_moves]                            } fields: kernels read `iter`,
     long long num_games;             //                                                } never these

@@ -90,6 +90,7 @@ class Engine:
         self.samples_per_move = self.gi.nsym if self.cfg.use_sym else 1
         self._nn = None
         self._match_running = False
+        self._stream = None
 
     def close(self):
         if self.handle:
@@ -373,8 +374,32 @@ class Engine:
         capi.check(self.lib.sprl_iteration_counts(self.handle, C.byref(m), C.byref(s)))
         return m.value, s.value
 
+    def stream_samples(self, cap_samples):
+        """Streamed sample output (sprl_stream_samples): allocates page-locked host arrays for up to cap_samples rows; from
+        now on finished games are embedded and copied while the others still play, and collect_samples() / run_iteration()
+        return views of these arrays (valid until the next iteration).  cap_samples = 0 turns it off."""
+        gi = self.gi
+        if not cap_samples:
+            capi.check(self.lib.sprl_stream_samples(self.handle, 0, None, None, None, 0))
+            self._stream = None
+            return
+        bufs = (np.empty((cap_samples, 2 * gi.history + 1, gi.rows, gi.cols), np.float32), np.empty((cap_samples, gi.actions), np.float32),
+                np.empty((cap_samples,), np.float32))
+        capi.check(self.lib.sprl_stream_samples(self.handle, cap_samples, _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), 1))
+        self._stream = bufs
+
+    def stream_info(self):
+        g, n, c = C.c_int64(), C.c_int64(), C.c_uint64()
+        capi.check(self.lib.sprl_stream_info(self.handle, C.byref(g), C.byref(n), C.byref(c)))
+        return dict(games_done=g.value, samples_done=n.value, chunks_while_playing=c.value)
+
     def collect_samples(self):
         gi = self.gi
+        if getattr(self, "_stream", None) is not None:
+            st, di, ou = self._stream
+            got = C.c_int64()
+            capi.check(self.lib.sprl_collect_samples(self.handle, st.shape[0], _ptr(st), _ptr(di), _ptr(ou), C.byref(got)))
+            return st[:got.value], di[:got.value], ou[:got.value]
         _, n = self.iteration_counts()
         states = np.empty((n, 2 * gi.history + 1, gi.rows, gi.cols), np.float32)
         dists = np.empty((n, gi.actions), np.float32)

@@ -248,6 +248,9 @@ def test_external_evaluator_bit_exact(game, sims, b, q, alpha, ngames, graph):
     assert net.calls > 0
     compare_selfplay(ref, got)
     assert st["sims"] == ref["stats"]["total_traversals"] and st["evals"] == ref["stats"]["total_evals"]
+    # quirk Q4: the fresh root alone is queued max_queue times in the first batch of a game; the copies are counted like the
+    # reference's getNumEvals but share one evaluator row
+    assert (q - 1) * ngames <= st["leaves_duplicate"] < st["evals"] // 2
 
 
 def test_reused_engine_and_captured_graph_follow_the_new_iteration():
@@ -383,6 +386,37 @@ def test_sharded_generation_equals_unsharded():
     for g in range(n):
         assert np.array_equal(merged[g][0], whole["move_N"][bounds[g]:bounds[g + 1]]), g
         assert np.array_equal(merged[g][1], whole["move_action"][bounds[g]:bounds[g + 1]]), g
+
+
+def test_streamed_samples_equal_the_collected_ones():
+    """sprl_stream_samples: finished games leave for the (page-locked) host arrays while the others still play -- more
+    games than slots, so most of them finish early; the result is the array collect_samples() builds at the end, bit for
+    bit, for a second iteration on the same registration too, and a too small capacity is reported."""
+    kw = dict(seed=4, sims=32, max_batch=8, max_queue=4, num_slots=24, max_games=400)
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, **kw) as eng:
+        want = [eng.run_iteration(n, first_game=f) for n, f in ((400, 0), (150, 1000))]
+    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_HASHNET, **kw) as eng:
+        eng.stream_samples(400 * 8 * 70)
+        for (n, f), ref in zip(((400, 0), (150, 1000)), want):
+            eng.begin_iteration(f, n)
+            chunks = []
+            while True:
+                for _ in range(8):
+                    eng.round()
+                playing, failed = eng.poll()
+                chunks.append(eng.stream_info()["games_done"])
+                if playing == 0:
+                    break
+            got = eng.collect_samples()
+            assert 0 < chunks[len(chunks) // 2] < n          # half way through, some games had left and some had not
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
+        assert eng.stream_info()["chunks_while_playing"] > 4
+        eng.stream_samples(1000)                              # far too small
+        with pytest.raises(capi.SprlError):
+            eng.run_iteration(40)
+        eng.stream_samples(0)
+        assert eng.run_iteration(40)[0].shape[0] > 40 * 8 * 20
 
 
 def test_device_resident_samples_alias_the_host_copy():
