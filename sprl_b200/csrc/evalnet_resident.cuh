@@ -13,10 +13,9 @@
 //   * two CTAs of a cluster form a tcgen05 CTA PAIR (cta_group::2, M = 256): each CTA supplies its own 128-cell tile
 //     and its own accumulators and holds HALF of the weight rows, which is what makes a whole block (2 x 147 KB of
 //     hi/lo fp16 weights) fit the pair's shared memory, and halves the B-operand reads per SM;
-//   * every CTA runs TWO tile streams (X, Y), each with its own image pair and 256 TMEM columns (192 accumulator + 64
-//     residual).  The leader's MMA warp issues stage j of X, then of Y, then stage j+1 of X ...; the 16 epilogue warps
-//     follow in the same order (each finishes 16 channels of a lane quarter), so the epilogue of one stream runs
-//     under the MMAs of the other inside ONE CTA.
+//   * every CTA runs TWO tile streams (X, Y): own image pair, own 256 TMEM columns (192 accumulator + 64 residual),
+//     own group of 8 epilogue warps.  The leader's MMA warp issues stage j of X, then of Y, then stage j+1 of X ...:
+//     the epilogue of one stream runs under the MMAs of the other inside ONE CTA.
 //
 // Per SM and tile-layer the shared-memory port now carries 144 KB of A reads + 108 KB of B reads + 37 KB of image
 // writes = 84 B/clk of 128 against 3.46 k cycles of MMAs (was: 147 + 221 + 147 KB of weight writes + 37).
@@ -27,7 +26,7 @@
 #pragma once
 
 constexpr int RB_STREAMS = 2;
-constexpr int RB_EPI_WARPS = 8;                              // per stream: 16 epilogue warps in all, every one serves both streams
+constexpr int RB_EPI_WARPS = 8;                              // per stream
 constexpr int RB_MMA_WARP = RB_STREAMS * RB_EPI_WARPS;       // warp 16
 constexpr int RB_THREADS = (RB_MMA_WARP + 1) * 32;           // 544
 constexpr int RB_SLOTS = 144;                                // 16 zero slots + 128 cells; the next group's zero slots close this one
@@ -74,7 +73,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
     const int off_bias = RB_OFF_W + ph.w_bytes, off_bars = off_bias + ph.n_stages * CH * 4, off_tmem = off_bars + 64;
     const uint32_t bar_acc = s_base + off_bars;      // [2] accumulators of stream s complete (committed by the leader to both CTAs)
     const uint32_t bar_img = bar_acc + 16;           // [2] leader's copy is used: stream s's image is written and its accumulators
-                                                     //     are drained in BOTH CTAs (one arrival per epilogue warp of the pair: 32)
+                                                     //     are drained in BOTH CTAs (one arrival per epilogue warp of the pair)
     const uint32_t bar_w = bar_img + 16;             // this CTA's resident weights have landed
     float* s_bias = reinterpret_cast<float*>(smem + off_bias);
     const long long n_tiles = (batch + 1) / 2, n_quads = (n_tiles + 3) / 4;      // a pair takes 4 tiles (2 streams x 2 CTAs) per turn
@@ -88,7 +87,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         s_bias[i] = net.bias[S.layer * CH + (i & (CH - 1))] * (S.kind != RB_HEADS ? ACT_SCALE : 1.0f);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RB_STREAMS; ++s) { mbar_init(bar_acc + 8 * s, 1); mbar_init(bar_img + 8 * s, 2 * RB_STREAMS * RB_EPI_WARPS); }
+        for (int s = 0; s < RB_STREAMS; ++s) { mbar_init(bar_acc + 8 * s, 1); mbar_init(bar_img + 8 * s, 2 * RB_EPI_WARPS); }
         mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -152,30 +151,30 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             if (lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[0] = t_wait; tm[2] = NOW() - t0; }
         }
     } else {
-        // ===== epilogue warps: cell m = TMEM lane m; warp w finishes channels [16 q, 16 q + 16) of lane quarter w & 3 =====
-        // All 16 warps serve BOTH streams, in the order the MMA warp issues them (X stage j, Y stage j, X stage j+1 ...):
-        // a stage's epilogue is then spread over twice the warps (the epilogue is a latency chain -- TMEM load, shuffles,
-        // split, store -- not an issue-bound loop), so it is short enough to hide under the other stream's MMAs.
-        const int q = warp >> 2;
-        const int m = (warp & 3) * 32 + lane;                        // cell 0..127 = TMEM lane
+        // ===== epilogue group of stream s: cell m = TMEM lane m =====
+        const int s = warp >> 3, w8 = warp & 7;
+        const int m = (w8 & 3) * 32 + lane;                          // cell 0..127 = TMEM lane
+        const int half = w8 >> 2;                                    // which half of the channels this warp finishes
         const int slot = cell_slot(m);
         const int g8 = m >> 3;
         const int r = g8 >> 1, c = m & 7, b = g8 & 1;
         const bool valid = r < net.rows && c < net.cols;             // lattice positions outside the board stay zero
         const int cell = r * net.cols + c;
-        const uint32_t t_lane0 = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t lead_img0 = map_to_cta(bar_img, 0);
+        const uint32_t t_lane = tmem + (uint32_t)(s * RB_STREAM_COLS) + ((uint32_t)((w8 & 3) * 32) << 16);
+        uint4* a_hi = reinterpret_cast<uint4*>(smem + (2 * s) * RB_IMG_BYTES);
+        uint4* a_lo = reinterpret_cast<uint4*>(smem + (2 * s + 1) * RB_IMG_BYTES);
+        const uint32_t lead_img = map_to_cta(bar_img + 8 * s, 0);
         float mx = 0.0f;                                             // largest |image value| this thread produced
         const float vmask = valid ? 1.0f : 0.0f, lmask = c > 0 ? 1.0f : 0.0f, rmask = c + 1 < net.cols ? 1.0f : 0.0f;
         const int cells = net.rows * net.cols, planes = net.in_planes;
-        uint32_t acc_phase = 0;                                      // bit s: parity of stream s's next wait
+        uint32_t acc_phase = 0;
         long long t_acc = 0, t0 = NOW();
         // "my part of stream s's image is written and I am done reading its accumulators", to the leader's MMA warp
-        auto signal = [&](int s) {
+        auto signal = [&]() {
             proxy_fence();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lead_img0 + 8 * s) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lead_img) : "memory");
         };
         // leaf planes -> stem image channels: channel dyi * planes + p of a cell holds plane p of the cell one row
         // above / at / below it (the stem's vertical taps are folded into K, see k_evalnet)
@@ -189,19 +188,20 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             }
         };
         const int last_stage = ph.n_stages - 1;
-        const int stem_cgs = ph.in_planes_mode ? 2 * ph.st[0].ksteps : 0;     // channel groups of the stem image
-        const long long quad_step = 4LL * n_pairs, tile_end = n_quads * 4;
-        float vnext[RB_STREAMS][KCH];                                        // the next tile's first channel group, per stream
-        // ---- the input of `tile` into stream s's image (and residual columns)
-        auto input_stage = [&](int s, long long tile) {
-            uint4* a_hi = reinterpret_cast<uint4*>(smem + (2 * s) * RB_IMG_BYTES);
-            uint4* a_lo = reinterpret_cast<uint4*>(smem + (2 * s + 1) * RB_IMG_BYTES);
+        const long long quad_step = 4LL * n_pairs;
+        const long long tile0 = (long long)pair * 4 + s * 2 + crank;
+        float vnext[KCH];
+        if (ph.in_planes_mode) load_planes(tile0, half, vnext);
+        mbar_wait(bar_w, 0u, net.error_flag, 20);                   // (the leader's MMAs read both CTAs' weights: every arrival below implies them)
+        for (long long tile = tile0; tile < n_quads * 4; tile += quad_step) {
+            const long long board = tile * 2 + b;
+            // ---- input stage ----
             if (ph.in_planes_mode) {
-                for (int cg = q; cg < stem_cgs; cg += 4) {
+                for (int cg = half; cg < 2 * ph.st[0].ksteps; cg += 2) {
                     float v[KCH];
-                    if (cg == q) {
+                    if (cg == half) {
 #pragma unroll
-                        for (int j = 0; j < KCH; ++j) v[j] = vnext[s][j];
+                        for (int j = 0; j < KCH; ++j) v[j] = vnext[j];
                     } else {
                         load_planes(tile, cg, v);
                     }
@@ -213,60 +213,46 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             } else {
                 // fp32 activations of the previous phase (image units): residual columns + hi/lo image
                 const float4* src = reinterpret_cast<const float4*>(ph.act) + (size_t)tile * (RB_ACT_TILE_FLOATS / 4) + m;
-                float o[16];
+#pragma unroll 1
+                for (int q = 2 * half; q < 2 * half + 2; ++q) {
+                    float o[16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 x = tile < n_tiles ? __ldcg(src + (q * 4 + j) * TILE_M) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    o[4 * j] = x.x; o[4 * j + 1] = x.y; o[4 * j + 2] = x.z; o[4 * j + 3] = x.w;
-                }
-                tmem_st16(t_lane0 + (uint32_t)(s * RB_STREAM_COLS) + RES_COL + q * 16, o);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 x = tile < n_tiles ? __ldcg(src + (q * 4 + j) * TILE_M) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        o[4 * j] = x.x; o[4 * j + 1] = x.y; o[4 * j + 2] = x.z; o[4 * j + 3] = x.w;
+                    }
+                    tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    uint4 h, l;
-                    split8(o + KCH * j, h, l, mx);
-                    a_hi[(q * 2 + j) * RB_SLOTS + slot] = h;
-                    a_lo[(q * 2 + j) * RB_SLOTS + slot] = l;
+                    for (int j = 0; j < 2; ++j) {
+                        uint4 h, l;
+                        split8(o + KCH * j, h, l, mx);
+                        a_hi[(q * 2 + j) * RB_SLOTS + slot] = h;
+                        a_lo[(q * 2 + j) * RB_SLOTS + slot] = l;
+                    }
                 }
             }
-        };
-        const long long first_tile = (long long)pair * 4 + crank;           // stream s: + 2 s
-        if (ph.in_planes_mode && q < stem_cgs) {
-#pragma unroll
-            for (int s = 0; s < RB_STREAMS; ++s) load_planes(first_tile + 2 * s, q, vnext[s]);
-        }
-        mbar_wait(bar_w, 0u, net.error_flag, 20);                   // (the leader's MMAs read both CTAs' weights: every arrival below implies them)
-        if (first_tile < tile_end) {
-#pragma unroll
-            for (int s = 0; s < RB_STREAMS; ++s) { input_stage(s, first_tile + 2 * s); signal(s); }
-        }
-        for (long long tile0 = first_tile; tile0 < tile_end; tile0 += quad_step) {
-            const bool more = tile0 + quad_step < tile_end;
+            signal();
             for (int j = 0; j <= last_stage; ++j) {
                 const RbStage S = ph.st[j];
+                if (j == last_stage && tile + quad_step < n_quads * 4) {
+                    // the next tile's input: planes into registers, activations towards L2, under this stage's MMAs
+                    if (ph.in_planes_mode) load_planes(tile + quad_step, half, vnext);
+                    else if (lane == 0 && tile + quad_step < n_tiles) {
+                        const float* nsrc = ph.act + (size_t)(tile + quad_step) * RB_ACT_TILE_FLOATS + (w8 & 3) * 32 * 4;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + ((2 * half) * 4 + k) * TILE_M * 4) : "memory");
+                    }
+                }
+                { long long a = NOW(); mbar_wait(bar_acc + 8 * s, acc_phase, net.error_flag, 30 + s); t_acc += NOW() - a; }
+                acc_phase ^= 1u;
+                tc_fence_after();
                 const float* bias = s_bias + j * CH;
                 // accumulator -> image units for the conv stages (real units for the heads); exact powers of two
                 const float inv_scale = net.inv_scale[S.layer] * (S.kind != RB_HEADS ? ACT_SCALE : 1.0f);
-#pragma unroll
-                for (int s = 0; s < RB_STREAMS; ++s) {
-                    const long long tile = tile0 + 2 * s;
-                    const long long board = tile * 2 + b;
-                    const uint32_t t_lane = t_lane0 + (uint32_t)(s * RB_STREAM_COLS);
-                    uint4* a_hi = reinterpret_cast<uint4*>(smem + (2 * s) * RB_IMG_BYTES);
-                    uint4* a_lo = reinterpret_cast<uint4*>(smem + (2 * s + 1) * RB_IMG_BYTES);
-                    if (j == last_stage && more) {
-                        // the next tile's input: planes into registers, activations towards L2, under this stage's MMAs
-                        if (ph.in_planes_mode) { if (q < stem_cgs) load_planes(tile + quad_step, q, vnext[s]); }
-                        else if (lane == 0 && tile + quad_step < n_tiles) {
-                            const float* nsrc = ph.act + (size_t)(tile + quad_step) * RB_ACT_TILE_FLOATS + (warp & 3) * 32 * 4;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + (q * 4 + k) * TILE_M * 4) : "memory");
-                        }
-                    }
-                    { long long a = NOW(); mbar_wait(bar_acc + 8 * s, (acc_phase >> s) & 1u, net.error_flag, 30 + s); t_acc += NOW() - a; }
-                    acc_phase ^= 1u << s;
-                    tc_fence_after();
-                    if (S.kind != RB_HEADS) {
+                if (S.kind != RB_HEADS) {
+#pragma unroll 1
+                    for (int q = 2 * half; q < 2 * half + 2; ++q) {
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = accumulator columns [dx*64, dx*64+64)
                         float o[16], v[16], w[16];
                         tmem_ld16x3(t_lane + CH + q * 16, t_lane + q * 16, t_lane + 2 * CH + q * 16, o, v, w);   // dx = 0, -1, +1
@@ -300,26 +286,25 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                                 a_lo[(q * 2 + jj) * RB_SLOTS + slot] = l;
                             }
                         }
-                    } else if (q == 0) {
-                        // ---- heads (1x1): columns 0..pc-1 = policy conv channels, column pc = value conv; the ReLU'd
-                        // activations go to HBM for k_heads
-                        float v[16];
-                        tmem_ld16(t_lane, v);
-                        const int pc = net.policy_channels;
-                        if (board < batch && valid) {
-                            float* dst = net.head_act + board * (long long)((pc + 1) * cells);
-#pragma unroll
-                            for (int jj = 0; jj < 3; ++jj)
-                                if (jj <= pc) dst[jj * cells + cell] = fmaxf(v[jj] * inv_scale + bias[jj], 0.0f);
-                        }
                     }
-                    if (j < last_stage) signal(s);
-                    else if (more) { input_stage(s, tile + quad_step); signal(s); }
+                } else {
+                    // ---- heads (1x1): columns 0..pc-1 = policy conv channels, column pc = value conv; the ReLU'd
+                    // activations go to HBM for k_heads
+                    float v[16];
+                    tmem_ld16(t_lane, v);
+                    const int pc = net.policy_channels;
+                    if (board < batch && half == 0 && valid) {
+                        float* dst = net.head_act + board * (long long)((pc + 1) * cells);
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj)
+                            if (jj <= pc) dst[jj * cells + cell] = fmaxf(v[jj] * inv_scale + bias[jj], 0.0f);
+                    }
                 }
+                if (j < last_stage) signal();       // (after the last stage the next tile's input stage signals)
             }
         }
         if (mx > HALF_MAX) atomicExch(net.error_flag + 1, 1ULL);
-        if ((warp & 3) == 0 && lane == 0 && q < 2 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[4 + q] = t_acc; tm[6 + q] = NOW() - t0; }
+        if (w8 == 0 && lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[4 + s] = t_acc; tm[6 + s] = NOW() - t0; }
     }
     tc_fence_before();
     __syncthreads();
