@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--slots", type=int, default=16384, help="concurrent games per GPU")
     ap.add_argument("--rounds", type=int, default=256, help="search rounds per step")
     ap.add_argument("--e2e-games", type=int, default=16384, help="games per e2e step per GPU")
-    ap.add_argument("--e2e-slots", type=int, default=8192, help="concurrent games of the e2e engine (fewer than games: slots refill, finished games stream out)")
+    ap.add_argument("--e2e-slots", type=int, default=16384, help="concurrent games of the e2e engine (fewer than games: slots refill, finished games stream out)")
     ap.add_argument("--e2e-no-stream", action="store_true", help="collect the samples at the end into pageable memory (round-1 behaviour)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
@@ -279,7 +279,9 @@ def run_ours(args):
                        "algorithmic_bytes_per_launch": round(bps * sims_per_launch, 1),
                        "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
                        "select_depth": round(D, 3), "legal_per_node": round(L, 3), "evals_per_sim": round(ef, 4),
-                       "sampled_launches": n_probe, "share_of_round": round(k_ms / (k_ms + nn_ms), 4)}
+                       "sampled_launches": n_probe, "share_of_round": round(k_ms / (k_ms + nn_ms), 4),
+                       "probe_note": "the two legs are timed un-graphed, with CUDA events between the launches of 64 extra rounds: their "
+                                     "sum runs 2-3 % above ms_per_step / rounds_per_step (event records and launch gaps the graph does not have)"}
     batch_rows = args.slots * MAX_QUEUE
     if evalnet is not None:
         # dominant kernel of the step: the evaluator's forward over the rows in use (the leaves the launch queued)
@@ -318,7 +320,7 @@ def run_ours(args):
     }
 
     if not args.no_e2e:
-        e2e = run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet)     # every rank, on its own shard
+        e2e = run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet, rank, world)     # every rank, on its own shard
         agg = torch.tensor([e2e.pop("_sims"), e2e.pop("_moves")], dtype=torch.float64, device=dev)
         tm = torch.tensor([e2e.pop("_ms")], dtype=torch.float64, device=dev)
         if world > 1:
@@ -337,9 +339,14 @@ def run_ours(args):
         emit(result)
 
 
-def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
-    """Full iterations through the public API with host buffers: weights H2D from pinned
-    memory, run_iteration of full games, samples D2H."""
+def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet, rank=0, world=1):
+    """Full generations through the public API with host buffers.  Every e2e step is one generation as SURVEY.md 8(d)
+    config 4 / 8(e) describe it: rank 0 holds the new network's weights in host memory and broadcasts the flat parameter +
+    buffer vector (NCCL at N > 1), every rank folds / packs / uploads them, plays its shard of the generation's games
+    (ids rank, rank + world, ...) start to finish, streams the samples to page-locked host arrays, and the ranks
+    all-gather their sample counts (the row ranges of the generation's arrays)."""
+    import torch.distributed as dist
+    from sprl_b200 import shard
     import numpy as np
     import torch
     from sprl_b200 import capi
@@ -360,14 +367,34 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
         else:
             eng.attach_network(module, use_cuda_graph=not args.no_graph)
 
+        eng.set_game_stride(world)
+        names = [k for k, _ in module.state_dict().items()]
+        shapes = [tuple(v.shape) for _, v in module.state_dict().items()]
+        flat_host = torch.cat([v.detach().reshape(-1).float().cpu() for _, v in module.state_dict().items()]).pin_memory()
+        counts = []
+
         def one(first):
+            if world > 1:
+                # the generation's weights: host (rank 0) -> device -> NCCL broadcast -> every rank's host copy for the packer
+                flat = flat_host.to(dev, non_blocking=True) if rank == 0 else torch.empty(flat_host.numel(), device=dev)
+                dist.broadcast(flat, 0)
+                flat_cpu = flat.cpu()
+            else:
+                flat_cpu = flat_host
             if evalnet is not None:
-                evalnet.update(host_state)          # host weights -> folded / packed -> device, inside the timed region
+                at, state = 0, {}
+                for k, shp in zip(names, shapes):
+                    n = int(np.prod(shp)) if shp else 1
+                    state[k] = flat_cpu[at:at + n].reshape(shp).numpy()
+                    at += n
+                evalnet.update(state)               # host weights -> folded / packed -> device, inside the timed region
             else:
                 with torch.no_grad():
                     for t, h in zip(flat_params, host_weights):
                         t.copy_(h, non_blocking=True)
-            return eng.run_iteration(G, first_game=first)
+            out = eng.run_iteration(G, first_game=first * world + rank)
+            counts.append(shard.gather_sample_counts(out[0].shape[0], device=dev))     # all-gather of one int64 per rank
+            return out
 
         # warm-up: a short iteration with the same engine (graph capture, cuDNN autotune)
         one(0) if args.e2e_steps > 1 else eng.run_iteration(min(G, 64), first_game=0)
@@ -388,6 +415,8 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet):
             "d2h_bytes_per_step": int(d2h / args.e2e_steps), "moves_per_sec": None,
             "games_per_step_per_gpu": G, "slots_per_gpu": min(G, args.e2e_slots), "steps": args.e2e_steps, "ms_per_step": None,
             "streamed_chunks_while_playing": None if args.e2e_no_stream else eng_info["chunks_while_playing"],
+            "collectives_per_step": "none (1 rank)" if world == 1 else f"NCCL broadcast of {flat_host.numel() * 4} weight bytes + all-gather of {world} sample counts",
+            "sample_rows_per_rank_last_step": counts[-1] if counts else None,
             "note": "public API (Engine.run_iteration) with host buffers: weights from host memory (fold + pack + H2D), full games "
                     "start to finish incl. the tail where few games are left, every sample row D2H into page-locked host arrays "
                     "(finished games stream out while the others play)",

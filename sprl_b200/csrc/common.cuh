@@ -1,6 +1,7 @@
 // common.cuh -- error plumbing shared by the translation units of libsprl_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -40,6 +41,16 @@ struct DeviceBuf {
         return cudaMalloc((void**)&p, count * sizeof(T));
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// NVTX range of a host entry point (the reference has a stopwatch only; here every C ABI call that
+// enqueues or waits for device work shows up as a named range in a timeline profiler; header-only nvtx3, free when no
+// profiler is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

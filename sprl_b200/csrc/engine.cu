@@ -313,6 +313,7 @@ int sprl_eval_rows(sprl_engine* e, const uint32_t** d_rows) {
 int64_t sprl_eval_batch(const sprl_engine* e) { return e ? (int64_t)e->cfg.num_slots * e->cfg.max_queue : 0; }
 
 int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games) {
+    NvtxRange nvtx_range("sprl_begin_iteration");
     ENGINE_CHECK(e);
     if (num_games <= 0) return fail(SPRL_E_INVALID, "num_games must be positive");
     if (num_games > e->cfg.max_games) return fail(SPRL_E_CAPACITY, "num_games %lld exceeds max_games %lld", (long long)num_games, (long long)e->cfg.max_games);
@@ -346,6 +347,7 @@ int sprl_begin_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games)
 static int load_game_moves(sprl_engine* e, int64_t* n_moves);
 
 int sprl_match_begin(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t first_game, int64_t num_games) {
+    NvtxRange nvtx_range("sprl_match_begin");
     ENGINE_CHECK(e);
     if (!h_agents) return fail(SPRL_E_INVALID, "null agents");
     if (num_games <= 0) return fail(SPRL_E_INVALID, "num_games must be positive");
@@ -510,6 +512,7 @@ int sprl_stream_info(sprl_engine* e, int64_t* games_done, int64_t* samples_done,
 }
 
 int sprl_round(sprl_engine* e) {
+    NvtxRange nvtx_range("sprl_round");
     ENGINE_CHECK(e);
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration in progress");
     if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !e->p.nn_in) return fail(SPRL_E_STATE, "evaluator buffers are not bound");
@@ -526,6 +529,7 @@ int sprl_round(sprl_engine* e) {
 }
 
 int sprl_poll(sprl_engine* e, int64_t* slots_playing, int64_t* slots_failed) {
+    NvtxRange nvtx_range("sprl_poll");
     ENGINE_CHECK(e);
     unsigned long long c[4] = { 0, 0, 0, 0 };
     ENGINE_CUDA(e, cudaMemcpyAsync(c, e->p.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
@@ -578,6 +582,7 @@ static int run_rounds(sprl_engine* e, bool external, sprl_forward_fn forward, vo
 }
 
 int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, sprl_forward_fn forward, void* user) {
+    NvtxRange nvtx_range("sprl_run_iteration");
     ENGINE_CHECK(e);
     if (e->cfg.evaluator == SPRL_EVAL_EXTERNAL && !forward) return fail(SPRL_E_INVALID, "SPRL_EVAL_EXTERNAL needs a forward callback");
     int rc = sprl_begin_iteration(e, first_game, num_games);
@@ -587,6 +592,7 @@ int sprl_run_iteration(sprl_engine* e, uint64_t first_game, int64_t num_games, s
 
 int sprl_run_match(sprl_engine* e, const sprl_agent_config* h_agents, uint64_t first_game, int64_t num_games,
                    sprl_forward_fn forward, void* user) {
+    NvtxRange nvtx_range("sprl_run_match");
     ENGINE_CHECK(e);
     if (!h_agents) return fail(SPRL_E_INVALID, "null agents");
     const bool external = h_agents[0].evaluator == SPRL_EVAL_EXTERNAL || h_agents[1].evaluator == SPRL_EVAL_EXTERNAL;
@@ -619,6 +625,7 @@ int sprl_iteration_counts(sprl_engine* e, int64_t* n_moves, int64_t* n_samples) 
 }
 
 int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_distributions, float** d_outcomes, int64_t* n_samples) {
+    NvtxRange nvtx_range("sprl_collect_samples_device");
     ENGINE_CHECK(e);
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
     int64_t moves = 0;
@@ -659,6 +666,7 @@ int sprl_collect_samples_device(sprl_engine* e, float** d_states, float** d_dist
 
 int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, float* h_distributions, float* h_outcomes,
                          int64_t* n_samples) {
+    NvtxRange nvtx_range("sprl_collect_samples");
     if (e && e->so.active && h_states == e->so.h_states && h_distributions == e->so.h_dists && h_outcomes == e->so.h_outcomes) {
         // streamed output: most rows are on the host already; embed and copy the games that finished last
         ENGINE_CHECK(e);
@@ -694,6 +702,7 @@ int sprl_collect_samples(sprl_engine* e, int64_t cap_samples, float* h_states, f
 int sprl_move_stats(sprl_engine* e, int64_t cap_moves, float* h_N, float* h_W, float* h_P, float* h_root_N,
                     float* h_root_W, int32_t* h_action, int32_t* h_traversals, int8_t* h_player,
                     int32_t* h_game_moves, uint64_t* h_game_draws, int64_t* n_moves) {
+    NvtxRange nvtx_range("sprl_move_stats");
     ENGINE_CHECK(e);
     if (!e->cfg.record_stats) return fail(SPRL_E_STATE, "engine was created without record_stats");
     if (!e->iteration_open) return fail(SPRL_E_STATE, "no iteration has been run");
@@ -766,6 +775,7 @@ static int stepwise_rounds(sprl_engine* e, sprl_forward_fn forward, void* user, 
 }
 
 int sprl_search(sprl_engine* e, int sims, sprl_forward_fn forward, void* user) {
+    NvtxRange nvtx_range("sprl_search");
     ENGINE_CHECK(e);
     int rc = stepwise_check(e);
     if (rc) return rc;
@@ -799,6 +809,7 @@ int sprl_apply_evaluations(sprl_engine* e) {
 
 int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, float* h_P, float* h_root_N, float* h_root_W,
                     int8_t* h_player, int8_t* h_terminal, int8_t* h_winner, int32_t* h_traversals, int8_t* h_mask, int32_t* h_queued) {
+    NvtxRange nvtx_range("sprl_root_stats");
     ENGINE_CHECK(e);
     int rc = stepwise_check(e);
     if (rc) return rc;
@@ -835,6 +846,7 @@ int sprl_root_stats(sprl_engine* e, int64_t cap_trees, float* h_N, float* h_W, f
 }
 
 int sprl_advance(sprl_engine* e, const int32_t* h_actions, int64_t n_actions) {
+    NvtxRange nvtx_range("sprl_advance");
     ENGINE_CHECK(e);
     int rc = stepwise_check(e);
     if (rc) return rc;

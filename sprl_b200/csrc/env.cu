@@ -456,6 +456,7 @@ int sprl_game_info_get(int game, sprl_game_info* out) {
 int sprl_env_step(int device, int game, int64_t n, const int8_t* h_cells, const int8_t* h_player,
                   const int32_t* h_action, int8_t* h_next_cells, int8_t* h_next_player,
                   int8_t* h_terminal, int8_t* h_winner, int8_t* h_mask) {
+    NvtxRange nvtx_range("sprl_env_step");
     if (n < 0 || !h_cells || !h_player || !h_action || !h_next_cells || !h_next_player || !h_terminal || !h_winner || !h_mask)
         return fail(SPRL_E_INVALID, "sprl_env_step: null buffer or negative count");
     if (n == 0) return SPRL_OK;
@@ -472,6 +473,7 @@ int sprl_env_rollout(int device, int game, uint64_t seed, uint64_t first_game, i
                      int32_t* h_game_steps, int8_t* h_final_winner, int64_t cap,
                      int8_t* h_cells, int8_t* h_player, int8_t* h_terminal, int8_t* h_winner,
                      int8_t* h_mask, int32_t* h_action, int64_t* total_positions, float* elapsed_ms) {
+    NvtxRange nvtx_range("sprl_env_rollout");
     if (ngames < 0) return fail(SPRL_E_INVALID, "negative game count");
     if (h_cells && (!h_player || !h_terminal || !h_winner || !h_mask || !h_action))
         return fail(SPRL_E_INVALID, "sprl_env_rollout: trace buffers must be given together");
@@ -483,6 +485,7 @@ int sprl_env_rollout(int device, int game, uint64_t seed, uint64_t first_game, i
 }
 
 int sprl_env_perft(int device, int game, int depth, uint64_t* count, float* elapsed_ms) {
+    NvtxRange nvtx_range("sprl_env_perft");
     if (!count) return fail(SPRL_E_INVALID, "null output");
     int rc = use_device(device);
     if (rc) return rc;

@@ -1185,6 +1185,7 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
 }
 
 int sprl_evalnet_update(sprl_evalnet* e, const sprl_network_params* params) {
+    NvtxRange nvtx_range("sprl_evalnet_update");
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     int rc = validate(params);
     if (rc) return rc;
@@ -1203,6 +1204,7 @@ int sprl_evalnet_forward(sprl_evalnet* e, const float* d_in, int64_t batch, floa
 
 int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint32_t* d_rows, int64_t batch, float* d_logits,
                                  float* d_value, void* cuda_stream) {
+    NvtxRange nvtx_range("sprl_evalnet_forward_counted");
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     if (batch < 0 || (batch > 0 && (!d_in || !d_logits || !d_value))) return fail(SPRL_E_INVALID, "bad argument to sprl_evalnet_forward");
     if (batch == 0) return SPRL_OK;

@@ -174,7 +174,10 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             proxy_fence();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lead_img) : "memory");
+            // release at CTA scope: what was written is this CTA's own image, read by this CTA's tensor core (the pair's MMA
+            // reads each tile from its own SM); the leader only learns that it may issue.  (A cluster-scope release costs a
+            // MEMBAR.ALL.GPU per arrival -- 12 % of the epilogue's busy samples in the first ncu capture.)
+            if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(lead_img) : "memory");
         };
         // leaf planes -> stem image channels: channel dyi * planes + p of a cell holds plane p of the cell one row
         // above / at / below it (the stem's vertical taps are folded into K, see k_evalnet)
@@ -184,7 +187,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
             for (int j = 0; j < KCH; ++j) {
                 const int ch = cg * KCH + j, dyi = ch / planes, p = ch - dyi * planes, rr = r + dyi - 1;
                 v[j] = (valid && dyi < 3 && rr >= 0 && rr < net.rows && board_ < batch)
-                           ? in[(board_ * planes + p) * cells + rr * net.cols + c] * ACT_SCALE : 0.0f;
+                           ? __ldg(in + (board_ * planes + p) * cells + rr * net.cols + c) : 0.0f;      // scaled at use: a prefetch must not wait for its data
             }
         };
         const int last_stage = ph.n_stages - 1;
@@ -201,9 +204,11 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                     float v[KCH];
                     if (cg == half) {
 #pragma unroll
-                        for (int j = 0; j < KCH; ++j) v[j] = vnext[j];
+                        for (int j = 0; j < KCH; ++j) v[j] = vnext[j] * ACT_SCALE;
                     } else {
                         load_planes(tile, cg, v);
+#pragma unroll
+                        for (int j = 0; j < KCH; ++j) v[j] *= ACT_SCALE;
                     }
                     uint4 h, l;
                     split8(v, h, l, mx);

@@ -18,6 +18,25 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda", 0)
 
+# ---- config 1: Connect Four through the reference's own CPU worker, as is (C4Worker.cpp:11-27), one core, next to the GPU engine below
+import subprocess
+import tempfile
+REF_WORKER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_worker")
+if os.path.exists(REF_WORKER) and not os.environ.get("SPRL_BENCH_NO_CPU"):
+    with tempfile.TemporaryDirectory() as tmp:
+        pt = os.path.join(tmp, "c4.pt")
+        trace_network(make_network("c4", 0), "cpu").save(pt)
+        # iteration-0 leg: RandomNetwork, 2,048 descents, batch 1 / queue 1; iteration-1 leg: the traced net, 512 descents, 8 / 4
+        for leg, model, sims, b, q in (("iteration0_uniform", "uniform", 2048, 1, 1), ("iteration1_traced_net", pt, 512, 8, 4)):
+            out = subprocess.run([REF_WORKER, "c4", model, "0", "0", str(sims), str(b), str(q), "0.25", "0.5", "10", "10"],
+                                 capture_output=True, text=True, check=True).stdout.strip().split("\n")[-1]
+            o = json.loads(out)
+            print(json.dumps({"config": "c4_reference_cpu_worker", "leg": leg, "cores": 1, "sims_per_move": sims, "batch_queue": [b, q],
+                              "games": o["games"], "moves_per_sec": round(o["moves"] / o["seconds"], 2),
+                              "sims_per_sec": round(o["sims"] / o["seconds"], 1), "window_seconds": round(o["seconds"], 1),
+                              "protocol": "one discarded warm-up game, then up to 10 full games through the reference's runIteration "
+                                          "(C4Worker.cpp constants) or 10 s, whichever ends first"}), flush=True)
+
 # ---- config 2: perft
 for d in (8, 9, 10, 11):
     count, ms = SP.env_perft(capi.GAME_OTHELLO, d)
