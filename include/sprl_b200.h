@@ -275,6 +275,11 @@ typedef struct {
 int sprl_get_stats(sprl_engine* e, sprl_stats* out);
 int sprl_reset_stats(sprl_engine* e);
 
+/* Debug aid (the reference has no race or bounds tooling): every device pool of the engine lies
+ * between two 256-byte guard bands; this synchronises the device and reports how many pools have a damaged band,
+ * i.e. were written out of bounds by a kernel. */
+int sprl_debug_check_guards(sprl_engine* e, int64_t* pools_checked, int64_t* pools_damaged);
+
 /* npy::write_npy (utils/npy.hpp:616-639) for float32 C-order data: byte-identical header. */
 int sprl_write_npy_f32(const char* path, const float* h_data, const uint64_t* shape, int ndim);
 

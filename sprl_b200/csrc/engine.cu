@@ -67,18 +67,25 @@ struct sprl_engine {
     sprl_stats base;
     std::vector<int> h_moves;
 
+    // Every pool sits between two 256-byte guard bands filled with a pattern (sprl_debug_check_guards): the kernels index
+    // their pools with tree-, queue- and game-relative offsets, and compute-sanitizer is not available on every box.
+    static constexpr size_t GUARD = 256;
+    struct Pool { unsigned char* base; size_t bytes; };
+    std::vector<Pool> pools;
     template <typename T> int alloc(T** out, size_t count, bool zero) {
         void* ptr = nullptr;
-        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-        cudaError_t err = cudaMalloc(&ptr, bytes);
+        size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+        cudaError_t err = cudaMalloc(&ptr, bytes + 2 * GUARD);
         if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
-        if (zero) {
-            err = cudaMemset(ptr, 0, bytes);
-            if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaMemset: %s", cudaGetErrorString(err));
-        }
+        unsigned char* base = (unsigned char*)ptr;
+        err = cudaMemset(base, 0xA5, GUARD);
+        if (err == cudaSuccess) err = cudaMemset(base + GUARD + bytes, 0xA5, GUARD);
+        if (err == cudaSuccess && zero) err = cudaMemset(base + GUARD, 0, bytes);
+        if (err != cudaSuccess) return fail(SPRL_E_CUDA, "cudaMemset: %s", cudaGetErrorString(err));
         allocations.push_back(ptr);
-        device_bytes += bytes;
-        *out = (T*)ptr;
+        pools.push_back(Pool{ base, bytes });
+        device_bytes += bytes + 2 * GUARD;
+        *out = (T*)(base + GUARD);
         return SPRL_OK;
     }
     void free_all() {
@@ -864,6 +871,23 @@ int sprl_advance(sprl_engine* e, const int32_t* h_actions, int64_t n_actions) {
     ENGINE_CUDA(e, cudaMemcpyAsync(c, e->p.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
     ENGINE_CUDA(e, cudaStreamSynchronize(e->stream));
     if (c[1] > 0) return report_slot_failure(e);
+    return SPRL_OK;
+}
+
+int sprl_debug_check_guards(sprl_engine* e, int64_t* pools_checked, int64_t* pools_damaged) {
+    ENGINE_CHECK(e);
+    ENGINE_CUDA(e, cudaDeviceSynchronize());
+    int64_t bad = 0;
+    std::vector<unsigned char> g(2 * sprl_engine::GUARD);
+    for (const sprl_engine::Pool& pl : e->pools) {
+        ENGINE_CUDA(e, cudaMemcpy(g.data(), pl.base, sprl_engine::GUARD, cudaMemcpyDeviceToHost));
+        ENGINE_CUDA(e, cudaMemcpy(g.data() + sprl_engine::GUARD, pl.base + sprl_engine::GUARD + pl.bytes, sprl_engine::GUARD, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        for (unsigned char c : g) ok = ok && c == 0xA5;
+        if (!ok) ++bad;
+    }
+    if (pools_checked) *pools_checked = (int64_t)e->pools.size();
+    if (pools_damaged) *pools_damaged = bad;
     return SPRL_OK;
 }
 

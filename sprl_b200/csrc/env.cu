@@ -82,6 +82,13 @@ struct LineHist {
         }
         return false;
     }
+    template <class F> __host__ __device__ void for_each(F&& f) const {
+        for (int i = 0; i < count; ++i) {
+            Bits<W> b0, b1;
+            for (int w = 0; w < W; ++w) { b0.set_word(w, data[(size_t)i * 2 * W + w]); b1.set_word(w, data[(size_t)i * 2 * W + W + w]); }
+            f(b0, b1);
+        }
+    }
 };
 
 // ---- batched single transitions ----------------------------------------------------
@@ -171,6 +178,18 @@ struct PerftHist {
             if (same) return true;
         }
         return false;
+    }
+    template <class F> __device__ void for_each(F&& f) const {
+        int d = depth;
+        u32 idx = index;
+        while (d > 0) {
+            idx = lv->level[d][idx].parent;
+            --d;
+            const PosRec& r = lv->level[d][idx];
+            Bits<W> b0, b1;
+            for (int w = 0; w < W; ++w) { b0.set_word(w, r.b[w]); b1.set_word(w, r.b[2 + w]); }
+            f(b0, b1);
+        }
     }
 };
 

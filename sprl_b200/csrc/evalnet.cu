@@ -1020,8 +1020,9 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     // ---- resident format: phases of [stem] [conv, conv] [heads] stages, as many per launch as shared memory holds
     std::vector<RbPhase> phases;
     std::vector<unsigned short> rbw;
-    if (p->rows <= 8 && p->cols <= 8) {
-        const int budget = RB_MAX_SMEM - RB_OFF_W - RB_MAX_STAGES * CH * 4 - 64 - 16;
+    {
+        const bool linear = p->rows > 8 || p->cols > 8;
+        const int budget = RB_MAX_SMEM - RB_OFF_W - RB_MAX_STAGES * CH * 4 - 64 - 16 - (linear ? RB_XCH_BYTES : 0);
         std::vector<std::vector<RbStage>> plan(1);
         std::vector<int> plan_bytes(1, 0);
         auto add_group = [&](std::vector<RbStage> group) {
@@ -1173,7 +1174,8 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     if (getenv("SPRL_EVALNET_PATH")) e->path = atoi(getenv("SPRL_EVALNET_PATH"));      // experiments: 1 streaming, 2 resident
     err = cudaFuncSetAttribute(k_evalnet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX_SMEM);
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
     if (heads_smem_bytes(params->policy_channels, params->rows * params->cols) > 227 * 1024) { delete e; return fail(SPRL_E_INVALID, "head layers of %d channels x %d cells do not fit k_heads' shared memory", params->policy_channels, params->rows * params->cols); }
     err = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // the attribute is per process: always the maximum, whatever this evaluator's board
@@ -1246,14 +1248,15 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(RB_THREADS);
-            cfg.dynamicSmemBytes = (size_t)rb_smem_bytes(ph);
+            cfg.dynamicSmemBytes = (size_t)rb_smem_bytes(ph, e->dev.linear != 0);
             cfg.stream = (cudaStream_t)cuda_stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            err = cudaLaunchKernelEx(&cfg, k_evalnet_resident, e->dev, ph, d_in, (long long)batch, (const unsigned*)d_rows);
+            err = e->dev.linear ? cudaLaunchKernelEx(&cfg, k_evalnet_resident<true>, e->dev, ph, d_in, (long long)batch, (const unsigned*)d_rows)
+                                : cudaLaunchKernelEx(&cfg, k_evalnet_resident<false>, e->dev, ph, d_in, (long long)batch, (const unsigned*)d_rows);
             e->launches += 1;
             if (err == cudaSuccess) err = cudaGetLastError();
             if (err != cudaSuccess) break;
@@ -1312,7 +1315,13 @@ int sprl_evalnet_info(sprl_evalnet* e, int64_t* upload_bytes, int32_t* ring_stag
     if (!e) return fail(SPRL_E_INVALID, "null evaluator");
     if (upload_bytes) *upload_bytes = e->upload_bytes;
     if (ring_stages) *ring_stages = e->dev.nst;
-    if (smem_bytes) *smem_bytes = smem_bytes_for(e->dev.n_layers, e->dev.nst);
+    if (smem_bytes) {
+        *smem_bytes = smem_bytes_for(e->dev.n_layers, e->dev.nst);
+        if (!e->phases.empty() && e->path != SPRL_EVALNET_PATH_STREAMING) {      // the resident kernel: its largest phase
+            *smem_bytes = 0;
+            for (const RbPhase& ph : e->phases) *smem_bytes = std::max(*smem_bytes, rb_smem_bytes(ph, e->dev.linear != 0));
+        }
+    }
     return SPRL_OK;
 }
 

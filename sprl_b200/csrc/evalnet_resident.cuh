@@ -58,12 +58,16 @@ struct RbPhase {
     float* act;                  // [tiles][16 channel quads][128 cells][4]: activations between phases, image units, in place
     int index;                   // position of the phase in the forward (timing slots)
 };
-__host__ __device__ inline int rb_smem_bytes(const RbPhase& ph) { return RB_OFF_W + ph.w_bytes + ph.n_stages * CH * 4 + 64 + 16; }
+// linear lattice (boards wider than 8, one per tile): Z_-1 / Z_+1 of a warp's edge lanes for its neighbour warps,
+// [stream][channel half][double buffer][warp of the quarter][left | right][16 values]
+constexpr int RB_XCH_BYTES = RB_STREAMS * 2 * 2 * 4 * 2 * 16 * 4;
+__host__ __device__ inline int rb_smem_bytes(const RbPhase& ph, bool linear) { return RB_OFF_W + ph.w_bytes + ph.n_stages * CH * 4 + 64 + 16 + (linear ? RB_XCH_BYTES : 0); }
 __host__ __device__ inline int rb_stage_ndy(int kind) { return kind == RB_CONV ? 3 : 1; }
 __host__ __device__ inline int rb_stage_n1(int kind) { return kind == RB_HEADS ? HEAD_N : 3 * CH; }
 // bytes of a stage's weights held by ONE CTA of the pair: [dy][k chunk of 8][hi rows | lo rows of this CTA][8 halfs]
 __host__ __device__ inline int rb_stage_bytes(int kind, int ksteps) { return rb_stage_ndy(kind) * ksteps * 2 * rb_stage_n1(kind) * 16; }
 
+template <bool LINEAR>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long long batch, const unsigned* __restrict__ d_rows) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -76,7 +80,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                                                      //     are drained in BOTH CTAs (one arrival per epilogue warp of the pair)
     const uint32_t bar_w = bar_img + 16;             // this CTA's resident weights have landed
     float* s_bias = reinterpret_cast<float*>(smem + off_bias);
-    const long long n_tiles = (batch + 1) / 2, n_quads = (n_tiles + 3) / 4;      // a pair takes 4 tiles (2 streams x 2 CTAs) per turn
+    const long long n_tiles = LINEAR ? batch : (batch + 1) / 2, n_quads = (n_tiles + 3) / 4;      // a pair takes 4 tiles (2 streams x 2 CTAs) per turn
     const uint32_t crank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
@@ -132,7 +136,8 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                         const uint32_t d_tmem = tmem + (uint32_t)(s * RB_STREAM_COLS);
                         uint32_t acc = 0;                                        // 0 for the stage's very first MMA only
                         for (int t = 0; t < ndy; ++t) {
-                            const uint32_t a_off = (uint32_t)(16 + 16 * (ndy == 3 ? t - 1 : 0));   // 16-byte slots: two storage rows per board row
+                            // 16-byte slots: two storage rows per board row, or one row of `cols` cells in the linear lattice
+                            const uint32_t a_off = (uint32_t)(16 + (LINEAR ? net.cols : 16) * (ndy == 3 ? t - 1 : 0));
                             const uint64_t bt = b0 + (uint32_t)(t * S.ksteps) * b_kstep;
 #pragma unroll 2
                             for (int ks = 0; ks < S.ksteps; ++ks) {
@@ -157,9 +162,14 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         const int half = w8 >> 2;                                    // which half of the channels this warp finishes
         const int slot = cell_slot(m);
         const int g8 = m >> 3;
-        const int r = g8 >> 1, c = m & 7, b = g8 & 1;
+        const int r = LINEAR ? m / net.cols : g8 >> 1, c = LINEAR ? m - r * net.cols : m & 7, b = LINEAR ? 0 : g8 & 1;
         const bool valid = r < net.rows && c < net.cols;             // lattice positions outside the board stay zero
         const int cell = r * net.cols + c;
+        // linear lattice: the left / right neighbour of lane 0 / 31 lives in another warp of the same stream and channel half
+        const int wq = w8 & 3;
+        float* xch = reinterpret_cast<float*>(smem + off_tmem + 16) + (s * 2 + half) * (2 * 4 * 2 * 16);
+        const bool xl = LINEAR && lane == 0 && wq > 0, xr = LINEAR && lane == 31 && wq < 3;
+        uint32_t xbuf = 0;
         const uint32_t t_lane = tmem + (uint32_t)(s * RB_STREAM_COLS) + ((uint32_t)((w8 & 3) * 32) << 16);
         uint4* a_hi = reinterpret_cast<uint4*>(smem + (2 * s) * RB_IMG_BYTES);
         uint4* a_lo = reinterpret_cast<uint4*>(smem + (2 * s + 1) * RB_IMG_BYTES);
@@ -182,7 +192,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         // leaf planes -> stem image channels: channel dyi * planes + p of a cell holds plane p of the cell one row
         // above / at / below it (the stem's vertical taps are folded into K, see k_evalnet)
         auto load_planes = [&](long long tile_, int cg, float* v) {
-            const long long board_ = tile_ * 2 + b;
+            const long long board_ = LINEAR ? tile_ : tile_ * 2 + b;
 #pragma unroll
             for (int j = 0; j < KCH; ++j) {
                 const int ch = cg * KCH + j, dyi = ch / planes, p = ch - dyi * planes, rr = r + dyi - 1;
@@ -193,11 +203,12 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         const int last_stage = ph.n_stages - 1;
         const long long quad_step = 4LL * n_pairs;
         const long long tile0 = (long long)pair * 4 + s * 2 + crank;
+        const int xbar = 1 + s * 2 + half;                           // named barrier of this stream's channel half (4 warps)
         float vnext[KCH];
         if (ph.in_planes_mode) load_planes(tile0, half, vnext);
         mbar_wait(bar_w, 0u, net.error_flag, 20);                   // (the leader's MMAs read both CTAs' weights: every arrival below implies them)
         for (long long tile = tile0; tile < n_quads * 4; tile += quad_step) {
-            const long long board = tile * 2 + b;
+            const long long board = LINEAR ? tile : tile * 2 + b;
             // ---- input stage ----
             if (ph.in_planes_mode) {
                 for (int cg = half; cg < 2 * ph.st[0].ksteps; cg += 2) {
@@ -261,11 +272,28 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                         // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = accumulator columns [dx*64, dx*64+64)
                         float o[16], v[16], w[16];
                         tmem_ld16x3(t_lane + CH + q * 16, t_lane + q * 16, t_lane + 2 * CH + q * 16, o, v, w);   // dx = 0, -1, +1
+                        if (LINEAR) {
+                            // publish what the neighbouring warps need: lane 31's Z_-1 (for the next warp's lane 0) and lane 0's
+                            // Z_+1 (for the previous warp's lane 31); double-buffered per iteration
+                            float* mine = xch + (xbuf * 4 + wq) * 32;
+                            if (lane == 31) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) mine[i] = v[i];
+                            }
+                            if (lane == 0) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) mine[16 + i] = w[i];
+                            }
+                            named_bar(xbar, 128);
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                            float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                            if (xl) zl = xch[(xbuf * 4 + wq - 1) * 32 + i];
+                            if (xr) zr = xch[(xbuf * 4 + wq + 1) * 32 + 16 + i];
                             o[i] = fmaf(zl, lmask, fmaf(zr, rmask, o[i]));
                         }
+                        xbuf ^= 1u;
                         if (S.add_res) {                                                             // block input (image units), kept in TMEM
                             tmem_ld16(t_lane + RES_COL + q * 16, v);
 #pragma unroll

@@ -151,8 +151,19 @@ struct Pos {
 
 // History oracle handed to Game::next for rules that look at earlier positions
 // (Go's positional superko).  Games without such rules ignore it.
+// A history type answers seen(b0, b1) and enumerates its boards with for_each(f), f(b0, b1) -> void.
 struct NoHistory {
     template <int W> __host__ __device__ bool seen(const Bits<W>&, const Bits<W>&) const { return false; }
+    template <class F> __host__ __device__ void for_each(F&&) const {}
+};
+
+// a history with one more board in front of it
+template <class Hist, int W>
+struct HistPlus {
+    const Hist& h;
+    Bits<W> s0, s1;
+    __host__ __device__ bool seen(const Bits<W>& a, const Bits<W>& b) const { return (a == s0 && b == s1) || h.seen(a, b); }
+    template <class F> __host__ __device__ void for_each(F&& f) const { f(s0, s1); h.for_each(f); }
 };
 
 // ---- Othello (games/OthelloNode.cpp) ---------------------------------------------
@@ -431,6 +442,62 @@ struct Go {
         return player == 0 ? !hist.seen(o, e) : !hist.seen(e, o);
     }
 
+    // The legal placements of the side to move, all at once (the same rule as legal_at, cell by cell):
+    //   * a point that captures (it is the last liberty of an adjacent opponent group) never is suicide; its new board
+    //     depends on the capture, so the superko test is the full one (legal_at) -- few points, rarely;
+    //   * any other empty point p is no suicide iff it has an empty neighbour or touches an own group that keeps a
+    //     liberty besides p (a group with at least two liberties); its new board is the current one plus the stone, so
+    //     it repeats an earlier board h exactly when h has the same opponent stones and the own stones plus ONE more:
+    //     one pass over the history instead of one per point.
+    // `groups(own)`: a callback that, for a colour's stones, ORs the liberties of its groups with >= 2 liberties into
+    // `multi` and the single liberties of its groups in atari into `atari` -- serial here, lane-parallel in the search.
+    template <class Hist>
+    __host__ __device__ static B legal_from_groups(const B& own, const B& opp, int player, const Masks& m, const Hist& hist,
+                                                   const B& own_multi, const B& opp_atari) {
+        const B empty = m.all & ~(own | opp);
+        const B open = neighbors(empty, m.not_col0, m.not_colN, m.all);           // points with an empty neighbour
+        const B capturing = empty & opp_atari;
+        B plain = empty & ~capturing & (open | own_multi);
+        if (plain.any()) {
+            B repeats;
+            hist.for_each([&](const B& h0, const B& h1) {
+                const B& ho = player == 0 ? h0 : h1;
+                const B& he = player == 0 ? h1 : h0;
+                if (he == opp && (ho & own) == own) {
+                    const B extra = ho ^ own;
+                    if (extra.count() == 1) repeats = repeats | extra;
+                }
+            });
+            plain = plain & ~repeats;
+        }
+        B legal = plain;
+        for (B rest = capturing; rest.any();) {
+            const int c = rest.lowest();
+            rest = rest & ~B::bit(c);
+            if (legal_at(own, opp, player, c, m, hist)) legal = legal | B::bit(c);
+        }
+        return legal;
+    }
+    // liberties of the groups of `stones`: >= 2 liberties -> multi, exactly one -> atari (`from`: the stones to start floods from)
+    __host__ __device__ static void group_liberties(const B& from, const B& stones, const B& empty, const Masks& m, B& multi, B& atari) {
+        for (B rest = from; rest.any();) {
+            const B g = flood(B::bit(rest.lowest()), stones, m);
+            const B libs = neighbors(g, m.not_col0, m.not_colN, m.all) & empty;
+            const int n = libs.count();
+            if (n >= 2) multi = multi | libs;
+            else if (n == 1) atari = atari | libs;
+            rest = rest & ~g;
+        }
+    }
+    template <class Hist>
+    __host__ __device__ static B legal_mask(const B& own, const B& opp, int player, const Masks& m, const Hist& hist) {
+        const B empty = m.all & ~(own | opp);
+        B own_multi, own_atari, opp_multi, opp_atari;
+        group_liberties(own, own, empty, m, own_multi, own_atari);
+        group_liberties(opp, opp, empty, m, opp_multi, opp_atari);
+        return legal_from_groups(own, opp, player, m, hist, own_multi, opp_atari);
+    }
+
     // Tromp-Taylor area count (countTerritory, games/GoNode.cpp:230-290)
     __host__ __device__ static void score(const B& b0, const B& b1, const Masks& m, int terr[2]) {
         terr[0] = b0.count(); terr[1] = b1.count();
@@ -489,19 +556,10 @@ struct Go {
         next_board<Hist>(par, action, p);
         if (p.terminal) return;
         const Masks m = masks();
-        B legal;
-        struct WithSelf {
-            const Hist& h; B s0, s1;
-            __host__ __device__ bool seen(const B& a, const B& b) const { return (a == s0 && b == s1) || h.seen(a, b); }
-        } hs = { hist, p.b[0], p.b[1] };
-        // the parent's board is an ancestor of the new node as well
-        struct WithPar {
-            const WithSelf& h; B s0, s1;
-            __host__ __device__ bool seen(const B& a, const B& b) const { return (a == s0 && b == s1) || h.seen(a, b); }
-        } hp = { hs, par.b[0], par.b[1] };
-        for (int c = 0; c < CELLS; ++c)
-            if (legal_at(p.b[p.player], p.b[1 - p.player], p.player, c, m, hp)) legal = legal | B::bit(c);
-        p.legal = legal;
+        // the new node's own board and the parent's are ancestors of the new node's children as well
+        const HistPlus<Hist, W> hs = { hist, p.b[0], p.b[1] };
+        const HistPlus<HistPlus<Hist, W>, W> hp = { hs, par.b[0], par.b[1] };
+        p.legal = legal_mask(p.b[p.player], p.b[1 - p.player], p.player, m, hp);
     }
 };
 

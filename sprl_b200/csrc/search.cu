@@ -215,6 +215,24 @@ struct TreeWarp {
             }
             return false;
         }
+        template <class F> __device__ void for_each(F&& f) const {
+            u32 cur = start;
+            for (;;) {
+                Bits<W> b0, b1;
+                HL<W>::load_boards(t->slab + cur, b0, b1);
+                f(b0, b1);
+                if (cur == ROOT_UNIT) break;
+                u32 par, own;
+                HL<W>::load_links(t->slab + cur, par, own);
+                cur = par;
+            }
+            const unsigned long long* rb = t->p.rec_board + (size_t)t->st.game_index * t->p.max_moves * 2 * W;
+            for (int mv = t->st.move_count - 1; mv >= 0; --mv) {
+                Bits<W> b0, b1;
+                for (int w = 0; w < W; ++w) { b0.set_word(w, rb[(size_t)mv * 2 * W + w]); b1.set_word(w, rb[(size_t)mv * 2 * W + W + w]); }
+                f(b0, b1);
+            }
+        }
     };
 
     // boards of the position `t` plies above `unit` (0 = itself); false when the game is younger
@@ -238,27 +256,41 @@ struct TreeWarp {
         if constexpr (G::KIND == GAME_GO7 || G::KIND == GAME_GO9) {
             G::template next_board<NoHistory>(par, action, child);
             if (!child.terminal) {
-                // legality of every empty point for the side to move, one lane per cell;
-                // superko compares against the new board itself, `par` and everything above it
+                // Legal placements of the new position (checkLegalPlacement, games/GoNode.cpp:178-228) for all points at once
+                // (Go::legal_from_groups).  The group scan is spread over the warp: every lane floods the groups of its own
+                // cells and the liberty sets are OR-ed across the lanes; the rest is warp-uniform.  Superko compares against
+                // the new board itself, `par` and everything above it.
                 const typename G::Masks m = G::masks();
-                struct Hist {
-                    TreeHist th; Bits<W> s0, s1;
-                    __device__ bool seen(const Bits<W>& a, const Bits<W>& b) const { return (a == s0 && b == s1) || th.seen(a, b); }
-                } hist = { { this, par_unit }, child.b[0], child.b[1] };
-                Bits<W> legal;
+                const Bits<W> own = child.b[child.player], opp = child.b[1 - child.player], empty = m.all & ~(own | opp);
+                Bits<W> own_multi, own_atari, opp_multi, opp_atari;
                 for (int base = 0; base < G::CELLS; base += 32) {
-                    int c = base + lane;
-                    bool ok = c < G::CELLS && G::legal_at(child.b[child.player], child.b[1 - child.player], child.player, c, m, hist);
-                    u32 bal = __ballot_sync(FULL, ok);
-                    legal = legal | from_ballot(bal, base);
+                    const int c = base + lane;
+                    if (c < G::CELLS) {
+                        if (own.test(c)) G::group_liberties(Bits<W>::bit(c), own, empty, m, own_multi, own_atari);
+                        else if (opp.test(c)) G::group_liberties(Bits<W>::bit(c), opp, empty, m, opp_multi, opp_atari);
+                    }
                 }
-                child.legal = legal;
+                own_multi = warp_or(own_multi);
+                opp_atari = warp_or(opp_atari);
+                const TreeHist th = { this, par_unit };
+                const HistPlus<TreeHist, W> hist = { th, child.b[0], child.b[1] };
+                child.legal = G::legal_from_groups(own, opp, child.player, m, hist, own_multi, opp_atari);
             }
         } else if constexpr (G::KIND == GAME_OTHELLO) {
             G::next_warp(par, action, lane, child);          // called by the whole warp with uniform arguments
         } else {
             G::next(par, action, NoHistory(), child);
         }
+    }
+    // OR of a bit set over the lanes of the warp
+    __device__ static Bits<W> warp_or(const Bits<W>& x) {
+        Bits<W> r;
+        for (int w = 0; w < W; ++w) {
+            const u64 v = x.word(w);
+            const u32 lo = __reduce_or_sync(FULL, (u32)v), hi = __reduce_or_sync(FULL, (u32)(v >> 32));
+            r.set_word(w, (u64)lo | ((u64)hi << 32));
+        }
+        return r;
     }
     // 32 cells [base, base+32) of a bit set, from a warp ballot
     __device__ static Bits<W> from_ballot(u32 bal, int base) {

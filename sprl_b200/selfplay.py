@@ -136,6 +136,12 @@ class Engine:
         capi.check(self.lib.sprl_get_stats(self.handle, C.byref(s)))
         return s.as_dict()
 
+    def check_guards(self):
+        """(pools checked, pools whose guard bands were overwritten): out-of-bounds writes of the kernels."""
+        n, bad = C.c_int64(), C.c_int64()
+        capi.check(self.lib.sprl_debug_check_guards(self.handle, C.byref(n), C.byref(bad)))
+        return n.value, bad.value
+
     def reset_stats(self):
         capi.check(self.lib.sprl_reset_stats(self.handle))
 

@@ -20,6 +20,9 @@ struct VecHist {
         for (size_t i = 0; i < b0->size(); ++i) if ((*b0)[i] == x0 && (*b1)[i] == x1) return true;
         return false;
     }
+    template <class F> void for_each(F&& f) const {
+        for (size_t i = 0; i < b0->size(); ++i) f((*b0)[i], (*b1)[i]);
+    }
 };
 
 template <class G>

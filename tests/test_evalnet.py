@@ -94,10 +94,11 @@ def test_evalnet_smaller_boards(kind, rows, cols, batch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,rows,cols,batch,phases", [("othello", 8, 8, 4099, 2), ("othello", 8, 8, 5, 2), ("c4", 6, 7, 1031, 2),
-                                                         ("go7", 7, 7, 300, 7)])
+                                                         ("go7", 7, 7, 300, 7), ("go9", 9, 9, 203, 7)])
 def test_resident_and_streaming_kernels_agree_bit_for_bit(kind, rows, cols, batch, phases):
     """The resident-weight kernel (CTA pairs, one launch per residual block, activations through HBM) accumulates
-    every output in the same order as the streaming kernel: identical bits, for every batch size and row."""
+    every output in the same order as the streaming kernel: identical bits, for every batch size and row -- two boards per
+    tile on the 8x8 lattice, one on the linear lattice (Go 9x9)."""
     net = randomized(make_network(kind, 2), 6)
     x = (torch.rand(batch, net.conv.in_channels, rows, cols) > 0.5).float().cuda()
     ev = EvalNet(net, device=0, rows=rows, cols=cols)
@@ -111,15 +112,6 @@ def test_resident_and_streaming_kernels_agree_bit_for_bit(kind, rows, cols, batc
     ev.status()
     assert torch.equal(l_res, l_str) and torch.equal(v_res, v_str)
     assert torch.equal(l_again, l_res[: batch // 2 + 1]) and torch.equal(v_again, v_res[: batch // 2 + 1])
-    ev.close()
-
-
-@pytest.mark.gpu
-def test_go9_keeps_the_streaming_kernel():
-    ev = EvalNet(make_network("go9", 0), device=0, rows=9, cols=9)
-    assert ev.phases == 0
-    with pytest.raises(capi.SprlError):
-        ev.set_path(capi.EVALNET_PATH_RESIDENT)
     ev.close()
 
 

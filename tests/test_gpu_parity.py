@@ -110,6 +110,8 @@ def run_engine(game, evaluator, seed, first_game, ngames, sims, b, q, eps, alpha
                    max_games=ngames, record_stats=1, **kw) as eng:
         states, dists, outcomes = eng.run_iteration(ngames, first_game=first_game)
         got = eng.move_stats(ngames)
+        pools, damaged = eng.check_guards()            # no kernel wrote outside its pools (every parity run checks)
+        assert pools > 20 and damaged == 0
         got.update(states=states, distributions=dists, outcomes=outcomes, stats=eng.stats())
     return got
 
@@ -245,6 +247,7 @@ def test_external_evaluator_bit_exact(game, sims, b, q, alpha, ngames, graph):
         got = eng.move_stats(ngames)
         got.update(states=states, distributions=dists, outcomes=outcomes)
         st = eng.stats()
+        assert eng.check_guards()[1] == 0
     assert net.calls > 0
     compare_selfplay(ref, got)
     assert st["sims"] == ref["stats"]["total_traversals"] and st["evals"] == ref["stats"]["total_evals"]
