@@ -32,6 +32,26 @@ sys.path.insert(0, ROOT)
 SIMS, MAX_BATCH, MAX_QUEUE, EPS, ALPHA = 400, 8, 4, 0.25, 0.3
 WORKLOAD = "othello8x8_selfplay_400sims_batch8_queue4_d4sym_net2x64_fp32"
 NET_FLOP_PER_LEAF = 2 * (64 * 27 * 64 + 4 * 64 * 64 * 9 * 64 + 3 * 64 * 64 + 128 * 65 + 64 * 64 + 64)   # 19.1 MFLOP
+NET_KIND, GAME_NAME, BOARD, PLANES, ACTIONS, METRIC, MAX_PLIES = "othello", "GAME_OTHELLO", (8, 8), 3, 65, "othello_selfplay_mcts_sims_per_sec", 66
+
+
+def net_flop_per_leaf(rows, cols, planes, blocks, actions, ch=64):
+    cells = rows * cols
+    return 2 * (ch * 9 * planes * cells + 2 * blocks * ch * ch * 9 * cells + 3 * ch * cells + 2 * cells * actions + cells * ch + ch)
+
+
+def select_workload(name):
+    """BASELINE.json's headline configuration (default) or config 5 (Go 9x9: GoWorker.cpp:12-27 constants -- alpha 0.2,
+    batch 16 / queue 8 -- with 400 sims/move, the reference's 6-block network shape, subtree reuse and Dirichlet noise on)."""
+    global SIMS, MAX_BATCH, MAX_QUEUE, EPS, ALPHA, WORKLOAD, NET_FLOP_PER_LEAF, NET_KIND, GAME_NAME, BOARD, PLANES, ACTIONS, METRIC, MAX_PLIES
+    if name == "othello":
+        return
+    if name != "go9":
+        raise SystemExit(f"unknown workload {name}")
+    SIMS, MAX_BATCH, MAX_QUEUE, EPS, ALPHA = 400, 16, 8, 0.25, 0.2
+    WORKLOAD = "go9x9_selfplay_400sims_batch16_queue8_d4sym_net6x64_fp32_komi7.5"
+    NET_KIND, GAME_NAME, BOARD, PLANES, ACTIONS, METRIC, MAX_PLIES = "go9", "GAME_GO9", (9, 9), 17, 82, "go9_selfplay_mcts_sims_per_sec", 163
+    NET_FLOP_PER_LEAF = net_flop_per_leaf(9, 9, 17, 6, 82)
 
 
 def parse():
@@ -40,6 +60,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="othello", choices=["othello", "go9"], help="othello = BASELINE.json's headline configuration; go9 = its config 5")
     ap.add_argument("--slots", type=int, default=16384, help="concurrent games per GPU")
     ap.add_argument("--rounds", type=int, default=256, help="search rounds per step")
     ap.add_argument("--e2e-games", type=int, default=16384, help="games per e2e step per GPU")
@@ -54,7 +75,15 @@ def parse():
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="timed window of the cpu_baseline leg (one core), seconds")
     ap.add_argument("--ref-window", type=float, default=60.0, help="timed window of --impl reference (every core), seconds")
     ap.add_argument("--ref-test-sims", type=int, default=0, help="smoke tests only: sims/move of the reference worker")
-    return ap.parse_args()
+    args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload == "go9":          # smaller defaults: a Go 9x9 tree slab is 6.5 MB, a sample row 5.8 KB
+        if args.slots == 16384:
+            args.slots = 4096
+        if args.e2e_games == 16384:
+            args.e2e_games, args.e2e_slots = 1024, 1024
+        args.no_cpu_baseline = True     # the reference arm exists for the headline workload (and Connect Four, tools/bench_configs.py)
+    return args
 
 
 # ------------------------------------------------------------------------ clocks sampler
@@ -138,14 +167,14 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- the evaluator: the reference's network shape, random init, traced as the controller does
-    net = make_network("othello", seed=0)
+    net = make_network(NET_KIND, seed=0)
     n_params = num_parameters(net)
     module = trace_network(net, dev)
     flat_params = [p for p in module.parameters()] + [b for b in module.buffers()]
     weight_bytes = sum(t.numel() * t.element_size() for t in flat_params)
 
     from sprl_b200.evalnet import EvalNet
-    evalnet = EvalNet(net, device=local) if args.evaluator == "evalnet" else None
+    evalnet = EvalNet(net, device=local, rows=BOARD[0], cols=BOARD[1]) if args.evaluator == "evalnet" else None
 
     def attach(engine):
         if evalnet is not None:
@@ -157,7 +186,7 @@ def run_ours(args):
         """New generation: rank 0 draws fresh random-init weights, NCCL broadcasts the flat
         parameter + buffer vector; every rank updates its module in place."""
         if rank == 0:
-            fresh = make_network("othello", seed=1000 + generation)
+            fresh = make_network(NET_KIND, seed=1000 + generation)
             src = [p for p in fresh.parameters()] + [b for b in fresh.buffers()]
             flat = torch.cat([t.detach().reshape(-1).float() for t in src]).to(dev)
         else:
@@ -176,16 +205,16 @@ def run_ours(args):
     # ---- evaluator accuracy on this box: ours vs the fp64 forward of the same network (CPU)
     eval_err = None
     if evalnet is not None and rank == 0:
-        xs = (torch.rand(512, 3, 8, 8) > 0.5).float()
+        xs = (torch.rand(512, PLANES, *BOARD) > 0.5).float()
         with torch.no_grad():
-            want = make_network("othello", seed=0).double()(xs.double())[0]
+            want = make_network(NET_KIND, seed=0).double()(xs.double())[0]
             got = evalnet(xs.to(dev))[0].cpu().double()
         eval_err = float((got - want).abs().max())
         assert eval_err < 1e-4, f"evaluator deviates from the fp64 forward by {eval_err}"
 
     # ---- steady-state engine: continuous play, games sharded by id % world
     games_cap = args.slots * 24
-    eng = SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=0, sims=SIMS, max_batch=MAX_BATCH,
+    eng = SP.Engine(getattr(capi, GAME_NAME), capi.EVAL_EXTERNAL, device=local, seed=0, sims=SIMS, max_batch=MAX_BATCH,
                     max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=args.slots, max_games=games_cap)
     eng.set_game_stride(world)
     attach(eng)
@@ -253,7 +282,7 @@ def run_ours(args):
     D = pst["depth_sum"] / max(1, pst["sims"])
     L = pst["legal_sum"] / max(1, pst["nodes_visited"])
     ef = pst["evals"] / max(1, pst["sims"])
-    bps = bytes_per_sim(D, L, ef)
+    bps = bytes_per_sim(D, L, ef, planes_cells=PLANES * BOARD[0] * BOARD[1], A=ACTIONS)
     sims_per_launch = pst["sims"] / n_probe
     peaks = {}
     try:
@@ -274,7 +303,7 @@ def run_ours(args):
         return t["dram_bytes_per_launch"] if t and t.get("slots") == args.slots else None
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bps * sims_per_launch / (k_ms / 1e3) / 1e9
-    roofline_search = {"kernel": "k_round<Othello>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+    roofline_search = {"kernel": "k_round<%s>" % ("Othello" if NET_KIND == "othello" else "Go<9>"), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                        "frac": round(achieved / peak, 5), "traffic": traffic_of("k_round"), "peak_source": peak_src,
                        "algorithmic_bytes_per_launch": round(bps * sims_per_launch, 1),
                        "launch_ms": round(k_ms, 4), "sims_per_launch": round(sims_per_launch, 1), "bytes_per_sim": round(bps, 1),
@@ -299,7 +328,7 @@ def run_ours(args):
     else:
         roofline = dict(roofline_search, network_forward_ms=round(nn_ms, 4))
     result = {
-        "metric": "othello_selfplay_mcts_sims_per_sec", "value": round(value, 1), "unit": "sims/s",
+        "metric": METRIC, "value": round(value, 1), "unit": "sims/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (tree statistics fp32; network split-fp16 x3 on tcgen05, fp32 accumulate, max |dlogit| ~1e-7 vs fp64)" if evalnet is not None else "fp32",
@@ -354,12 +383,12 @@ def run_e2e(args, local, module, flat_params, weight_bytes, barrier, evalnet, ra
     dev = torch.device("cuda", local)
     host_weights = [t.detach().cpu().pin_memory() for t in flat_params]
     G = args.e2e_games
-    with SP.Engine(capi.GAME_OTHELLO, capi.EVAL_EXTERNAL, device=local, seed=1, sims=SIMS, max_batch=MAX_BATCH,
+    with SP.Engine(getattr(capi, GAME_NAME), capi.EVAL_EXTERNAL, device=local, seed=1, sims=SIMS, max_batch=MAX_BATCH,
                    max_queue=MAX_QUEUE, dir_eps=EPS, dir_alpha=ALPHA, num_slots=min(G, args.e2e_slots), max_games=G) as eng:
         if not args.e2e_no_stream:
             # page-locked sample arrays, registered once (as a worker would keep them across iterations): finished games
             # are embedded and copied while the others play; an Othello game has at most 60 placements + passes
-            eng.stream_samples(G * 8 * 66)
+            eng.stream_samples(G * 8 * MAX_PLIES)
         if evalnet is not None:
             eng.attach_evalnet(evalnet, use_cuda_graph=not args.no_graph)
             host_state = {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
@@ -505,6 +534,9 @@ def run_reference(args):
     least 60); a step is 1/K of that window."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload != "othello":
+        emit({"impl": "reference", "unavailable": "the reference arm times the headline workload (Othello); Go 9x9 needs the two-constant reference copy with LibTorch"})
         return
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     m = cpu_baseline(args, threads, args.ref_window)

@@ -9,7 +9,7 @@ from sprl_b200.evalnet import EvalNet
 from sprl_b200.network import make_network
 
 kind = os.environ.get("KIND", "othello")
-shape = {"othello": (8, 8), "c4": (6, 7), "go7": (7, 7)}[kind]
+shape = {"othello": (8, 8), "c4": (6, 7), "go7": (7, 7), "go9": (9, 9)}[kind]
 net = make_network(kind, 0)
 planes = net.conv.in_channels
 ev = EvalNet(net, device=0, rows=shape[0], cols=shape[1])
