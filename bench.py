@@ -318,9 +318,10 @@ def run_ours(args):
         batch_rows = (pst["evals"] - pst["leaves_duplicate"]) / n_probe     # a leaf queued twice in a batch (quirk Q4) takes one row
         tf = batch_rows * NET_FLOP_PER_LEAF / (nn_ms / 1e3) / 1e12
         roofline = {"kernel": "k_evalnet_resident" if evalnet.phases else "k_evalnet", "launches_per_forward": max(1, evalnet.phases), "bound": "tensor", "achieved": round(tf, 2), "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": round(tf / tpeak, 5), "traffic": traffic_of("k_evalnet"), "peak_source": peak_src + " bf16 sustained",
+                    "frac": round(tf / tpeak, 5), "traffic": traffic_of("k_evalnet_resident" if evalnet.phases else "k_evalnet"), "peak_source": peak_src + " bf16 sustained",
                     "launch_ms": round(nn_ms, 4), "leaves_per_launch": round(batch_rows, 1), "leaf_batch_capacity": args.slots * MAX_QUEUE, "flop_per_leaf": NET_FLOP_PER_LEAF,
-                    "note": "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
+                    "note": "launch_ms = one forward = the conv tower (launches_per_forward launches of the kernel) + k_heads; "
+                            "achieved = algorithmic fp32 FLOPs / time against the measured bf16 peak; the kernel issues 3x that "
                             "as fp16 MMAs (hi/lo split of both operands: hi*hi + hi*lo + lo*hi, fp32 accumulate) to keep fp32-level "
                             "accuracy, so issued_frac is the tensor-pipe utilisation",
                     "issued_tflops": round(3 * tf, 1), "issued_frac": round(3 * tf / tpeak, 4),
