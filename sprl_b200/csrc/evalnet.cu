@@ -135,6 +135,7 @@ struct NetDev {
     const float* vfc1_wt;    // [64][64]        (value_fc1.weight transposed)
     const float* vfc1_b;     // [64]
     const float* vfc2_w;     // [64] weights, then the bias
+    const float* head_w;     // [4][64] fp32 weights of the 1x1 head convolutions (rows 0..pc-1 policy, row pc value, rest zero): k_evalnet_resident
     int n_layers;            // 1 stem + 2*blocks + 1 heads
     int rows, cols;          // board: cell (r, c) lives at lattice position (r, c) of an 8 x 8 tile half, or ...
     int linear;              // ... boards wider or taller than 8 (Go 9x9): ONE board per tile, cell r * cols + c = TMEM lane
@@ -147,6 +148,7 @@ struct NetDev {
     unsigned long long* error_flag;   // [0] pipeline barrier time-out, [1] an activation left the fp16-split range
     float inv_scale[MAX_LAYERS];      // 2^-(ACT_SHIFT + weight shift of the layer): accumulator -> real units
     long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
+    long long* trace;        // -DSPRL_EVALNET_TRACE builds: [phase][role: mma, epilogue X, epilogue Y][1 + 255 events] of CTA 0, clock << 12 | code
     int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue, 6 = MMAs but no conv epilogue
 };
 
@@ -370,6 +372,19 @@ __device__ __forceinline__ int cell_slot(int m) { return m + 16; }
 #define NOW() clock64()
 #else
 #define NOW() 0LL
+#endif
+// Event trace of one CTA pair's leader (resident kernel): every role keeps its events' count in a register and writes
+// (clock << 12 | stream << 8 | stage << 4 | kind) into its own region; dumped by sprl_evalnet_status.  kinds: 1 the MMA
+// warp may issue a stage (image barrier passed), 2 it has committed it, 3 the epilogue sees the accumulators, 4 it has
+// finished the stage (before its signal), 5 the next tile's input is written.
+#ifdef SPRL_EVALNET_TRACE
+#define TRACE_DECL(role) long long* trace_at = (net.trace && blockIdx.x == 0 && lane == 0) ? net.trace + ((long long)ph.index * 3 + (role)) * 256 : nullptr; int trace_n = 0;
+#define TRACE(s_, j_, kind_) do { if (trace_at && trace_n < 255) { trace_at[1 + trace_n] = (clock64() << 12) | ((long long)(s_) << 8) | ((long long)(j_) << 4) | (kind_); trace_n += 1; } } while (0)
+#define TRACE_END() do { if (trace_at) trace_at[0] = trace_n; } while (0)
+#else
+#define TRACE_DECL(role)
+#define TRACE(s_, j_, kind_) do { } while (0)
+#define TRACE_END() do { } while (0)
 #endif
 
 template <bool LINEAR>
@@ -1017,29 +1032,37 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
         append_units(units, bb, HEAD_N, C, shift);
         layers.push_back(LayerW{ std::move(bb), HEAD_N, C, shift });
     }
-    // ---- resident format: phases of [stem] [conv, conv] [heads] stages, as many per launch as shared memory holds
+    // ---- resident format: phases of [stem] [conv, conv] stage groups, as many per launch as shared memory holds; the
+    // head convolutions ride on the network's last conv stage
     std::vector<RbPhase> phases;
     std::vector<unsigned short> rbw;
+    std::vector<float> head_w(4 * (size_t)C, 0.0f);
+    for (int j = 0; j <= p->policy_channels && j < 4; ++j)
+        for (int ci = 0; ci < C; ++ci) head_w[(size_t)j * C + ci] = layers[L - 1].b[0][(size_t)j * C + ci];
     {
         const bool linear = p->rows > 8 || p->cols > 8;
-        const int budget = RB_MAX_SMEM - RB_OFF_W - RB_MAX_STAGES * CH * 4 - 64 - 16 - (linear ? RB_XCH_BYTES : 0);
         std::vector<std::vector<RbStage>> plan(1);
-        std::vector<int> plan_bytes(1, 0);
-        auto add_group = [&](std::vector<RbStage> group) {
-            int bytes = 0;
-            for (const RbStage& st : group) bytes += rb_stage_bytes(st.kind, st.ksteps);
-            if (!plan.back().empty() && (plan_bytes.back() + bytes > budget || plan.back().size() + group.size() > (size_t)RB_MAX_STAGES)) {
-                plan.emplace_back(); plan_bytes.push_back(0);
-            }
-            for (const RbStage& st : group) plan.back().push_back(st);
-            plan_bytes.back() += bytes;
+        auto plan_smem = [&](const std::vector<RbStage>& stages) {
+            RbPhase t;
+            memset(&t, 0, sizeof(t));
+            t.n_stages = (int)stages.size();
+            for (size_t j = 0; j < stages.size() && j < (size_t)RB_MAX_STAGES; ++j) { t.st[j] = stages[j]; t.w_bytes += rb_stage_bytes(stages[j].kind, stages[j].ksteps); }
+            t.w_bytes = (t.w_bytes + 127) / 128 * 128;
+            return rb_smem_bytes(t, linear);
         };
-        add_group({ RbStage{ RB_STEM, 0, in_k / KSTEP_CH, 0, 0, 0, 0 } });
+        auto add_group = [&](std::vector<RbStage> group) {
+            std::vector<RbStage> both = plan.back();
+            both.insert(both.end(), group.begin(), group.end());
+            if (!plan.back().empty() && (both.size() > (size_t)RB_MAX_STAGES || plan_smem(both) > RB_MAX_SMEM)) plan.push_back(group);
+            else plan.back() = both;
+        };
+        const int last_conv = L - 2;                              // layer index of the network's last conv (the stem if there are no blocks)
+        add_group({ RbStage{ RB_STEM, 0, in_k / KSTEP_CH, 0, 0, 0, 0, last_conv == 0 ? 1 : 0 } });
         for (int b = 0; b < p->blocks; ++b)
-            add_group({ RbStage{ RB_CONV, 1 + 2 * b, CH / KSTEP_CH, 0, 0, 0, 0 }, RbStage{ RB_CONV, 2 + 2 * b, CH / KSTEP_CH, 0, 1, 0, 0 } });
-        add_group({ RbStage{ RB_HEADS, L - 1, CH / KSTEP_CH, 0, 0, 0, 0 } });
-        bool fits = true;
-        for (size_t i = 0; i < plan.size(); ++i) fits = fits && plan_bytes[i] <= budget;
+            add_group({ RbStage{ RB_CONV, 1 + 2 * b, CH / KSTEP_CH, 0, 0, 0, 0, 0 },
+                        RbStage{ RB_CONV, 2 + 2 * b, CH / KSTEP_CH, 0, 1, 0, 0, last_conv == 2 + 2 * b ? 1 : 0 } });
+        bool fits = p->policy_channels <= 2;                      // three head outputs: the fused head sums hold that many
+        for (size_t i = 0; i < plan.size(); ++i) fits = fits && plan_smem(plan[i]) <= RB_MAX_SMEM;
         if (fits) {
             std::vector<size_t> w_at;                       // offset (in halfs) of every phase's [rank 0 | rank 1] weights
             for (size_t i = 0; i < plan.size(); ++i) {
@@ -1053,8 +1076,8 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
                     st.w_off = off;
                     off += rb_stage_bytes(st.kind, st.ksteps);
                     const bool last = j + 1 == ph.n_stages;
-                    st.save_res = (!last && st.kind != RB_HEADS && plan[i][j + 1].kind == RB_CONV && !plan[i][j + 1].add_res) ? 1 : 0;
-                    st.out_global = (last && st.kind != RB_HEADS) ? 1 : 0;
+                    st.save_res = (!last && plan[i][j + 1].kind == RB_CONV && !plan[i][j + 1].add_res) ? 1 : 0;
+                    st.out_global = (last && !st.heads) ? 1 : 0;
                     ph.st[j] = st;
                 }
                 ph.w_bytes = (off + 127) / 128 * 128;
@@ -1092,6 +1115,13 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     e->dev.wunits_bytes = (long long)(one * sizeof(unsigned short));
     e->dev.replicas = REPLICAS;
     e->dev.debug = getenv("SPRL_EVALNET_DEBUG") ? atoi(getenv("SPRL_EVALNET_DEBUG")) : 0;
+#ifdef SPRL_EVALNET_TRACE
+    if (getenv("SPRL_EVALNET_TRACE") && !e->dev.trace) {
+        std::vector<long long> z(16 * 3 * 256, 0);
+        const long long* tp = nullptr;
+        if (!e->upload(z, &tp)) e->dev.trace = const_cast<long long*>(tp);
+    }
+#endif
 #ifdef SPRL_EVALNET_TIMERS        // per-role cycle counters: only in builds that compile the clock reads in
     if (getenv("SPRL_EVALNET_TIMING") && !e->dev.timing) {
         std::vector<long long> z(1024 * 12, 0);
@@ -1103,6 +1133,7 @@ static int pack_and_upload(sprl_evalnet* e, const sprl_network_params* p) {
     if (getenv("SPRL_EVALNET_NST")) e->dev.nst = std::max(2, std::min(MAX_NST, atoi(getenv("SPRL_EVALNET_NST"))));   // experiments
     while (e->dev.nst > 2 && smem_bytes_for(L, e->dev.nst) > MAX_SMEM) e->dev.nst -= 1;
     int rc = e->upload(units, &e->dev.wunits);
+    if (!rc) rc = e->upload(head_w, &e->dev.head_w);
     if (!rc && !phases.empty()) {
         rc = e->upload(rbw, &e->rb_weights);
         for (RbPhase& ph : phases) ph.w = reinterpret_cast<const unsigned char*>(e->rb_weights) + reinterpret_cast<size_t>(ph.w);
@@ -1307,6 +1338,24 @@ int sprl_evalnet_status(sprl_evalnet* e, uint64_t* launches) {
             fprintf(stderr, "[evalnet timing, CTA %d, last launch] %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld\n",
                     b, t[b * 12 + 0], t[b * 12 + 1], t[b * 12 + 2], t[b * 12 + 3], t[b * 12 + 4], t[b * 12 + 5], t[b * 12 + 6], t[b * 12 + 7], t[b * 12 + 8], t[b * 12 + 9], t[b * 12 + 10]);
     }
+#ifdef SPRL_EVALNET_TRACE
+    if (e->dev.trace) {
+        std::vector<long long> t(16 * 3 * 256);
+        cudaMemcpy(t.data(), e->dev.trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        static const char* kinds[] = { "?", "mma_may_issue", "mma_committed", "epi_acc_ready", "epi_stage_done", "epi_next_input_written" };
+        for (size_t phx = 0; phx < e->phases.size() && phx < 16; ++phx) {
+            std::vector<long long> ev;
+            for (int role = 0; role < 3; ++role) {
+                const long long* r = t.data() + (phx * 3 + role) * 256;
+                for (long long i = 0; i < r[0] && i < 255; ++i) ev.push_back(r[1 + i]);
+            }
+            std::sort(ev.begin(), ev.end());
+            fprintf(stderr, "== phase %zu: %zu events\n", phx, ev.size());
+            for (long long x : ev)
+                fprintf(stderr, "%8lld  %-22s stream %lld stage %lld\n", (x >> 12) - (ev[0] >> 12), kinds[std::min<long long>(x & 15, 5)], (x >> 8) & 15, (x >> 4) & 15);
+        }
+    }
+#endif
     if (launches) *launches = e->launches;
     return SPRL_OK;
 }

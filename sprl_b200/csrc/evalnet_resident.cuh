@@ -15,7 +15,12 @@
 //     hi/lo fp16 weights) fit the pair's shared memory, and halves the B-operand reads per SM;
 //   * every CTA runs TWO tile streams (X, Y): own image pair, own 256 TMEM columns (192 accumulator + 64 residual),
 //     own group of 8 epilogue warps.  The leader's MMA warp issues stage j of X, then of Y, then stage j+1 of X ...:
-//     the epilogue of one stream runs under the MMAs of the other inside ONE CTA.
+//     the epilogue of one stream runs under the MMAs of the other inside ONE CTA;
+//   * the LAST stage of a phase never writes the image (its output goes to HBM or into the head convolutions), so its
+//     epilogue also writes the NEXT tile's input (image + residual columns) channel group by channel group and the next
+//     tile's first MMAs can be issued as soon as that epilogue ends; the 1x1 head convolutions (3 outputs) are 96 FMAs
+//     per thread inside the last conv epilogue instead of an MMA stage of their own (which put two more barrier round
+//     trips and the input load between two tiles: 4.5 k idle tensor cycles of 19 k per pair of tiles).
 //
 // Per SM and tile-layer the shared-memory port now carries 144 KB of A reads + 108 KB of B reads + 37 KB of image
 // writes = 84 B/clk of 128 against 3.46 k cycles of MMAs (was: 147 + 221 + 147 KB of weight writes + 37).
@@ -48,6 +53,7 @@ struct RbStage {
     int add_res;       // second conv of a block: + block input (TMEM residual columns)
     int save_res;      // the output is the input of the block that follows in this phase
     int out_global;    // last stage of a phase that does not end the network: fp32 activations to HBM
+    int heads;         // last conv of the network: the 1x1 head convolutions are computed from this stage's output
 };
 struct RbPhase {
     int n_stages;
@@ -61,7 +67,13 @@ struct RbPhase {
 // linear lattice (boards wider than 8, one per tile): Z_-1 / Z_+1 of a warp's edge lanes for its neighbour warps,
 // [stream][channel half][double buffer][warp of the quarter][left | right][16 values]
 constexpr int RB_XCH_BYTES = RB_STREAMS * 2 * 2 * 4 * 2 * 16 * 4;
-__host__ __device__ inline int rb_smem_bytes(const RbPhase& ph, bool linear) { return RB_OFF_W + ph.w_bytes + ph.n_stages * CH * 4 + 64 + 16 + (linear ? RB_XCH_BYTES : 0); }
+// fused head convolutions: fp32 weights [4][64] (rows above policy_channels are zero), then per stream the partial sums
+// of the upper channel half, one float4 per cell
+constexpr int RB_HEADW_BYTES = 4 * CH * 4;
+constexpr int RB_HEADS_BYTES = RB_HEADW_BYTES + RB_STREAMS * TILE_M * 16;
+__host__ __device__ inline int rb_smem_bytes(const RbPhase& ph, bool linear) {
+    return RB_OFF_W + ph.w_bytes + ph.n_stages * CH * 4 + 64 + 16 + (linear ? RB_XCH_BYTES : 0) + (ph.st[ph.n_stages - 1].heads ? RB_HEADS_BYTES : 0);
+}
 __host__ __device__ inline int rb_stage_ndy(int kind) { return kind == RB_CONV ? 3 : 1; }
 __host__ __device__ inline int rb_stage_n1(int kind) { return kind == RB_HEADS ? HEAD_N : 3 * CH; }
 // bytes of a stage's weights held by ONE CTA of the pair: [dy][k chunk of 8][hi rows | lo rows of this CTA][8 halfs]
@@ -90,6 +102,10 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         const RbStage& S = ph.st[i / CH];
         s_bias[i] = net.bias[S.layer * CH + (i & (CH - 1))] * (S.kind != RB_HEADS ? ACT_SCALE : 1.0f);
     }
+    const int off_heads = off_tmem + 16 + (LINEAR ? RB_XCH_BYTES : 0);
+    if (ph.st[ph.n_stages - 1].heads)
+        for (int i = threadIdx.x; i < 4 * CH; i += RB_THREADS)
+            reinterpret_cast<float*>(smem + off_heads)[i] = i / CH <= net.policy_channels ? net.head_w[i] : 0.0f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < RB_STREAMS; ++s) { mbar_init(bar_acc + 8 * s, 1); mbar_init(bar_img + 8 * s, 2 * RB_EPI_WARPS); }
         mbar_init(bar_w, 1);
@@ -117,6 +133,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         // ===== MMA issuer: the leader's warp runs the loop convergently, one elected lane issues =====
         if (crank == 0) {
             uint32_t img_phase = 0u;                                             // bit s: parity of stream s's next wait
+            TRACE_DECL(0)
             long long t_wait = 0, t0 = NOW();
             constexpr uint32_t A_KSTEP = (2u * RB_CG_STRIDE) >> 4;
             for (long long quad = pair; quad < n_quads; quad += n_pairs) {
@@ -131,6 +148,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                         { long long a = NOW(); mbar_wait_cluster(bar_img + 8 * s, (img_phase >> s) & 1u, net.error_flag, 10 + s); t_wait += NOW() - a; }
                         img_phase ^= 1u << s;
                         tc_fence_after();
+                        TRACE(s, j, 1);
                         const uint64_t a_hi0 = smem_desc(s_base + (2 * s) * RB_IMG_BYTES, RB_CG_STRIDE, 128);
                         const uint64_t a_lo0 = smem_desc(s_base + (2 * s + 1) * RB_IMG_BYTES, RB_CG_STRIDE, 128);
                         const uint32_t d_tmem = tmem + (uint32_t)(s * RB_STREAM_COLS);
@@ -150,10 +168,12 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                         }
                         umma_commit_pair(bar_acc + 8 * s);                      // both CTAs' epilogue groups of stream s
                         __syncwarp();
+                        TRACE(s, j, 2);
                     }
                 }
             }
             if (lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[0] = t_wait; tm[2] = NOW() - t0; }
+            TRACE_END();
         }
     } else {
         // ===== epilogue group of stream s: cell m = TMEM lane m =====
@@ -204,139 +224,188 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         const long long quad_step = 4LL * n_pairs;
         const long long tile0 = (long long)pair * 4 + s * 2 + crank;
         const int xbar = 1 + s * 2 + half;                           // named barrier of this stream's channel half (4 warps)
+        const int hbar = 5 + s * 4 + wq;                             // ... of the two warps that share a lane quarter (head sums)
+        const float4* s_hw = reinterpret_cast<const float4*>(smem + off_heads);                       // [4][64]
+        float4* s_hp = reinterpret_cast<float4*>(smem + off_heads + RB_HEADW_BYTES) + s * TILE_M;     // [cell]
+        const bool planes_in = ph.in_planes_mode != 0;
+        // stem image of a tile; its first channel group was prefetched into vnext
         float vnext[KCH];
-        if (ph.in_planes_mode) load_planes(tile0, half, vnext);
+        auto put_planes = [&](long long tile_) {
+            for (int cg = half; cg < 2 * ph.st[0].ksteps; cg += 2) {
+                float v[KCH];
+                if (cg == half) {
+#pragma unroll
+                    for (int j = 0; j < KCH; ++j) v[j] = vnext[j] * ACT_SCALE;
+                } else {
+                    load_planes(tile_, cg, v);
+#pragma unroll
+                    for (int j = 0; j < KCH; ++j) v[j] *= ACT_SCALE;
+                }
+                uint4 h, l;
+                split8(v, h, l, mx);
+                a_hi[cg * RB_SLOTS + slot] = h;
+                a_lo[cg * RB_SLOTS + slot] = l;
+            }
+        };
+        // fp32 activations of the previous phase (image units), 16 channels of this thread's cell: residual columns + hi/lo image
+        auto load_acts = [&](long long tile_, int q, float* x) {
+            const float4* src = reinterpret_cast<const float4*>(ph.act) + (size_t)tile_ * (RB_ACT_TILE_FLOATS / 4) + m;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = tile_ < n_tiles ? __ldcg(src + (q * 4 + j) * TILE_M) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+            }
+        };
+        auto put_acts = [&](int q, const float* x) {
+            tmem_st16(t_lane + RES_COL + q * 16, x);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 h, l;
+                split8(x + KCH * j, h, l, mx);
+                a_hi[(q * 2 + j) * RB_SLOTS + slot] = h;
+                a_lo[(q * 2 + j) * RB_SLOTS + slot] = l;
+            }
+        };
+        if (planes_in) load_planes(tile0, half, vnext);
         mbar_wait(bar_w, 0u, net.error_flag, 20);                   // (the leader's MMAs read both CTAs' weights: every arrival below implies them)
+        float xin[16];
+        TRACE_DECL(w8 == 0 ? 1 + s : 3)
+#ifdef SPRL_EVALNET_TRACE
+        if (w8 != 0) trace_at = nullptr;
+#endif
+        // ---- input of the first tile; every later tile's input is written by the last stage's epilogue of the tile before ----
+        if (planes_in) put_planes(tile0);
+        else {
+#pragma unroll 1
+            for (int q = 2 * half; q < 2 * half + 2; ++q) { load_acts(tile0, q, xin); put_acts(q, xin); }
+        }
+        signal();
         for (long long tile = tile0; tile < n_quads * 4; tile += quad_step) {
             const long long board = LINEAR ? tile : tile * 2 + b;
-            // ---- input stage ----
-            if (ph.in_planes_mode) {
-                for (int cg = half; cg < 2 * ph.st[0].ksteps; cg += 2) {
-                    float v[KCH];
-                    if (cg == half) {
-#pragma unroll
-                        for (int j = 0; j < KCH; ++j) v[j] = vnext[j] * ACT_SCALE;
-                    } else {
-                        load_planes(tile, cg, v);
-#pragma unroll
-                        for (int j = 0; j < KCH; ++j) v[j] *= ACT_SCALE;
-                    }
-                    uint4 h, l;
-                    split8(v, h, l, mx);
-                    a_hi[cg * RB_SLOTS + slot] = h;
-                    a_lo[cg * RB_SLOTS + slot] = l;
-                }
-            } else {
-                // fp32 activations of the previous phase (image units): residual columns + hi/lo image
-                const float4* src = reinterpret_cast<const float4*>(ph.act) + (size_t)tile * (RB_ACT_TILE_FLOATS / 4) + m;
-#pragma unroll 1
-                for (int q = 2 * half; q < 2 * half + 2; ++q) {
-                    float o[16];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 x = tile < n_tiles ? __ldcg(src + (q * 4 + j) * TILE_M) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        o[4 * j] = x.x; o[4 * j + 1] = x.y; o[4 * j + 2] = x.z; o[4 * j + 3] = x.w;
-                    }
-                    tmem_st16(t_lane + RES_COL + q * 16, o);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint4 h, l;
-                        split8(o + KCH * j, h, l, mx);
-                        a_hi[(q * 2 + j) * RB_SLOTS + slot] = h;
-                        a_lo[(q * 2 + j) * RB_SLOTS + slot] = l;
-                    }
-                }
-            }
-            signal();
+            const long long next = tile + quad_step;
+            const bool has_next = next < n_quads * 4;
             for (int j = 0; j <= last_stage; ++j) {
                 const RbStage S = ph.st[j];
-                if (j == last_stage && tile + quad_step < n_quads * 4) {
-                    // the next tile's input: planes into registers, activations towards L2, under this stage's MMAs
-                    if (ph.in_planes_mode) load_planes(tile + quad_step, half, vnext);
-                    else if (lane == 0 && tile + quad_step < n_tiles) {
-                        const float* nsrc = ph.act + (size_t)(tile + quad_step) * RB_ACT_TILE_FLOATS + (w8 & 3) * 32 * 4;
+                const bool feed = j == last_stage && has_next;       // this epilogue also writes the next tile's input
+                if (j == 0 && !planes_in && lane == 0 && next < n_tiles) {
+                    // the next tile's activations towards L2, a whole tile ahead of their use
+                    const float* nsrc = ph.act + (size_t)next * RB_ACT_TILE_FLOATS + (w8 & 3) * 32 * 4;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + ((2 * half) * 4 + k) * TILE_M * 4) : "memory");
-                    }
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + ((2 * half) * 4 + k) * TILE_M * 4) : "memory");
+                }
+                if (feed) {                                          // into registers under this stage's MMAs
+                    if (planes_in) load_planes(next, half, vnext);
+                    else load_acts(next, 2 * half, xin);
                 }
                 { long long a = NOW(); mbar_wait(bar_acc + 8 * s, acc_phase, net.error_flag, 30 + s); t_acc += NOW() - a; }
                 acc_phase ^= 1u;
                 tc_fence_after();
+                TRACE(s, j, 3);
+                // the image is free from here on in the last stage: its MMAs are complete and its output does not go there
+                if (feed && planes_in) put_planes(next);
                 const float* bias = s_bias + j * CH;
-                // accumulator -> image units for the conv stages (real units for the heads); exact powers of two
-                const float inv_scale = net.inv_scale[S.layer] * (S.kind != RB_HEADS ? ACT_SCALE : 1.0f);
-                if (S.kind != RB_HEADS) {
+                // accumulator -> image units; exact powers of two
+                const float inv_scale = net.inv_scale[S.layer] * ACT_SCALE;
+                float hp0 = 0.0f, hp1 = 0.0f, hp2 = 0.0f;            // head convolutions over this thread's 32 channels
 #pragma unroll 1
-                    for (int q = 2 * half; q < 2 * half + 2; ++q) {
-                        // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = accumulator columns [dx*64, dx*64+64)
-                        float o[16], v[16], w[16];
-                        tmem_ld16x3(t_lane + CH + q * 16, t_lane + q * 16, t_lane + 2 * CH + q * 16, o, v, w);   // dx = 0, -1, +1
-                        if (LINEAR) {
-                            // publish what the neighbouring warps need: lane 31's Z_-1 (for the next warp's lane 0) and lane 0's
-                            // Z_+1 (for the previous warp's lane 31); double-buffered per iteration
-                            float* mine = xch + (xbuf * 4 + wq) * 32;
-                            if (lane == 31) {
+                for (int q = 2 * half; q < 2 * half + 2; ++q) {
+                    // out[c] = Z_-1[c-1] + Z_0[c] + Z_+1[c+1]; Z_dx = accumulator columns [dx*64, dx*64+64)
+                    float o[16], v[16], w[16];
+                    tmem_ld16x3(t_lane + CH + q * 16, t_lane + q * 16, t_lane + 2 * CH + q * 16, o, v, w);   // dx = 0, -1, +1
+                    if (LINEAR) {
+                        // publish what the neighbouring warps need: lane 31's Z_-1 (for the next warp's lane 0) and lane 0's
+                        // Z_+1 (for the previous warp's lane 31); double-buffered per iteration
+                        float* mine = xch + (xbuf * 4 + wq) * 32;
+                        if (lane == 31) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) mine[i] = v[i];
-                            }
-                            if (lane == 0) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) mine[16 + i] = w[i];
-                            }
-                            named_bar(xbar, 128);
+                            for (int i = 0; i < 16; ++i) mine[i] = v[i];
                         }
+                        if (lane == 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
-                            if (xl) zl = xch[(xbuf * 4 + wq - 1) * 32 + i];
-                            if (xr) zr = xch[(xbuf * 4 + wq + 1) * 32 + 16 + i];
-                            o[i] = fmaf(zl, lmask, fmaf(zr, rmask, o[i]));
+                            for (int i = 0; i < 16; ++i) mine[16 + i] = w[i];
                         }
-                        xbuf ^= 1u;
-                        if (S.add_res) {                                                             // block input (image units), kept in TMEM
-                            tmem_ld16(t_lane + RES_COL + q * 16, v);
+                        named_bar(xbar, 128);
+                    }
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, v[i] + bias[q * 16 + i]), 0.0f) * vmask;
-                        } else {
+                    for (int i = 0; i < 16; ++i) {
+                        float zl = __shfl_up_sync(0xffffffffu, v[i], 1), zr = __shfl_down_sync(0xffffffffu, w[i], 1);
+                        if (xl) zl = xch[(xbuf * 4 + wq - 1) * 32 + i];
+                        if (xr) zr = xch[(xbuf * 4 + wq + 1) * 32 + 16 + i];
+                        o[i] = fmaf(zl, lmask, fmaf(zr, rmask, o[i]));
+                    }
+                    xbuf ^= 1u;
+                    if (S.add_res) {                                                             // block input (image units), kept in TMEM
+                        tmem_ld16(t_lane + RES_COL + q * 16, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, bias[q * 16 + i]), 0.0f) * vmask;
+                        for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, v[i] + bias[q * 16 + i]), 0.0f) * vmask;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = fmaxf(fmaf(o[i], inv_scale, bias[q * 16 + i]), 0.0f) * vmask;
+                    }
+                    if (S.out_global) {
+                        if (tile < n_tiles) {
+                            float4* dst = reinterpret_cast<float4*>(ph.act) + (size_t)tile * (RB_ACT_TILE_FLOATS / 4) + m;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                __stcg(dst + (q * 4 + jj) * TILE_M, make_float4(o[4 * jj], o[4 * jj + 1], o[4 * jj + 2], o[4 * jj + 3]));
                         }
-                        if (S.out_global) {
-                            if (tile < n_tiles) {
-                                float4* dst = reinterpret_cast<float4*>(ph.act) + (size_t)tile * (RB_ACT_TILE_FLOATS / 4) + m;
+                    } else if (S.heads) {
+                        // 1x1 head convolutions: rows 0..pc-1 policy conv, row pc value conv; ascending channel order
 #pragma unroll
-                                for (int jj = 0; jj < 4; ++jj)
-                                    __stcg(dst + (q * 4 + jj) * TILE_M, make_float4(o[4 * jj], o[4 * jj + 1], o[4 * jj + 2], o[4 * jj + 3]));
-                            }
-                        } else {
-                            if (S.save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 w0 = s_hw[q * 4 + i4], w1 = s_hw[16 + q * 4 + i4], w2 = s_hw[32 + q * 4 + i4];
+                            hp0 = fmaf(o[4 * i4 + 3], w0.w, fmaf(o[4 * i4 + 2], w0.z, fmaf(o[4 * i4 + 1], w0.y, fmaf(o[4 * i4], w0.x, hp0))));
+                            hp1 = fmaf(o[4 * i4 + 3], w1.w, fmaf(o[4 * i4 + 2], w1.z, fmaf(o[4 * i4 + 1], w1.y, fmaf(o[4 * i4], w1.x, hp1))));
+                            hp2 = fmaf(o[4 * i4 + 3], w2.w, fmaf(o[4 * i4 + 2], w2.z, fmaf(o[4 * i4 + 1], w2.y, fmaf(o[4 * i4], w2.x, hp2))));
+                        }
+                    } else {
+                        if (S.save_res) tmem_st16(t_lane + RES_COL + q * 16, o);
 #pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                uint4 h, l;
-                                split8(o + KCH * jj, h, l, mx);
-                                a_hi[(q * 2 + jj) * RB_SLOTS + slot] = h;
-                                a_lo[(q * 2 + jj) * RB_SLOTS + slot] = l;
-                            }
+                        for (int jj = 0; jj < 2; ++jj) {
+                            uint4 h, l;
+                            split8(o + KCH * jj, h, l, mx);
+                            a_hi[(q * 2 + jj) * RB_SLOTS + slot] = h;
+                            a_lo[(q * 2 + jj) * RB_SLOTS + slot] = l;
                         }
                     }
-                } else {
-                    // ---- heads (1x1): columns 0..pc-1 = policy conv channels, column pc = value conv; the ReLU'd
-                    // activations go to HBM for k_heads
-                    float v[16];
-                    tmem_ld16(t_lane, v);
-                    const int pc = net.policy_channels;
-                    if (board < batch && half == 0 && valid) {
-                        float* dst = net.head_act + board * (long long)((pc + 1) * cells);
-#pragma unroll
-                        for (int jj = 0; jj < 3; ++jj)
-                            if (jj <= pc) dst[jj * cells + cell] = fmaxf(v[jj] * inv_scale + bias[jj], 0.0f);
+                    if (feed && !planes_in) {
+                        // this thread is done with residual columns q and the image is free: the next tile's channels q
+                        put_acts(q, xin);
+                        if (q == 2 * half) load_acts(next, q + 1, xin);
                     }
                 }
-                if (j < last_stage) signal();       // (after the last stage the next tile's input stage signals)
+                const bool heads_first = S.heads && last_stage == 0;     // (single-stage phase: the partial sums must be read before
+                                                                         //  this warp lets the next tile's MMAs go)
+                auto finish_heads = [&]() {
+                    // upper channel half -> shared memory -> the warp of the lower half of the same cells; the ReLU'd
+                    // activations go to HBM for k_heads
+                    if (half == 1) {
+                        s_hp[m] = make_float4(hp0, hp1, hp2, 0.0f);
+                        __threadfence_block();
+                        asm volatile("bar.arrive %0, 64;" ::"r"(hbar) : "memory");
+                    } else {
+                        named_bar(hbar, 64);
+                        const float4 u = s_hp[m];
+                        const int pc = net.policy_channels;
+                        if (board < batch && valid) {
+                            const float* hb = net.bias + (net.n_layers - 1) * CH;
+                            float* dst = net.head_act + board * (long long)((pc + 1) * cells);
+                            const float sum[3] = { hp0 + u.x, hp1 + u.y, hp2 + u.z };
+#pragma unroll
+                            for (int jj = 0; jj < 3; ++jj)
+                                if (jj <= pc) dst[jj * cells + cell] = fmaxf(fmaf(sum[jj], 1.0f / ACT_SCALE, hb[jj]), 0.0f);
+                        }
+                    }
+                };
+                if (heads_first) finish_heads();
+                TRACE(s, j, feed ? 5 : 4);
+                if (j < last_stage || has_next) signal();
+                if (S.heads && !heads_first) finish_heads();
             }
         }
         if (mx > HALF_MAX) atomicExch(net.error_flag + 1, 1ULL);
+        TRACE_END();
         if (w8 == 0 && lane == 0 && net.timing) { long long* tm = net.timing + (ph.index * 160 + blockIdx.x) * 12; tm[4 + s] = t_acc; tm[6 + s] = NOW() - t0; }
     }
     tc_fence_before();

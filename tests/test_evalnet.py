@@ -95,10 +95,12 @@ def test_evalnet_smaller_boards(kind, rows, cols, batch):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,rows,cols,batch,phases", [("othello", 8, 8, 4099, 2), ("othello", 8, 8, 5, 2), ("c4", 6, 7, 1031, 2),
                                                          ("go7", 7, 7, 300, 7), ("go9", 9, 9, 203, 7)])
-def test_resident_and_streaming_kernels_agree_bit_for_bit(kind, rows, cols, batch, phases):
-    """The resident-weight kernel (CTA pairs, one launch per residual block, activations through HBM) accumulates
-    every output in the same order as the streaming kernel: identical bits, for every batch size and row -- two boards per
-    tile on the 8x8 lattice, one on the linear lattice (Go 9x9)."""
+def test_resident_and_streaming_kernels_agree(kind, rows, cols, batch, phases):
+    """The resident-weight kernel (CTA pairs, one launch per residual block, activations through HBM) accumulates the
+    conv tower in the same order as the streaming kernel; its 1x1 head convolutions are fp32 FMAs inside the last conv
+    epilogue instead of split-fp16 MMAs, so the two agree to rounding (1e-6 on logits and value, both within 2e-6 of the
+    fp64 forward in the tests above) -- two boards per tile on the 8x8 lattice, one on the linear lattice (Go 9x9).  The
+    resident path itself is bit-identical from one grid size to another."""
     net = randomized(make_network(kind, 2), 6)
     x = (torch.rand(batch, net.conv.in_channels, rows, cols) > 0.5).float().cuda()
     ev = EvalNet(net, device=0, rows=rows, cols=cols)
@@ -110,7 +112,7 @@ def test_resident_and_streaming_kernels_agree_bit_for_bit(kind, rows, cols, batc
     ev.set_path(capi.EVALNET_PATH_RESIDENT)
     l_again, v_again = ev(x[: batch // 2 + 1])              # another grid size on the resident path
     ev.status()
-    assert torch.equal(l_res, l_str) and torch.equal(v_res, v_str)
+    assert (l_res - l_str).abs().max().item() <= 1e-6 and (v_res - v_str).abs().max().item() <= 1e-6
     assert torch.equal(l_again, l_res[: batch // 2 + 1]) and torch.equal(v_again, v_res[: batch // 2 + 1])
     ev.close()
 

@@ -1,4 +1,4 @@
-"""A/B of the two conv-tower kernels on the GPU: bit-equality of the outputs and CUDA-event timing.
+"""A/B of the two conv-tower kernels on the GPU: agreement of the outputs and CUDA-event timing.
     python tools/check_resident.py [rows ...]        (default 65536 61960 4096)"""
 import sys
 import os
@@ -8,6 +8,34 @@ from sprl_b200 import capi
 from sprl_b200.evalnet import EvalNet
 from sprl_b200.network import make_network
 
+import threading
+import time
+import pynvml
+pynvml.nvmlInit()
+_h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+
+class Sampler:
+    """SM clock and board power while a timing loop runs (NVML, every 5 ms)."""
+    def __enter__(self):
+        self.clk, self.pw, self.stop = [], [], False
+        def run():
+            while not self.stop:
+                self.clk.append(pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM))
+                self.pw.append(pynvml.nvmlDeviceGetPowerUsage(_h) / 1e3)
+                time.sleep(0.005)
+        self.t = threading.Thread(target=run)
+        self.t.start()
+        return self
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join()
+    def summary(self):
+        c, p = sorted(self.clk), sorted(self.pw)
+        return f"sm clock median {c[len(c) // 2]} MHz (min {c[0]}), power median {p[len(p) // 2]:.0f} W (max {p[-1]:.0f}) over {len(c)} samples"
+
+
+REPS = int(os.environ.get("REPS", "20"))
 kind = os.environ.get("KIND", "othello")
 shape = {"othello": (8, 8), "c4": (6, 7), "go7": (7, 7), "go9": (9, 9)}[kind]
 net = make_network(kind, 0)
@@ -27,12 +55,15 @@ for n in sizes:
         for _ in range(3):
             ev(x)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        e0.record()
-        for _ in range(reps):
-            ev(x)
-        e1.record()
-        torch.cuda.synchronize()
+        reps = REPS
+        with Sampler() as smp:
+            e0.record()
+            for _ in range(reps):
+                ev(x)
+            e1.record()
+            torch.cuda.synchronize()
+        if reps >= 100:
+            print(f"  {name}: {smp.summary()}", flush=True)
         out[name] = (l, v, e0.elapsed_time(e1) / reps)
         ev.status()
     (lr, vr, tr), (ls, vs, ts) = out["resident"], out["streaming"]
