@@ -90,7 +90,7 @@ def parse():
 class ClockSampler:
     """Samples nvidia-smi clocks and throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -118,17 +118,23 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts, limit = [], None, set(), [], None
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except ValueError:
                 continue
+            try:
+                watts.append(float(r[2])); limit = float(r[7]) if len(r) > 7 else None
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        watts.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": watts[len(watts) // 2] if watts else None, "power_limit_w": limit}
 
 
 def bytes_per_sim(D, L, e, planes_cells=192, A=65):

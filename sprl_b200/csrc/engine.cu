@@ -223,7 +223,17 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
         int64_t nodes = 6 * (int64_t)(cfg->sims + cfg->max_batch) + 64;
         e->cfg.units_per_tree = std::max<int64_t>(4096, nodes * (hdr + typical));
     }
-    if (e->cfg.units_per_tree > (1 << 24) - 1) e->cfg.units_per_tree = (1 << 24) - 1;       // child index is 24 bits
+    if (cfg->units_per_tree > (1 << 24) - 1) {                                               // child index is 24 bits
+        delete e;
+        return fail(SPRL_E_INVALID, "units_per_tree = %lld exceeds the 24-bit child index (at most %d units of 16 bytes per slab)", (long long)cfg->units_per_tree, (1 << 24) - 1);
+    }
+    if (e->cfg.units_per_tree > (1 << 24) - 1) {
+        // derived from the search budget (the reference's Go worker asks for 32,768 descents per move): the slab stops
+        // at the index width, and a tree that outgrows it reports SPRL_E_CAPACITY when it happens
+        fprintf(stderr, "sprl_create: sims = %d asks for %lld units per tree, clamped to %d (24-bit child index, %.2f GB per tree)\n",
+                cfg->sims, (long long)e->cfg.units_per_tree, (1 << 24) - 1, 2.0 * 16.0 * ((1 << 24) - 1) / 1e9);
+        e->cfg.units_per_tree = (1 << 24) - 1;
+    }
     if (e->cfg.units_per_tree < 2 * (hdr + gi.actions) + SLAB_SLACK + 2) { delete e; return fail(SPRL_E_INVALID, "units_per_tree too small"); }
 
     EngineParams& p = e->p;
@@ -242,6 +252,14 @@ int sprl_create(const sprl_config* cfg, sprl_engine** out) {
 
     const size_t S = (size_t)cfg->num_slots, MG = (size_t)e->cfg.max_games, MM = (size_t)gi.max_plies, A = (size_t)gi.actions;
     rc = e->alloc(&p.pool, S * 2 * p.cap_units, false);
+    if (rc) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double per_tree = 2.0 * 16.0 * (double)p.cap_units;
+        rc = fail(SPRL_E_CAPACITY, "the tree slabs do not fit: %d slots x %.1f MB per tree (2 slabs of %llu units) = %.1f GB, %.1f GB free on the device; "
+                  "lower num_slots (about %lld fit) or units_per_tree", cfg->num_slots, per_tree / 1e6, p.cap_units, per_tree * S / 1e9, free_b / 1e9,
+                  (long long)(0.9 * free_b / per_tree));
+    }
     if (!rc) rc = e->alloc(&p.trees, S, true);
     if (!rc) rc = e->alloc(&p.q_leaf, S * cfg->max_queue, true);
     if (!rc) rc = e->alloc(&p.q_sym, S * cfg->max_queue, true);

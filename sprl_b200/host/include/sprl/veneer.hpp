@@ -326,8 +326,10 @@ MatchResult runMatch(INetwork<State, ACTION_SIZE>* network0, INetwork<State, ACT
         check(sprl_bind_eval_buffers(e, d_in, d_logits, d_value));
         const uint32_t* d_rows = nullptr;
         check(sprl_eval_rows(e, &d_rows));
+        // each network evaluates the rows its side queued (count read on the device); ONE network object serving both
+        // sides has a single row-count slot, so it evaluates both halves at full size instead
         for (int k = 0; k < 2; ++k)
-            if (ctx.net[k]) ctx.net[k]->setRowCount(d_rows + k);
+            if (ctx.net[k]) ctx.net[k]->setRowCount(ctx.net[0] == ctx.net[1] ? nullptr : d_rows + k);
     }
     sprl_forward_fn fwd = [](void* user, const float* in, int64_t, float* logits, float* value, void* stream) -> int {
         Ctx* c = static_cast<Ctx*>(user);

@@ -504,6 +504,23 @@ def test_match_vs_oracle(game, evs, syms, qs, sims, b, q, ngames, pairs):
     assert got["wins"][0] + got["wins"][1] + got["draws"] == ngames
 
 
+def test_match_move_without_any_visit_is_the_first_legal_action():
+    """With sims <= max_queue an agent's search ends after the descent that evaluates its (always fresh) root: every edge
+    has 0 visits.  The reference's std::max_element then returns action 0 whether or not it is legal
+    (agents/UCTNetworkAgent.hpp:92-93) and walks into an illegal child; the engine plays the first LEGAL action instead
+    (search.cu: finalize_match_move) -- the one documented departure of match play, pinned here: every move of every game
+    has all-zero visit counts and is the lowest legal action, and the games end with a result."""
+    agents = [dict(evaluator=capi.EVAL_UNIFORM, hash_salt=0, use_sym=0, init_q=capi.INITQ_PARENT)] * 2
+    got = run_match(capi.GAME_OTHELLO, agents, 3, 0, 4, 1, 1, 1)
+    n = len(got["move_action"])
+    assert n > 4 * 20
+    assert not got["move_N"].any()
+    for m in range(n):
+        legal = np.flatnonzero(got["move_P"][m] > 0)
+        assert legal.size > 0 and got["move_action"][m] == legal[0]
+    assert got["wins"][0] + got["wins"][1] + got["draws"] == 4
+
+
 @pytest.mark.parametrize("game,sims,b,q,ngames,pairs,graph,second", [
     (capi.GAME_OTHELLO, 64, 8, 4, 6, 3, False, "net"),
     (capi.GAME_OTHELLO, 48, 8, 4, 4, 4, True, "net"),          # round + both forwards replayed as one CUDA graph
