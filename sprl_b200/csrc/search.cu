@@ -1003,7 +1003,10 @@ struct TreeWarp {
 };
 
 // ---- kernels -------------------------------------------------------------------------------------
-constexpr int WARPS_PER_BLOCK = 1;         // one tree per block: a finished tree frees its slot at once
+#ifndef SPRL_SEARCH_WARPS_PER_BLOCK
+#define SPRL_SEARCH_WARPS_PER_BLOCK 1
+#endif
+constexpr int WARPS_PER_BLOCK = SPRL_SEARCH_WARPS_PER_BLOCK;      // 1: one tree per block, a finished tree frees its slot at once
 #ifndef SPRL_SEARCH_BLOCKS_PER_SM
 #define SPRL_SEARCH_BLOCKS_PER_SM 32
 #endif
