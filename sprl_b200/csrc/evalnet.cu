@@ -942,6 +942,7 @@ struct sprl_evalnet {
     float* act = nullptr;          // [act_cap_tiles][RB_ACT_TILE_FLOATS]
     int64_t act_cap_tiles = 0;
     int path = 0;                  // SPRL_EVALNET_PATH_*: 0 auto (resident when the network fits), 1 streaming, 2 resident
+    int max_ctas = 0;              // experiments (SPRL_EVALNET_MAX_CTAS): caps the resident kernel's grid, leaving SMs to a concurrent search launch
     // First call allocates; later calls (a new generation's weights) overwrite in place, so device
     // pointers captured in a CUDA graph stay valid.
     template <typename T> int upload(const std::vector<T>& h, const T** out) {
@@ -1202,6 +1203,7 @@ int sprl_evalnet_create(int device, const sprl_network_params* params, sprl_eval
     if (err != cudaSuccess) { delete e; return fail(SPRL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err)); }
     if (prop.major != 10) { delete e; return fail(SPRL_E_NOGPU, "the tcgen05 evaluator needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
     e->sm_count = prop.multiProcessorCount;
+    if (getenv("SPRL_EVALNET_MAX_CTAS")) e->max_ctas = atoi(getenv("SPRL_EVALNET_MAX_CTAS"));
     if (getenv("SPRL_EVALNET_PATH")) e->path = atoi(getenv("SPRL_EVALNET_PATH"));      // experiments: 1 streaming, 2 resident
     err = cudaFuncSetAttribute(k_evalnet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(k_evalnet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
@@ -1273,7 +1275,8 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
             if (err != cudaSuccess) return fail(SPRL_E_CAPACITY, "cudaMalloc of the inter-phase activations failed: %s", cudaGetErrorString(err));
             e->act_cap_tiles = quads * 4;
         }
-        const int grid = (int)std::min<long long>(2 * quads, (long long)(e->sm_count / 2 * 2));     // one CTA per SM, in pairs
+        int grid = (int)std::min<long long>(2 * quads, (long long)(e->sm_count / 2 * 2));     // one CTA per SM, in pairs
+        if (e->max_ctas >= 2) grid = std::min(grid, e->max_ctas / 2 * 2);
         for (RbPhase ph : e->phases) {
             ph.act = e->act;
             cudaLaunchConfig_t cfg = {};

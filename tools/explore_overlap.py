@@ -14,7 +14,9 @@ dev = torch.device("cuda", 0)
 net = make_network("othello", 0)
 TOTAL = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 
-for groups in (1, 2, 3, 4):
+GROUPS = [int(g) for g in os.environ.get("GROUPS", "1,2,3,4").split(",")]
+print("SPRL_EVALNET_MAX_CTAS =", os.environ.get("SPRL_EVALNET_MAX_CTAS"), flush=True)
+for groups in GROUPS:
     slots = TOTAL // groups
     engines, graphs, streams, evs = [], [], [], []
     for g in range(groups):
