@@ -327,10 +327,12 @@ int sprl_evalnet_forward_counted(sprl_evalnet* net, const float* d_in, const uin
 int sprl_evalnet_status(sprl_evalnet* net, uint64_t* launches);
 /* Bytes copied host -> device by one create / update, weight-ring depth and shared memory per CTA. */
 int sprl_evalnet_info(sprl_evalnet* net, int64_t* upload_bytes, int32_t* ring_stages, int32_t* smem_bytes);
-/* Which kernel runs the conv tower.  AUTO: the resident-weight kernel (csrc/evalnet_resident.cuh: weights of one
- * residual block stay in shared memory for a whole launch, one launch per block) when the board is at most 8x8 and
- * a block fits, else the streaming kernel (weights re-read from L2 per tile; also Go 9x9).  Both compute the same
- * arithmetic in the same order; STREAMING / RESIDENT force one of them (tests, A/B timing). */
+/* Which kernel runs the conv tower.  AUTO: the resident-weight kernel (csrc/evalnet_resident.cuh: the weights of one
+ * residual block stay in shared memory for a whole launch, one launch per block; boards of up to 128 cells incl. Go 9x9)
+ * when a block fits, else the streaming kernel (weights re-read from L2 per tile).  Both accumulate the conv tower in
+ * the same order; the resident kernel computes the 1x1 head convolutions as fp32 FMAs instead of split-fp16 MMAs, so
+ * their outputs agree to rounding (1e-6), each within 2e-6 of the fp64 forward.  STREAMING / RESIDENT force one of
+ * them (tests, A/B timing). */
 #define SPRL_EVALNET_PATH_AUTO 0
 #define SPRL_EVALNET_PATH_STREAMING 1
 #define SPRL_EVALNET_PATH_RESIDENT 2
