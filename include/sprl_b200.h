@@ -337,6 +337,15 @@ int sprl_evalnet_info(sprl_evalnet* net, int64_t* upload_bytes, int32_t* ring_st
 #define SPRL_EVALNET_PATH_STREAMING 1
 #define SPRL_EVALNET_PATH_RESIDENT 2
 int sprl_evalnet_set_path(sprl_evalnet* net, int path);
+/* Arithmetic of the conv tower.  FP32_SPLIT (default; what every parity statement and the headline benchmark use): both
+ * operands of every product are split into two fp16 terms, three MMAs per product, fp32 accumulation -- within 2e-6 of
+ * the fp64 forward, the accuracy of the reference's fp32 LibTorch path.  FP16 (opt-in, resident kernel only): the hi
+ * terms alone, one MMA per product, fp32 accumulation, fp32 bias / residual / head layers -- the "bf16/fp16 with fp32
+ * accumulate" design point of an inference-only evaluator; about 1e-3 on logits.  It is NOT the reference's precision:
+ * self-play statistics differ from an fp32 evaluator's, and a throughput measured with it is a different metric. */
+#define SPRL_EVALNET_PRECISION_FP32_SPLIT 0
+#define SPRL_EVALNET_PRECISION_FP16 1
+int sprl_evalnet_set_precision(sprl_evalnet* net, int precision);
 /* Launches of the resident-weight kernel per forward (0: the streaming kernel is in use). */
 int sprl_evalnet_phases(sprl_evalnet* net);
 void sprl_evalnet_destroy(sprl_evalnet* net);

@@ -16,6 +16,7 @@ GAME_OTHELLO, GAME_C4, GAME_GO7, GAME_GO9 = 0, 1, 2, 3
 EVAL_UNIFORM, EVAL_HASHNET, EVAL_EXTERNAL, EVAL_OTHELLO_HEURISTIC = 0, 1, 2, 3
 INITQ_ZERO, INITQ_PARENT, INITQ_DROP_PARENT = 0, 1, 2
 EVALNET_PATH_AUTO, EVALNET_PATH_STREAMING, EVALNET_PATH_RESIDENT = 0, 1, 2
+EVALNET_PRECISION_FP32_SPLIT, EVALNET_PRECISION_FP16 = 0, 1
 
 EXPORTS = [
     "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
@@ -24,7 +25,7 @@ EXPORTS = [
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device", "sprl_stream_samples", "sprl_stream_info",
     "sprl_match_begin", "sprl_run_match", "sprl_match_results", "sprl_begin_trees", "sprl_search", "sprl_search_batch",
     "sprl_apply_evaluations", "sprl_root_stats", "sprl_advance", "sprl_move_stats", "sprl_debug_check_guards", "sprl_get_stats", "sprl_reset_stats", "sprl_write_npy_f32",
-    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_forward_counted", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_set_path", "sprl_evalnet_phases", "sprl_evalnet_destroy",
+    "sprl_evalnet_create", "sprl_evalnet_update", "sprl_evalnet_forward", "sprl_evalnet_forward_counted", "sprl_evalnet_status", "sprl_evalnet_info", "sprl_evalnet_set_path", "sprl_evalnet_set_precision", "sprl_evalnet_phases", "sprl_evalnet_destroy",
 ]
 
 
@@ -136,6 +137,7 @@ def load():
     lib.sprl_evalnet_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.sprl_evalnet_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.sprl_evalnet_set_path.argtypes = [C.c_void_p, C.c_int]
+    lib.sprl_evalnet_set_precision.argtypes = [C.c_void_p, C.c_int]
     lib.sprl_evalnet_phases.argtypes = [C.c_void_p]
     lib.sprl_evalnet_destroy.restype = None
     lib.sprl_evalnet_destroy.argtypes = [C.c_void_p]

@@ -148,6 +148,7 @@ struct NetDev {
     unsigned long long* error_flag;   // [0] pipeline barrier time-out, [1] an activation left the fp16-split range
     float inv_scale[MAX_LAYERS];      // 2^-(ACT_SHIFT + weight shift of the layer): accumulator -> real units
     long long* timing;       // [grid][12] cycle counters per role (debug >= 0: always written, tiny)
+    int single_pass;         // SPRL_EVALNET_PRECISION_FP16 (resident kernel): one fp16 MMA per product instead of the three of the hi/lo split
     long long* trace;        // -DSPRL_EVALNET_TRACE builds: [phase][role: mma, epilogue X, epilogue Y][1 + 255 events] of CTA 0, clock << 12 | code
     int debug;               // timing experiments only (SPRL_EVALNET_DEBUG): 1 skip lo pass, 3 no MMAs, 5 = 3 + no conv epilogue, 6 = MMAs but no conv epilogue
 };
@@ -1262,6 +1263,7 @@ int sprl_evalnet_forward_counted(sprl_evalnet* e, const float* d_in, const uint3
     const bool resident = !e->phases.empty() && e->path != SPRL_EVALNET_PATH_STREAMING;
     if (e->path == SPRL_EVALNET_PATH_RESIDENT && e->phases.empty())
         return fail(SPRL_E_STATE, "this network does not fit the resident-weight kernel (boards up to 8x8, one stage group per launch within 227 KB)");
+    if (e->dev.single_pass && !resident) return fail(SPRL_E_STATE, "the single-pass fp16 mode exists on the resident-weight kernel only");
     if (resident) {
         const long long quads = (tiles + 3) / 4;
         if (e->phases.size() > 1 && quads * 4 > e->act_cap_tiles) {
@@ -1383,6 +1385,15 @@ int sprl_evalnet_set_path(sprl_evalnet* e, int path) {
     if (path == SPRL_EVALNET_PATH_RESIDENT && e->phases.empty())
         return fail(SPRL_E_STATE, "this network does not fit the resident-weight kernel");
     e->path = path;
+    return SPRL_OK;
+}
+
+int sprl_evalnet_set_precision(sprl_evalnet* e, int precision) {
+    if (!e) return fail(SPRL_E_INVALID, "null evaluator");
+    if (precision != SPRL_EVALNET_PRECISION_FP32_SPLIT && precision != SPRL_EVALNET_PRECISION_FP16) return fail(SPRL_E_INVALID, "unknown evaluator precision %d", precision);
+    if (precision == SPRL_EVALNET_PRECISION_FP16 && (e->phases.empty() || e->path == SPRL_EVALNET_PATH_STREAMING))
+        return fail(SPRL_E_STATE, "the single-pass fp16 mode exists on the resident-weight kernel only");
+    e->dev.single_pass = precision == SPRL_EVALNET_PRECISION_FP16 ? 1 : 0;
     return SPRL_OK;
 }
 

@@ -133,6 +133,7 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
         // ===== MMA issuer: the leader's warp runs the loop convergently, one elected lane issues =====
         if (crank == 0) {
             uint32_t img_phase = 0u;                                             // bit s: parity of stream s's next wait
+            const bool split = net.single_pass == 0;                             // (SPRL_EVALNET_PRECISION_FP16: hi x hi only)
             TRACE_DECL(0)
             long long t_wait = 0, t0 = NOW();
             constexpr uint32_t A_KSTEP = (2u * RB_CG_STRIDE) >> 4;
@@ -161,8 +162,10 @@ k_evalnet_resident(NetDev net, RbPhase ph, const float* __restrict__ in, long lo
                             for (int ks = 0; ks < S.ksteps; ++ks) {
                                 const uint64_t ah = a_hi0 + a_off + ks * A_KSTEP, al = a_lo0 + a_off + ks * A_KSTEP, bd = bt + ks * b_kstep;
                                 umma_f16_pair(d_tmem, ah, bd, idesc, acc);
-                                umma_f16_pair(d_tmem, ah, bd + b_lo_off, idesc, 1u);
-                                umma_f16_pair(d_tmem, al, bd, idesc, 1u);
+                                if (split) {                                     // the two correction products of the hi/lo split
+                                    umma_f16_pair(d_tmem, ah, bd + b_lo_off, idesc, 1u);
+                                    umma_f16_pair(d_tmem, al, bd, idesc, 1u);
+                                }
                                 acc = 1;
                             }
                         }

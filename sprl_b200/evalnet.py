@@ -93,6 +93,11 @@ class EvalNet:
                          torch.cuda.current_stream(x.device).cuda_stream)
         return logits, value.reshape(-1, 1)
 
+    def set_precision(self, precision):
+        """capi.EVALNET_PRECISION_FP32_SPLIT (default: fp32-level accuracy, three fp16 MMAs per product) or
+        capi.EVALNET_PRECISION_FP16 (opt-in: one MMA per product, ~1e-3 on logits; not the reference's precision)."""
+        capi.check(self.lib.sprl_evalnet_set_precision(self.handle, precision))
+
     def set_path(self, path):
         """capi.EVALNET_PATH_AUTO / _STREAMING / _RESIDENT: which conv-tower kernel runs (same arithmetic, same order)."""
         capi.check(self.lib.sprl_evalnet_set_path(self.handle, path))

@@ -266,3 +266,35 @@ def test_evalnet_large_batchnorm_scales(gain, ok):
                 ev.status()
             assert "range" in str(err.value)
         ev.close()
+
+
+@pytest.mark.gpu
+def test_evalnet_single_pass_fp16_is_opt_in_and_labelled():
+    """SPRL_EVALNET_PRECISION_FP16: one fp16 MMA per product instead of the three of the hi/lo split.  Opt-in, resident
+    kernel only; accuracy of fp16 operands with fp32 accumulation (measured here, bound 5e-3 on logits of O(1)); switching
+    back restores the default path's bits; the streaming kernel refuses the mode."""
+    net = randomized(make_network("othello", 2), 4)
+    x = (torch.rand(515, 3, 8, 8) > 0.5).float()
+    with torch.no_grad():
+        want_l, want_v = net.double()(x.double())
+        net.float()
+    ev = EvalNet(net, device=0)
+    l32, v32 = ev(x.cuda())
+    ev.set_precision(capi.EVALNET_PRECISION_FP16)
+    l16, v16 = ev(x.cuda())
+    l16b, _ = ev(x[:77].cuda())                                   # deterministic and independent of the batch
+    ev.status()
+    e32 = (l32.cpu().double() - want_l).abs().max().item()
+    e16 = (l16.cpu().double() - want_l).abs().max().item()
+    assert e32 <= 2e-6
+    assert 1e-5 < e16 <= 5e-3, e16                                 # a different, coarser arithmetic -- and only when asked for
+    assert (v16.cpu().double() - want_v).abs().max().item() <= 5e-3
+    assert torch.equal(l16b, l16[:77])
+    ev.set_precision(capi.EVALNET_PRECISION_FP32_SPLIT)
+    l_again, v_again = ev(x.cuda())
+    assert torch.equal(l_again, l32) and torch.equal(v_again, v32)
+    ev.set_precision(capi.EVALNET_PRECISION_FP16)
+    ev.set_path(capi.EVALNET_PATH_STREAMING)
+    with pytest.raises(capi.SprlError):
+        ev(x.cuda())
+    ev.close()
