@@ -126,6 +126,14 @@ private:
             std::cout << "Evaluator: TorchScript module through LibTorch (" << sprl_last_error() << ")" << std::endl;
         } else {
             std::cout << "Evaluator: tcgen05 network kernel of libsprl_b200" << std::endl;
+            // opt-in only: SPRL_EVALNET_PRECISION=fp16 selects the single-pass mode (not the reference's fp32 arithmetic)
+            const char* prec = std::getenv("SPRL_EVALNET_PRECISION");
+            if (prec && std::string(prec) == "fp16") {
+                if (sprl_evalnet_set_precision(m_evalnet, SPRL_EVALNET_PRECISION_FP16) == SPRL_OK)
+                    std::cout << "Evaluator precision: single-pass fp16 (SPRL_EVALNET_PRECISION=fp16; NOT the reference's fp32)" << std::endl;
+                else
+                    std::cout << "Evaluator precision: fp32-equivalent split (" << sprl_last_error() << ")" << std::endl;
+            }
         }
     }
 
