@@ -70,6 +70,15 @@ int sprl_env_step(int device, int game, int64_t n, const int8_t* h_cells, const 
                   const int32_t* h_action, int8_t* h_next_cells, int8_t* h_next_player,
                   int8_t* h_terminal, int8_t* h_winner, int8_t* h_mask);
 
+/* One line of play from the start position: h_actions[0 .. n_actions-1] in order -- the chain of
+ * GameNode::getAddChild calls of a host program (games/GameNode.hpp:96-110; the start position is the node
+ * constructor's setStartNode, :176), for every game incl. Go (the line itself is the history of the positional-superko
+ * rule, games/GoNode.cpp:88-170).  Outputs (host, any may be NULL) for the n_actions + 1 positions along the line, start
+ * position first: cells [n+1, cells], player / terminal / winner [n+1], mask [n+1, actions], encodings as in
+ * sprl_env_step.  An action that is not legal where it is played fails with SPRL_E_INVALID (the reference asserts). */
+int sprl_env_line(int device, int game, int32_t n_actions, const int32_t* h_actions, int8_t* h_cells, int8_t* h_player,
+                  int8_t* h_terminal, int8_t* h_winner, int8_t* h_mask);
+
 /* Random playouts from the start position, one GPU thread per game; move k of
  * game g is legal[UniformInt(0, nlegal-1)] from the stream (seed, first_game+g).
  * h_game_steps [ngames] receives positions per game (start and terminal

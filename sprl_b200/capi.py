@@ -19,7 +19,7 @@ EVALNET_PATH_AUTO, EVALNET_PATH_STREAMING, EVALNET_PATH_RESIDENT = 0, 1, 2
 EVALNET_PRECISION_FP32_SPLIT, EVALNET_PRECISION_FP16 = 0, 1
 
 EXPORTS = [
-    "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_rollout",
+    "sprl_last_error", "sprl_device_count", "sprl_game_info_get", "sprl_env_step", "sprl_env_line", "sprl_env_rollout",
     "sprl_env_perft", "sprl_default_config", "sprl_create", "sprl_destroy", "sprl_set_stream",
     "sprl_bind_eval_buffers", "sprl_eval_batch", "sprl_eval_rows", "sprl_set_game_stride", "sprl_begin_iteration", "sprl_round", "sprl_poll",
     "sprl_run_iteration", "sprl_iteration_counts", "sprl_collect_samples", "sprl_collect_samples_device", "sprl_stream_samples", "sprl_stream_info",
@@ -126,6 +126,7 @@ def load():
     lib.sprl_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.sprl_reset_stats.argtypes = [C.c_void_p]
     lib.sprl_env_step.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 8
+    lib.sprl_env_line.argtypes = [C.c_int, C.c_int, C.c_int32] + [C.c_void_p] * 6
     lib.sprl_env_rollout.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.sprl_env_perft.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]

@@ -106,6 +106,36 @@ __global__ void k_env_step(int64_t n, const u64* __restrict__ b0, const u64* __r
     pos_to_rec<G>(nx, out[i]);
 }
 
+// ---- one line of play from the start position (a chain of GameNode::getAddChild calls, games/GameNode.hpp:96-110) ----
+// One thread: the line is sequential.  rec[k] = the position after k actions; for Go the line is the history of the
+// positional-superko rule.  *bad = index of the first action that is not legal where it is played (or -1).
+template <class G>
+__global__ void k_env_line(int n_actions, const int* __restrict__ actions, PosRec* __restrict__ rec,
+                           u64* __restrict__ hist /* [n_actions + 1][2W] */, int* __restrict__ bad) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    typename G::P cur, nx;
+    G::start(cur);
+    *bad = -1;
+    for (int k = 0;; ++k) {
+        PosRec r;
+        pos_to_rec<G>(cur, r);
+        r.action = k < n_actions ? actions[k] : -1;
+        rec[k] = r;
+        if (k == n_actions) break;
+        const int a = actions[k];
+        const bool legal = !cur.terminal && a >= 0 && a < G::ACTIONS &&
+                           ((G::HAS_PASS && a == G::CELLS) ? cur.pass_legal != 0 : cur.legal.test(a));
+        if (!legal) { *bad = k; break; }
+        const LineHist<G::W> lh = { hist, k };              // the positions before `cur`; next() adds `cur` and the new one
+        G::next(cur, a, lh, nx);
+        for (int w = 0; w < G::W; ++w) {
+            hist[(size_t)k * 2 * G::W + w] = cur.b[0].word(w);
+            hist[(size_t)k * 2 * G::W + G::W + w] = cur.b[1].word(w);
+        }
+        cur = nx;
+    }
+}
+
 // ---- random playouts, one thread per game ----------------------------------------------
 template <class G>
 __global__ void k_rollout(uint64_t seed, uint64_t first_game, int64_t ngames, int max_steps,
@@ -372,6 +402,31 @@ static int env_rollout_impl(uint64_t seed, uint64_t first_game, int64_t ngames, 
 }
 
 template <class G>
+static int env_line_impl(int32_t n_actions, const int32_t* h_actions, int8_t* h_cells, int8_t* h_player, int8_t* h_terminal,
+                         int8_t* h_winner, int8_t* h_mask) {
+    if (n_actions > G::MAX_PLIES) return fail(SPRL_E_INVALID, "a line of %d actions is longer than a game (%d plies)", n_actions, G::MAX_PLIES);
+    const size_t n = (size_t)n_actions + 1;
+    DeviceBuf<int> dact, dbad; DeviceBuf<PosRec> drec; DeviceBuf<u64> dhist;
+    SPRL_CUDA(dact.alloc(n)); SPRL_CUDA(dbad.alloc(1)); SPRL_CUDA(drec.alloc(n)); SPRL_CUDA(dhist.alloc(n * 2 * G::W));
+    if (n_actions) SPRL_CUDA(cudaMemcpy(dact.p, h_actions, (size_t)n_actions * 4, cudaMemcpyHostToDevice));
+    k_env_line<G><<<1, 32>>>(n_actions, dact.p, drec.p, dhist.p, dbad.p);
+    SPRL_CUDA(cudaGetLastError());
+    int bad = -1;
+    SPRL_CUDA(cudaMemcpy(&bad, dbad.p, 4, cudaMemcpyDeviceToHost));
+    if (bad >= 0) return fail(SPRL_E_INVALID, "action %d (index %d of the line) is not legal in the position it is played in", h_actions[bad], bad);
+    std::vector<PosRec> rec(n);
+    SPRL_CUDA(cudaMemcpy(rec.data(), drec.p, n * sizeof(PosRec), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < n; ++k) {
+        if (h_cells) cells_from_rec<G>(rec[k], h_cells + k * G::CELLS);
+        if (h_player) h_player[k] = rec[k].player;
+        if (h_terminal) h_terminal[k] = rec[k].terminal;
+        if (h_winner) h_winner[k] = winner_code(rec[k].winner);
+        if (h_mask) mask_from_rec<G>(rec[k], h_mask + k * G::ACTIONS);
+    }
+    return SPRL_OK;
+}
+
+template <class G>
 static int env_perft_impl(int depth, uint64_t* count, float* elapsed_ms) {
     if (depth < 0 || depth >= 40) return fail(SPRL_E_INVALID, "perft depth %d out of range", depth);
     cudaEvent_t e0, e1;
@@ -486,6 +541,15 @@ int sprl_env_step(int device, int game, int64_t n, const int8_t* h_cells, const 
     case SPRL_GAME_C4: return env_step_impl<ConnectFour>(n, h_cells, h_player, h_action, h_next_cells, h_next_player, h_terminal, h_winner, h_mask);
     default: return fail(SPRL_E_INVALID, "sprl_env_step supports Othello and Connect Four (game %d needs its history)", game);
     }
+}
+
+int sprl_env_line(int device, int game, int32_t n_actions, const int32_t* h_actions, int8_t* h_cells, int8_t* h_player,
+                  int8_t* h_terminal, int8_t* h_winner, int8_t* h_mask) {
+    NvtxRange nvtx_range("sprl_env_line");
+    if (n_actions < 0 || (n_actions > 0 && !h_actions)) return fail(SPRL_E_INVALID, "sprl_env_line: negative length or null actions");
+    int rc = use_device(device);
+    if (rc) return rc;
+    DISPATCH_GAME(game, env_line_impl<G>(n_actions, h_actions, h_cells, h_player, h_terminal, h_winner, h_mask));
 }
 
 int sprl_env_rollout(int device, int game, uint64_t seed, uint64_t first_game, int64_t ngames,

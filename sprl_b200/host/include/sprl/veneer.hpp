@@ -70,25 +70,163 @@ template <int ACTION_SIZE> struct GameActionDist : std::array<float, ACTION_SIZE
     GameActionDist operator/(float rhs) const { GameActionDist r; const float inv = 1.0f / rhs; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = (*this)[i] * inv; return r; }
     GameActionDist operator*(float rhs) const { GameActionDist r; for (int i = 0; i < ACTION_SIZE; ++i) r[i] = (*this)[i] * rhs; return r; }
 };
-template <int BOARD_SIZE, int HISTORY_SIZE> struct GridState {
+// games/GameNode.hpp:26-32, games/GridState.hpp:17-47
+constexpr Player otherPlayer(Player player) { return player == Player::ZERO ? Player::ONE : (player == Player::ONE ? Player::ZERO : Player::NONE); }
+constexpr Piece otherPiece(Piece piece) { return piece == Piece::ZERO ? Piece::ONE : (piece == Piece::ONE ? Piece::ZERO : Piece::NONE); }
+constexpr Piece pieceFromPlayer(Player player) { return static_cast<Piece>(static_cast<int8_t>(player)); }
+constexpr Player playerFromPiece(Piece piece) { return static_cast<Player>(static_cast<int8_t>(piece)); }
+
+template <int BOARD_SIZE> using GridBoard = std::array<Piece, BOARD_SIZE>;
+
+// games/GridState.hpp:56-115: the boards a network sees -- history[0] is the current board, higher indices go back in time,
+// size() of them are valid -- and the player to move.
+template <int BOARD_SIZE, int HISTORY_SIZE> class GridState {
+public:
     static constexpr int BOARD = BOARD_SIZE, HISTORY = HISTORY_SIZE;
+    GridState() { for (auto& b : m_history) b.fill(Piece::NONE); }
+    GridState(std::array<GridBoard<BOARD_SIZE>, HISTORY_SIZE>&& history, int size, Player player)
+        : m_history(std::move(history)), m_size(size), m_player(player) {}
+    const std::array<GridBoard<BOARD_SIZE>, HISTORY_SIZE>& getHistory() const { return m_history; }
+    int size() const { return m_size; }
+    Player getPlayer() const { return m_player; }
+private:
+    std::array<GridBoard<BOARD_SIZE>, HISTORY_SIZE> m_history;
+    int m_size { 0 };
+    Player m_player { Player::NONE };
 };
-// games/GameNode.hpp:50-200: positions live on the device; on the host a game node is a tag that names the rules
-template <typename ImplNode, typename State, int ACTION_SIZE> struct GameNode {};
+
+// errors of the C ABI as exceptions
+class EngineError : public std::runtime_error {
+public:
+    EngineError(int code, const std::string& what) : std::runtime_error(what), code(code) {}
+    int code;
+};
+inline void check(int rc) {
+    if (rc != SPRL_OK) throw EngineError(rc, std::string("libsprl_b200: ") + sprl_last_error());
+}
+inline int currentDevice();
+struct RawNode {};                   // constructs a node without asking the device for the start position
+
+// games/GameNode.hpp:50-200 on the host: a node is a position the DEVICE computed.  The constructor asks for the start
+// position, getAddChild(action) for the position after the line of actions from the root to this node plus `action`
+// (sprl_env_line: one launch, the line is also Go's superko history) and caches the child like the reference; mask,
+// player, winner, terminal flag, rewards and the GridState of the last HISTORY boards are the reference's accessors.
+// An illegal action throws EngineError(SPRL_E_INVALID) where the reference asserts.
+template <typename ImplNode, typename State, int ACTION_SIZE>
+class GameNode {
+public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
+    static constexpr int BOARD_CELLS = State::BOARD;
+
+    GameNode() {
+        int8_t player = 0, terminal = 0, winner = -1;
+        std::array<int8_t, ACTION_SIZE> mask {};
+        check(sprl_env_line(currentDevice(), ImplNode::GAME, 0, nullptr, m_cells.data(), &player, &terminal, &winner, mask.data()));
+        fill(player, terminal, winner, mask.data());
+    }
+    explicit GameNode(RawNode) {}
+    virtual ~GameNode() {}
+
+    ImplNode* getParent() const { return m_parent; }
+
+    ImplNode* getAddChild(ActionIdx action) {
+        if (m_isTerminal) throw EngineError(SPRL_E_STATE, "getAddChild on a terminal node");
+        if (action < 0 || action >= ACTION_SIZE || !(m_actionMask[action] > 0.0f))
+            throw EngineError(SPRL_E_INVALID, "getAddChild: action " + std::to_string(action) + " is not legal here");
+        if (!m_children[action]) {
+            std::vector<int32_t> line;                                   // the actions from the root to the new child
+            for (const GameNode* n = this; n->m_parent; n = n->m_parent) line.push_back(n->m_action);
+            std::reverse(line.begin(), line.end());
+            line.push_back(action);
+            const size_t n = line.size() + 1;
+            std::vector<int8_t> cells(n * BOARD_CELLS), player(n), terminal(n), winner(n), mask(n * ACTION_SIZE);
+            check(sprl_env_line(currentDevice(), ImplNode::GAME, (int32_t)line.size(), line.data(), cells.data(), player.data(),
+                                terminal.data(), winner.data(), mask.data()));
+            auto child = std::make_unique<ImplNode>(RawNode {});
+            child->m_parent = static_cast<ImplNode*>(this);
+            child->m_action = action;
+            std::copy(cells.end() - BOARD_CELLS, cells.end(), child->m_cells.begin());
+            child->fill(player.back(), terminal.back(), winner.back(), mask.data() + (n - 1) * ACTION_SIZE);
+            m_children[action] = std::move(child);
+        }
+        return m_children[action].get();
+    }
+
+    void pruneChildrenExcept(ActionIdx action) {
+        for (ActionIdx i = 0; i < ACTION_SIZE; ++i)
+            if (i != action) m_children[i] = nullptr;
+    }
+
+    Player getPlayer() const { return m_player; }
+    Player getWinner() const { return m_winner; }
+    bool isTerminal() const { return m_isTerminal; }
+    const ActionDist& getActionMask() const { return m_actionMask; }
+
+    State getGameState() const {
+        std::array<GridBoard<State::BOARD>, State::HISTORY> history;
+        int size = 0;
+        for (const GameNode* n = this; n && size < State::HISTORY; n = n->m_parent, ++size)
+            for (int i = 0; i < State::BOARD; ++i) history[size][i] = static_cast<Piece>(n->m_cells[i]);
+        for (int t = size; t < State::HISTORY; ++t) history[t].fill(Piece::NONE);
+        return State(std::move(history), size, m_player);
+    }
+
+    std::array<Value, 2> getRewards() const {              // the reference's getRewardsImpl of all three games
+        if (m_winner == Player::ZERO) return { 1.0f, -1.0f };
+        if (m_winner == Player::ONE) return { -1.0f, 1.0f };
+        return { 0.0f, 0.0f };
+    }
+
+    std::string toString() const {
+        std::string out;
+        const int cols = ImplNode::COLS;
+        for (int i = 0; i < State::BOARD; ++i) {
+            out += m_cells[i] == 0 ? 'O' : (m_cells[i] == 1 ? 'X' : '.');
+            if ((i + 1) % cols == 0) out += '\n';
+        }
+        return out;
+    }
+
+    const std::array<int8_t, State::BOARD>& cells() const { return m_cells; }     // Piece encoding, row-major
+
+protected:
+    void fill(int8_t player, int8_t terminal, int8_t winner, const int8_t* mask) {
+        m_player = static_cast<Player>(player);
+        m_isTerminal = terminal != 0;
+        m_winner = static_cast<Player>(winner);
+        for (int a = 0; a < ACTION_SIZE; ++a) m_actionMask[a] = mask[a] ? 1.0f : 0.0f;
+    }
+    ImplNode* m_parent { nullptr };
+    std::array<std::unique_ptr<ImplNode>, ACTION_SIZE> m_children;
+    ActionIdx m_action { 0 };
+    ActionDist m_actionMask;
+    Player m_player { Player::ZERO };
+    Player m_winner { Player::NONE };
+    bool m_isTerminal { false };
+    std::array<int8_t, State::BOARD> m_cells {};
+};
 
 // ---- games: constants of games/*.hpp and tags selecting the device rules ----
 constexpr int OTH_BOARD_WIDTH = 8;
 constexpr int OTH_BOARD_SIZE = OTH_BOARD_WIDTH * OTH_BOARD_WIDTH;
 constexpr int OTH_ACTION_SIZE = OTH_BOARD_SIZE + 1;
 constexpr int OTH_HISTORY_SIZE = 1;
-struct OthelloNode : GameNode<OthelloNode, GridState<OTH_BOARD_SIZE, OTH_HISTORY_SIZE>, OTH_ACTION_SIZE> { static constexpr int GAME = SPRL_GAME_OTHELLO; };
+struct OthelloNode : GameNode<OthelloNode, GridState<OTH_BOARD_SIZE, OTH_HISTORY_SIZE>, OTH_ACTION_SIZE> {
+    using State = GridState<OTH_BOARD_SIZE, OTH_HISTORY_SIZE>;
+    using GameNode::GameNode;
+    static constexpr int GAME = SPRL_GAME_OTHELLO, COLS = OTH_BOARD_WIDTH;
+};
 
 constexpr int C4_NUM_ROWS = 6;
 constexpr int C4_NUM_COLS = 7;
 constexpr int C4_BOARD_SIZE = C4_NUM_ROWS * C4_NUM_COLS;
 constexpr int C4_ACTION_SIZE = C4_NUM_COLS;
 constexpr int C4_HISTORY_SIZE = 1;
-struct ConnectFourNode : GameNode<ConnectFourNode, GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> { static constexpr int GAME = SPRL_GAME_C4; };
+struct ConnectFourNode : GameNode<ConnectFourNode, GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> {
+    using State = GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>;
+    using GameNode::GameNode;
+    static constexpr int GAME = SPRL_GAME_C4, COLS = C4_NUM_COLS;
+};
 
 #ifndef SPRL_GO_BOARD_WIDTH
 #define SPRL_GO_BOARD_WIDTH 7                 // games/GoNode.hpp:16; 9 selects the 9x9 / komi 7.5 rules
@@ -97,7 +235,11 @@ constexpr int GO_BOARD_WIDTH = SPRL_GO_BOARD_WIDTH;
 constexpr int GO_BOARD_SIZE = GO_BOARD_WIDTH * GO_BOARD_WIDTH;
 constexpr int GO_ACTION_SIZE = GO_BOARD_SIZE + 1;
 constexpr int GO_HISTORY_SIZE = 8;
-struct GoNode : GameNode<GoNode, GridState<GO_BOARD_SIZE, GO_HISTORY_SIZE>, GO_ACTION_SIZE> { static constexpr int GAME = (GO_BOARD_WIDTH == 9) ? SPRL_GAME_GO9 : SPRL_GAME_GO7; };
+struct GoNode : GameNode<GoNode, GridState<GO_BOARD_SIZE, GO_HISTORY_SIZE>, GO_ACTION_SIZE> {
+    using State = GridState<GO_BOARD_SIZE, GO_HISTORY_SIZE>;
+    using GameNode::GameNode;
+    static constexpr int GAME = (GO_BOARD_WIDTH == 9) ? SPRL_GAME_GO9 : SPRL_GAME_GO7, COLS = GO_BOARD_WIDTH;
+};
 
 // ---- evaluators ----
 // The reference's INetwork::evaluate(states, masks) is a host call per leaf batch.  Here an
@@ -168,15 +310,6 @@ public:
 };
 
 // ---- engine handle -------------------------------------------------------------------------
-class EngineError : public std::runtime_error {
-public:
-    EngineError(int code, const std::string& what) : std::runtime_error(what), code(code) {}
-    int code;
-};
-
-inline void check(int rc) {
-    if (rc != SPRL_OK) throw EngineError(rc, std::string("libsprl_b200: ") + sprl_last_error());
-}
 
 // Run-wide knobs a reference main cannot express (it has no notion of a device).
 struct DeviceOptions {
@@ -204,6 +337,7 @@ inline DeviceOptions& deviceOptions() {
     }();
     return o;
 }
+inline int currentDevice() { return deviceOptions().device; }
 
 inline int initQCode(InitQ q) {
     return q == InitQ::PARENT ? SPRL_INITQ_PARENT : (q == InitQ::DROP_PARENT ? SPRL_INITQ_DROP_PARENT : SPRL_INITQ_ZERO);

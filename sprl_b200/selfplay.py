@@ -71,6 +71,20 @@ def env_step(game, cells, player, action, device=0):
     return out
 
 
+def env_line(game, actions, device=0):
+    """The positions along one line of play from the start position (a chain of GameNode::getAddChild calls,
+    games/GameNode.hpp:96-110): dict of cells [n+1, cells], player / terminal / winner [n+1], mask [n+1, A].  Every game
+    incl. Go; an illegal action raises SprlError."""
+    gi = capi.game_info(game)
+    actions = np.ascontiguousarray(actions, np.int32).reshape(-1)
+    n = actions.shape[0] + 1
+    out = dict(cells=np.zeros((n, gi.cells), np.int8), player=np.zeros(n, np.int8), terminal=np.zeros(n, np.int8),
+               winner=np.zeros(n, np.int8), mask=np.zeros((n, gi.actions), np.int8))
+    capi.check(capi.load().sprl_env_line(device, game, n - 1, _ptr(actions), _ptr(out["cells"]), _ptr(out["player"]),
+                                         _ptr(out["terminal"]), _ptr(out["winner"]), _ptr(out["mask"])))
+    return out
+
+
 # ---------------------------------------------------------------------- the engine
 class Engine:
     """One self-play engine = `num_slots` concurrent trees on one GPU."""

@@ -89,6 +89,30 @@ def test_rollout_large_sweep_properties():
     assert set(np.unique(r["final_winner"])) <= {-1, 0, 1}
 
 
+@pytest.mark.parametrize("game,ngames", [(capi.GAME_OTHELLO, 40), (capi.GAME_C4, 60), (capi.GAME_GO7, 12), (capi.GAME_GO9, 4)])
+def test_env_line_replays_rollouts_position_by_position(game, ngames):
+    """sprl_env_line (a chain of GameNode::getAddChild calls from the start position) against the roll-out traces, which the
+    tests above pin to the oracle state by state: every position of every game -- cells, player, legal mask, terminal flag,
+    winner -- for all four games (Go: the line is the superko history); an illegal action is refused."""
+    r = SP.env_rollout(game, 5, 100, ngames, record=True)
+    at = 0
+    for g in range(ngames):
+        n = int(r["game_steps"][g])
+        sl = slice(at, at + n)
+        line = SP.env_line(game, r["action"][sl][:-1])
+        for k in ("cells", "player", "mask", "terminal", "winner"):
+            assert np.array_equal(line[k], r[k][sl]), (g, k)
+        at += n
+    gi = capi.game_info(game)
+    first = SP.env_line(game, [])
+    illegal = [a for a in range(gi.actions) if not first["mask"][0][a]]
+    if illegal:
+        with pytest.raises(capi.SprlError):
+            SP.env_line(game, [illegal[0]])
+    with pytest.raises(capi.SprlError):
+        SP.env_line(game, [gi.actions])
+
+
 def test_env_step_matches_oracle_positions():
     for game in (O.OG_OTHELLO, O.OG_C4):
         ref = O.rollout(game, 3, 0, 200)

@@ -132,3 +132,20 @@ def test_veneer_ucttree_move_loop_matches_the_reference(name, tmp_path):
     got = read_treewalk(out)
     G.assert_trace_equal(ref, got, ["game_moves", "game_winner", "move_N", "move_W", "move_P", "move_root_N", "move_root_W",
                                     "move_action", "move_traversals", "move_player"])
+
+
+def test_host_gamenode_and_gridstate_follow_the_device_rules():
+    """The veneer's GameNode / GridState (games/GameNode.hpp:50-200, games/GridState.hpp:56-115) node by node against one
+    sprl_env_line call per game, for Othello, Connect Four and Go: tests/hostcheck/gamenode.cpp."""
+    r = subprocess.run([binary("gamenode", "check"), "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "gamenode ok" in r.stdout
+
+
+def test_reference_unit_test_unchanged_passes_against_the_drop_in():
+    """/root/reference/cpp/tests/test_c4.cpp -- the reference's only unit test (a horizontal Connect Four win through
+    ConnectFourNode::getAddChild / isTerminal / getWinner / getParent / getPlayer / getRewards) -- compiled UNCHANGED against
+    this tree's headers (`make dropin`; Catch2's two macros come from tests/hostcheck/catch2) and run on the GPU."""
+    r = subprocess.run([binary("ref_test_c4", "dropin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "passed: Handles a basic horizontal victory" in r.stdout and "all 1 test case(s) passed" in r.stdout
