@@ -88,6 +88,64 @@ public:
     }
 
     void setRowCount(const uint32_t* d_rows) override { m_dRows = d_rows; }
+
+    // INetwork::evaluate for host callers (networks/GridNetwork.hpp:62-145 of the reference): the states are embedded as the
+    // planes the search kernel writes (2t / 2t+1 = the mover's / the opponent's stones t plies back, last plane = player
+    // ZERO to move, :72-97), the forward runs on the GPU, and exp / mask / normalise (uniform over the legal actions when
+    // everything underflows, :107-142) follow on the host with GameActionDist's arithmetic.
+    using ActionDist = GameActionDist<ACTION_SIZE>;
+    std::vector<std::pair<ActionDist, Value>> evaluate(const std::vector<State>& states, const std::vector<ActionDist>& masks) override {
+        std::vector<std::pair<ActionDist, Value>> results;
+        const int64_t n = (int64_t)states.size();
+        if (n == 0) return results;
+        constexpr int CELLS = NUM_ROWS * NUM_COLS, PLANES = 2 * HISTORY_SIZE + 1;
+        if (!m_model) throw EngineError(SPRL_E_STATE, "GridNetwork::evaluate: no model is loaded");
+        if (m_planes == 0 && attach(currentDevice(), PLANES, NUM_ROWS, NUM_COLS, ACTION_SIZE) != 0)
+            throw EngineError(SPRL_E_STATE, "GridNetwork::evaluate: the model could not be moved to the GPU");
+        std::vector<float> planes((size_t)n * PLANES * CELLS, 0.0f);
+        for (int64_t b = 0; b < n; ++b) {
+            const State& st = states[(size_t)b];
+            const Piece mine = pieceFromPlayer(st.getPlayer()), theirs = otherPiece(mine);
+            float* p = planes.data() + (size_t)b * PLANES * CELLS;
+            for (int t = 0; t < st.size() && t < HISTORY_SIZE; ++t)
+                for (int c = 0; c < CELLS; ++c) {
+                    p[(2 * t) * CELLS + c] = st.getHistory()[t][c] == mine ? 1.0f : 0.0f;
+                    p[(2 * t + 1) * CELLS + c] = st.getHistory()[t][c] == theirs ? 1.0f : 0.0f;
+                }
+            if (st.getPlayer() == Player::ZERO) for (int c = 0; c < CELLS; ++c) p[(PLANES - 1) * CELLS + c] = 1.0f;
+        }
+        auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(m_device);
+        c10::cuda::CUDAStream stream = c10::cuda::getCurrentCUDAStream(m_device.index());
+        c10::cuda::CUDAStreamGuard guard(stream);
+        torch::Tensor in = torch::from_blob(planes.data(), { n, PLANES, NUM_ROWS, NUM_COLS }, torch::kFloat32).to(m_device);
+        torch::Tensor logits = torch::empty({ n, ACTION_SIZE }, opts), value = torch::empty({ n }, opts);
+        const uint32_t* saved = m_dRows;
+        m_dRows = nullptr;                                   // the whole batch, not the engine's row count
+        const int rc = forward(in.data_ptr<float>(), n, logits.data_ptr<float>(), value.data_ptr<float>(), stream.stream());
+        m_dRows = saved;
+        if (rc != 0) throw EngineError(rc, std::string("GridNetwork::evaluate: ") + sprl_last_error());
+        const torch::Tensor hl = logits.cpu(), hv = value.cpu();
+        check(checkStatus());
+        results.reserve((size_t)n);
+        for (int64_t b = 0; b < n; ++b) {
+            ActionDist policy;
+            for (int i = 0; i < ACTION_SIZE; ++i) policy[i] = hl.data_ptr<float>()[b * ACTION_SIZE + i];
+            policy = policy.exp();
+            int numLegal = 0;
+            for (int i = 0; i < ACTION_SIZE; ++i) {
+                if (masks[(size_t)b][i] == 0.0f) policy[i] = 0.0f; else ++numLegal;
+            }
+            const float sum = policy.sum();
+            if (sum == 0.0f) {
+                for (int i = 0; i < ACTION_SIZE; ++i) policy[i] = masks[(size_t)b][i] == 0.0f ? 0.0f : 1.0f / numLegal;
+            } else {
+                policy = policy / sum;
+            }
+            results.emplace_back(policy, hv.data_ptr<float>()[b]);
+        }
+        this->addEvals((uint64_t)n);
+        return results;
+    }
     int checkStatus() override { return m_evalnet ? sprl_evalnet_status(m_evalnet, nullptr) : 0; }
 
 private:

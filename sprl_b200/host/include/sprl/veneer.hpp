@@ -10,7 +10,7 @@
 //   SPRL::ISymmetrizer<State,A>, D4GridSymmetrizer,   symmetry/*.hpp
 //         ConnectFourSymmetrizer
 //   SPRL::InitQ                                       uct/UCTNode.hpp:24-28
-//   SPRL::runIteration<Impl,State,A>(...)             selfplay/SelfPlay.hpp:203-208
+//   SPRL::runIteration<Impl,State,A>(...), selfPlay   selfplay/SelfPlay.hpp:203-208, :50-192
 //   SPRL::waitModelPath, SPRL::runWorker<NN,Impl,R,C,H,A>(...)   selfplay/GridWorker.hpp:35-55,84-91
 //   SPRL::playMatch<Impl,State,A>(...)                the game loop of Evaluate.cpp:93-157 (UCTNetworkAgent::act /
 //                                                     opponentAct inside playGame), all games concurrently
@@ -249,7 +249,14 @@ template <typename State, int ACTION_SIZE>
 class INetwork {
 public:
     virtual ~INetwork() = default;
+    using ActionDist = GameActionDist<ACTION_SIZE>;
     virtual int evaluatorKind() const = 0;                       // SPRL_EVAL_*
+    // networks/INetwork.hpp:25-27 for host callers: prior over the legal actions and value of every state.  The engine never
+    // calls this (its leaves are evaluated from device buffers, see forward()); evaluators that exist only on the device
+    // (the test HashNetwork) do not offer it.
+    virtual std::vector<std::pair<ActionDist, Value>> evaluate(const std::vector<State>& /*states*/, const std::vector<ActionDist>& /*masks*/) {
+        throw EngineError(SPRL_E_STATE, "this evaluator has no host-side evaluate()");
+    }
     // External networks only.  prepare(): allocate the device buffers of a leaf batch
     // (planes [batch, planes, rows, cols], logits [batch, actions], value [batch]) on `device`.
     // forward(): run the network on d_in and leave its outputs in d_logits / d_value, on `stream`.
@@ -274,7 +281,16 @@ protected:
 template <typename State, int ACTION_SIZE>
 class RandomNetwork : public INetwork<State, ACTION_SIZE> {       // networks/RandomNetwork.hpp
 public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
     int evaluatorKind() const override { return SPRL_EVAL_UNIFORM; }
+    // networks/RandomNetwork.hpp:21-49: uniform over the legal actions, value 0
+    std::vector<std::pair<ActionDist, Value>> evaluate(const std::vector<State>& states, const std::vector<ActionDist>& masks) override {
+        std::vector<std::pair<ActionDist, Value>> out;
+        out.reserve(states.size());
+        for (size_t b = 0; b < states.size(); ++b) out.emplace_back(masks[b] / masks[b].sum(), 0.0f);
+        this->addEvals(states.size());
+        return out;
+    }
 };
 
 // Deterministic test evaluator (parity runs), evaluated on the device.
@@ -284,29 +300,86 @@ public:
     int evaluatorKind() const override { return SPRL_EVAL_HASHNET; }
 };
 
-// ---- symmetrizers: presence selects the game's symmetry group on the device ----
+// ---- symmetrizers (symmetry/ISymmetrizer.hpp:17-57) ----
+// Inside the engine the PRESENCE of a symmetrizer selects the game's symmetry group on the device (leaf encoding, inverse
+// mapping of the policies, the symmetric samples).  The host functions below are the reference's interface for callers that
+// hold a GridState or an action distribution themselves; they use the same maps as the device (new[f_s(i)] = old[i]) and
+// tests/hostcheck/gamenode.cpp checks them against the device's symmetric samples.
 template <typename State, int ACTION_SIZE>
 class ISymmetrizer {
 public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
     virtual ~ISymmetrizer() = default;
     virtual int numSymmetries() const = 0;
     virtual SymmetryIdx inverseSymmetry(SymmetryIdx symmetry) const = 0;
+    virtual std::vector<State> symmetrizeState(const State& state, const std::vector<SymmetryIdx>& symmetries) const = 0;
+    virtual std::vector<ActionDist> symmetrizeActionDist(const ActionDist& actionDist, const std::vector<SymmetryIdx>& symmetries) const = 0;
+};
+
+// the board maps shared by a symmetrizer's two functions: cellTo(s, i) = f_s(i), actionTo(s, a)
+template <typename Derived, typename State, int ACTION_SIZE>
+class GridSymmetrizerBase : public ISymmetrizer<State, ACTION_SIZE> {
+public:
+    using ActionDist = GameActionDist<ACTION_SIZE>;
+    std::vector<State> symmetrizeState(const State& state, const std::vector<SymmetryIdx>& symmetries) const override {
+        std::vector<State> out;
+        out.reserve(symmetries.size());
+        for (SymmetryIdx s : symmetries) {
+            std::array<GridBoard<State::BOARD>, State::HISTORY> history;
+            for (int t = 0; t < State::HISTORY; ++t) {
+                history[t].fill(Piece::NONE);
+                if (t < state.size())
+                    for (int i = 0; i < State::BOARD; ++i) history[t][Derived::cellTo(s, i)] = state.getHistory()[t][i];
+            }
+            out.emplace_back(std::move(history), state.size(), state.getPlayer());
+        }
+        return out;
+    }
+    std::vector<ActionDist> symmetrizeActionDist(const ActionDist& actionDist, const std::vector<SymmetryIdx>& symmetries) const override {
+        std::vector<ActionDist> out;
+        out.reserve(symmetries.size());
+        for (SymmetryIdx s : symmetries) {
+            ActionDist d;
+            for (int a = 0; a < ACTION_SIZE; ++a) d[Derived::actionTo(s, a)] = actionDist[a];
+            out.push_back(d);
+        }
+        return out;
+    }
 };
 
 template <int BOARD_WIDTH, int HISTORY_SIZE>
-class D4GridSymmetrizer : public ISymmetrizer<GridState<BOARD_WIDTH * BOARD_WIDTH, HISTORY_SIZE>, BOARD_WIDTH * BOARD_WIDTH + 1> {
+class D4GridSymmetrizer
+    : public GridSymmetrizerBase<D4GridSymmetrizer<BOARD_WIDTH, HISTORY_SIZE>, GridState<BOARD_WIDTH * BOARD_WIDTH, HISTORY_SIZE>, BOARD_WIDTH * BOARD_WIDTH + 1> {
 public:
     int numSymmetries() const override { return 8; }
     SymmetryIdx inverseSymmetry(SymmetryIdx s) const override {
         static constexpr SymmetryIdx inv[8] = { 0, 3, 2, 1, 4, 5, 6, 7 };     // symmetry/D4GridSymmetrizer.hpp:47-50
         return inv[s];
     }
+    // symmetry/D4GridSymmetrizer.hpp:106-117 as one table: (r, c) goes to
+    // 0 (r,c)  1 (c,w-1-r)  2 (w-1-r,w-1-c)  3 (w-1-c,r)  4 (r,w-1-c)  5 (w-1-c,w-1-r)  6 (w-1-r,c)  7 (c,r)
+    static int cellTo(SymmetryIdx s, int from) {
+        const int w = BOARD_WIDTH, r = from / w, c = from % w, x = w - 1;
+        switch (s) {
+        case 1: return c * w + (x - r);
+        case 2: return (x - r) * w + (x - c);
+        case 3: return (x - c) * w + r;
+        case 4: return r * w + (x - c);
+        case 5: return (x - c) * w + (x - r);
+        case 6: return (x - r) * w + c;
+        case 7: return c * w + r;
+        default: return from;
+        }
+    }
+    static int actionTo(SymmetryIdx s, int a) { return a == BOARD_WIDTH * BOARD_WIDTH ? a : cellTo(s, a); }     // the pass stays
 };
 
-class ConnectFourSymmetrizer : public ISymmetrizer<GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> {
+class ConnectFourSymmetrizer : public GridSymmetrizerBase<ConnectFourSymmetrizer, GridState<C4_BOARD_SIZE, C4_HISTORY_SIZE>, C4_ACTION_SIZE> {
 public:
     int numSymmetries() const override { return 2; }
     SymmetryIdx inverseSymmetry(SymmetryIdx s) const override { return s; }
+    static int cellTo(SymmetryIdx s, int from) { return s == 1 ? (from / C4_NUM_COLS) * C4_NUM_COLS + (C4_NUM_COLS - 1 - from % C4_NUM_COLS) : from; }
+    static int actionTo(SymmetryIdx s, int a) { return s == 1 ? C4_NUM_COLS - 1 - a : a; }
 };
 
 // ---- engine handle -------------------------------------------------------------------------
@@ -401,6 +474,45 @@ runIteration(INetwork<State, ACTION_SIZE>* network, int numGames,
     network->addEvals(st.evals);
     std::cout << numGames << " games played, " << nSamples << " states collected.\n";
     return { std::move(states), std::move(dists), std::move(outcomes) };
+}
+
+// ---- selfPlay (selfplay/SelfPlay.hpp:50-192) ---------------------------------------------------
+// ONE game from the start position in the reference's own types: the symmetrised GridStates over time, the symmetrised
+// action distributions UCT produced and the outcome for the player to move at each of them -- decoded from the embedded
+// planes of a one-game runIteration (plane 2t / 2t+1 = the mover's / the opponent's stones t plies back, last plane =
+// "player ZERO to move", selfplay/GridWorker.hpp:146-171).  Successive calls draw from successive game streams.
+template <typename ImplNode, typename State, int ACTION_SIZE>
+std::tuple<std::vector<State>, std::vector<GameActionDist<ACTION_SIZE>>, std::vector<Value>>
+selfPlay(std::unique_ptr<GameNode<ImplNode, State, ACTION_SIZE>> rootNode,
+         INetwork<State, ACTION_SIZE>* network,
+         int numTraversals, int maxBatchSize, int maxQueueSize,
+         float dirEps, float dirAlpha, InitQ initQMethod,
+         ISymmetrizer<State, ACTION_SIZE>* symmetrizer, bool addNoise = true) {
+    if (!rootNode || rootNode->getParent() != nullptr)
+        throw EngineError(SPRL_E_INVALID, "selfPlay: the engine plays from the start position (pass a fresh root node)");
+    DeviceOptions& opt = deviceOptions();
+    auto [planes, flat, outcomes] = runIteration<ImplNode, State, ACTION_SIZE>(network, 1, numTraversals, maxBatchSize, maxQueueSize,
+                                                                              dirEps, dirAlpha, initQMethod, symmetrizer, addNoise);
+    opt.firstGame += opt.gameStride;
+    const int nsym = symmetrizer ? symmetrizer->numSymmetries() : 1;
+    const size_t n = outcomes.size(), row = (size_t)(2 * State::HISTORY + 1) * State::BOARD;
+    std::vector<State> states;
+    std::vector<GameActionDist<ACTION_SIZE>> distributions(n);
+    states.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = planes.data() + i * row;
+        const Player player = p[(size_t)2 * State::HISTORY * State::BOARD] > 0.5f ? Player::ZERO : Player::ONE;
+        const Piece mine = pieceFromPlayer(player), theirs = otherPiece(mine);
+        const int size = (int)std::min<size_t>(i / nsym + 1, State::HISTORY);
+        std::array<GridBoard<State::BOARD>, State::HISTORY> history;
+        for (int t = 0; t < State::HISTORY; ++t)
+            for (int c = 0; c < State::BOARD; ++c)
+                history[t][c] = (t < size && p[(size_t)(2 * t) * State::BOARD + c] > 0.5f) ? mine
+                              : ((t < size && p[(size_t)(2 * t + 1) * State::BOARD + c] > 0.5f) ? theirs : Piece::NONE);
+        states.emplace_back(std::move(history), size, player);
+        for (int a = 0; a < ACTION_SIZE; ++a) distributions[i][a] = flat[i * ACTION_SIZE + a];
+    }
+    return { std::move(states), std::move(distributions), std::move(outcomes) };
 }
 
 // ---- playMatch: the loop of Evaluate.cpp:93-157 ------------------------------------------------

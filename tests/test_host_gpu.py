@@ -149,3 +149,30 @@ def test_reference_unit_test_unchanged_passes_against_the_drop_in():
     r = subprocess.run([binary("ref_test_c4", "dropin")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "passed: Handles a basic horizontal victory" in r.stdout and "all 1 test case(s) passed" in r.stdout
+
+
+def test_host_inetwork_evaluate_matches_the_module(tmp_path):
+    """INetwork::evaluate(states, masks) for host callers (networks/INetwork.hpp:25-27): the veneer's GridNetwork embeds
+    GridStates, runs the traced module on the GPU and applies the reference's exp / mask / normalise on the host
+    (networks/GridNetwork.hpp:72-142); tests/hostcheck/netcheck.cpp evaluates 300 positions of random Othello games, PyTorch
+    recomputes them from the same module on the CPU.  RandomNetwork: uniform over the legal actions."""
+    import torch
+    from sprl_b200.network import make_network, trace_network
+    net = make_network("othello", 3)
+    pt = str(tmp_path / "net.pt")
+    trace_network(net, "cpu").save(pt)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([binary("netcheck", "check"), pt, "300", "11", prefix], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert "300 + 300 evaluations counted" in r.stdout
+    cells, player, mask, policy, value, uniform = (np.load(prefix + f"_{k}.npy") for k in ("cells", "player", "mask", "policy", "value", "uniform"))
+    mine = (cells == player[:, None]).astype(np.float32).reshape(-1, 8, 8)
+    theirs = (cells == (1 - player)[:, None]).astype(np.float32).reshape(-1, 8, 8)
+    turn = np.broadcast_to((player == 0).astype(np.float32)[:, None, None], mine.shape)
+    with torch.no_grad():
+        logits, v = net(torch.from_numpy(np.stack([mine, theirs, turn], 1).copy()))
+    want = np.exp(logits.numpy()) * mask
+    want /= want.sum(1, keepdims=True)
+    assert np.abs(policy - want).max() <= 1e-6 and np.abs(value - v.numpy().reshape(-1)).max() <= 1e-6
+    assert np.allclose(policy.sum(1), 1.0, atol=1e-6) and not (policy[mask == 0] != 0).any()
+    assert np.allclose(uniform, mask / mask.sum(1, keepdims=True), atol=1e-7)
