@@ -3,4 +3,5 @@
 #ifndef SPRL_B200_COMPAT_EVALUATE_PLAY_HPP
 #define SPRL_B200_COMPAT_EVALUATE_PLAY_HPP
 #include "../sprl/veneer.hpp"
+#include "../utils/Timer.hpp"     // as cpp/src/evaluate/play.hpp:8 does; Time.cpp relies on it
 #endif

@@ -176,3 +176,42 @@ def test_host_inetwork_evaluate_matches_the_module(tmp_path):
     assert np.abs(policy - want).max() <= 1e-6 and np.abs(value - v.numpy().reshape(-1)).max() <= 1e-6
     assert np.allclose(policy.sum(1), 1.0, atol=1e-6) and not (policy[mask == 0] != 0).any()
     assert np.allclose(uniform, mask / mask.sum(1, keepdims=True), atol=1e-7)
+
+
+def test_reference_time_main_unchanged_plays_the_engines_game(tmp_path):
+    """/root/reference/cpp/src/Time.cpp -- a Connect Four game driven by hand through UCTTree::searchAndGetLeaves /
+    evaluateAndBackpropLeaves / getDecisionNode()->getEdgeStatistics() / advanceDecision, GameNode::getAddChild / toString
+    and a GridNetwork -- compiled UNCHANGED against this tree's headers (`make dropin` -> bin/ref_Time).  Its printed actions
+    must be the game the step-wise C ABI plays from Python with the same network, seed and stream (same kernels, so the
+    same bits), and its last printed board must be that game's final position."""
+    import re
+    from sprl_b200.evalnet import EvalNet
+    from sprl_b200.network import make_network, trace_network
+    net = make_network("c4", 5)
+    pt = str(tmp_path / "c4.pt")
+    trace_network(net, "cpu").save(pt)
+    sims, b, q, seed = 96, 8, 4, 21
+    r = subprocess.run([binary("ref_Time", "dropin"), pt, str(sims), str(b), str(q)], env=dict(os.environ, SPRL_SEED=str(seed)),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    ref_actions = [int(x) for x in re.findall(r"^Action: (\d+)$", r.stdout, re.M)]
+    assert len(ref_actions) >= 7 and "Total time:" in r.stdout
+    with SP.Engine(capi.GAME_C4, capi.EVAL_EXTERNAL, seed=seed, sims=sims, max_batch=b, max_queue=q, dir_eps=0.25, dir_alpha=0.3,
+                   add_noise=0, use_sym=0, init_q=capi.INITQ_PARENT, u_weight=1.0,        # searchAndGetLeaves' default uWeight (uct/UCTTree.hpp:76-80)
+                   num_slots=1, max_games=1) as eng:
+        eng.attach_evalnet(EvalNet(net, device=0, rows=6, cols=7), use_cuda_graph=False)
+        eng.begin_trees(1)
+        actions = []
+        while True:
+            st = eng.root_stats()
+            if st["terminal"][0]:
+                break
+            eng.search(sims)
+            action = int(np.argmax(eng.root_stats()["N"][0]))           # std::max_element: the first of the most visited
+            actions.append(action)
+            eng.advance([action])
+    assert actions == ref_actions
+    line = SP.env_line(capi.GAME_C4, actions)
+    last = line["cells"][-1].reshape(6, 7)
+    board = "\n".join("".join("O" if v == 0 else ("X" if v == 1 else ".") for v in row) for row in last)
+    assert board in r.stdout.replace(" ", "")
